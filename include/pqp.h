@@ -1,0 +1,212 @@
+/*
+ * pqp.h — C ABI of the batched path-QP solver (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the solve path of LiJiangnanBit/path_optimizer_2:
+ *
+ *   reference interface being replaced                       | entry point here
+ *   ---------------------------------------------------------+----------------------------
+ *   BaseSolver::BaseSolver            base_solver.cpp:15-39   | pqp_create (+ host packer)
+ *   OsqpEigen settings                base_solver.cpp:59-62   | pqp_params / pqp_default_params
+ *   BaseSolver::solve                 base_solver.cpp:56-95   | pqp_solve / pqp_solve_device
+ *     setCost / setConstraints        base_solver.cpp:119-261 |   (assembled inside the kernel)
+ *     OsqpEigen initSolver + solve    base_solver.cpp:87-88   |   (ADMM inside the kernel)
+ *   BaseSolver::updateProblem...Solve base_solver.cpp:97-117  | pqp_resolve / pqp_resolve_device
+ *   BaseSolver::getOptimizedPath      base_solver.cpp:263-288 | pqp_frenet_to_cartesian
+ *   ~BaseSolver (OSQP workspace)      base_solver.hpp:62      | pqp_destroy
+ *
+ * Plain C: pointers, sizes, POD structs. No C++ / torch types cross this boundary and
+ * nothing here throws. Every function returns 0 on success or a negative PQP_E_* code;
+ * pqp_last_error() gives the text. There is NO CPU fallback: without a CUDA device
+ * pqp_create fails with PQP_E_NO_DEVICE.
+ *
+ * Problem: n knots, p "precise" knots (p == n unless the
+ * reference's rough_constraints_far_away flag is on),
+ *   variables  nv = 3n + (n-1) + (p+n)     [l,psi,kappa]*n, u*(n-1), slacks
+ *   rows       m  = 3n + n + 2p + (n-p) + 2
+ */
+#ifndef PQP_H_
+#define PQP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQP_VERSION 1
+
+/* per-instance solver status (mirrors the OSQP status the reference sees through osqp-eigen) */
+enum {
+    PQP_SOLVED = 0,
+    PQP_MAX_ITER_REACHED = 1,
+    PQP_PRIMAL_INFEASIBLE = 2,
+    PQP_DUAL_INFEASIBLE = 3,
+    PQP_SOLVED_INACCURATE = 4,
+    PQP_PRIMAL_INFEASIBLE_INACCURATE = 5,
+    PQP_DUAL_INFEASIBLE_INACCURATE = 6,
+    PQP_NUMERICAL_ERROR = 7,
+    PQP_UNSOLVED = 10
+};
+
+/* API error codes (function return values) */
+enum {
+    PQP_OK = 0,
+    PQP_E_INVALID = -1,    /* bad argument (null pointer, n < 2, n > n_max, batch > batch_max ...) */
+    PQP_E_NO_DEVICE = -2,  /* no CUDA device / wrong architecture */
+    PQP_E_CUDA = -3,       /* a CUDA runtime call failed; see pqp_last_error */
+    PQP_E_STATE = -4       /* resolve called before solve, etc. */
+};
+
+/* Field order inside one instance's knot block (doubles, each field n_max long). */
+enum {
+    PQP_F_S = 0,      /* reference arc length s_i                      (base_solver.cpp:174)        */
+    PQP_F_KREF = 1,   /* reference curvature k_ref,i                   (base_solver.cpp:182)        */
+    PQP_F_L = 2,      /* linearisation point l_i      = input_path[i].l          (:166-171)         */
+    PQP_F_PSI = 3,    /* linearisation point psi_i    = input_path[i].d_heading                     */
+    PQP_F_K = 4,      /* linearisation point k_i      = input_path[i].k                             */
+    PQP_F_B0_LB = 5,  /* row-0 clearance: front.lb (i<p) or center.lb (i>=p)  (:236,243)            */
+    PQP_F_B0_UB = 6,  /*                  front.ub        center.ub                                 */
+    PQP_F_B1_LB = 7,  /* row-1 clearance: rear.lb  (i<p), ignored for i>=p    (:237)                */
+    PQP_F_B1_UB = 8,
+    PQP_NFIELDS = 9
+};
+
+/* Per-instance scalar block (doubles). */
+enum {
+    PQP_I_L0 = 0,        /* vehicle_state.getInitError()[0]      (base_solver.cpp:217) */
+    PQP_I_PSI0 = 1,      /* vehicle_state.getInitError()[1]                            */
+    PQP_I_K0 = 2,        /* vehicle_state.getStartState().k      (:218)                */
+    PQP_I_EPSI_LO = 3,   /* end-heading row lower bound (-1e30 when unconstrained, :252-259) */
+    PQP_I_EPSI_HI = 4,
+    PQP_NINST = 5
+};
+
+/* Problem constants + OSQP settings. Defaults = reference flag defaults
+ * (planning_flags.cpp:16-22,95) + hard-coded weights (base_solver.cpp:123-126) +
+ * OSQP 0.6.x defaults with the reference's eps override (base_solver.cpp:61-62). */
+typedef struct pqp_params {
+    /* vehicle / formulation */
+    double front_length;            /* 3.9   */
+    double rear_length;             /* -1.0  */
+    double wheel_base;              /* 2.5   */
+    double max_steering_angle;      /* 35 deg in rad */
+    double expected_safety_margin;  /* 0.6   */
+    double weight_l;                /* 0     */
+    double weight_kappa;            /* 20    */
+    double weight_dkappa;           /* 100   */
+    double weight_slack;            /* 10    */
+    double end_l_lb;                /* -1.0  (base_solver.cpp:250) */
+    double end_l_ub;                /* +1.0  */
+    /* OSQP settings */
+    double rho;                     /* 0.1   */
+    double sigma;                   /* 1e-6  */
+    double alpha;                   /* 1.6   */
+    double eps_abs;                 /* 2e-3  */
+    double eps_rel;                 /* 2e-3  */
+    double eps_prim_inf;            /* 1e-4  */
+    double eps_dual_inf;            /* 1e-4  */
+    double adaptive_rho_tolerance;  /* 5     */
+    int32_t max_iter;               /* 4000  */
+    int32_t check_termination;      /* 25    */
+    int32_t scaling;                /* 10 Ruiz passes */
+    int32_t adaptive_rho;           /* 1     */
+    int32_t adaptive_rho_interval;  /* 25: fixed; OSQP's default 0 = wall-clock rule, not reproducible */
+    int32_t reserved;
+} pqp_params;
+
+/* Batch input. All pointers are HOST pointers for pqp_solve/pqp_resolve and DEVICE
+ * pointers for the *_device variants. Layout is instance-major so that one instance's
+ * knot block is one contiguous 9*n_max*8-byte span (one TMA bulk copy per instance):
+ *   knots[(b*PQP_NFIELDS + f)*n_max + i], inst[b*PQP_NINST + j], n[b], p[b].
+ * n_max must equal the handle's n_max. Entries i >= n[b] are ignored. */
+typedef struct pqp_batch_in {
+    int32_t batch;
+    int32_t n_max;
+    const double *knots;
+    const double *inst;
+    const int32_t *n;
+    const int32_t *p;   /* may be NULL: p[b] = n[b] */
+} pqp_batch_in;
+
+/* Batch output (caller-owned). sol is mandatory, the rest may be NULL.
+ *   sol[(b*4 + f)*n_max + i], f = 0:l 1:psi 2:kappa 3:u(=d_k, i<n-1)   (base_solver.cpp:270-281)
+ *   cost[b] = 0.5 x'Px, status[b] = PQP_* status, iters[b] = ADMM iterations
+ * Debug/parity outputs in the reference's own index order (Appendix A.1/A.3):
+ *   x_full[b*nv_max + j], y_full[b*m_max + r], z_full[b*m_max + r],
+ *   nv_max = 6*n_max - 1, m_max = 6*n_max + 2. */
+typedef struct pqp_batch_out {
+    double *sol;
+    double *cost;
+    int32_t *status;
+    int32_t *iters;
+    double *x_full;
+    double *y_full;
+    double *z_full;
+    double *info;      /* optional [b*PQP_NINFO + k]: see PQP_INFO_* */
+} pqp_batch_out;
+
+enum {
+    PQP_INFO_PRI_RES = 0,
+    PQP_INFO_DUA_RES = 1,
+    PQP_INFO_RHO = 2,
+    PQP_INFO_RHO_UPDATES = 3,
+    PQP_NINFO = 4
+};
+
+typedef struct pqp_handle pqp_handle;
+
+/* Fill *params with the defaults listed above. */
+int pqp_default_params(pqp_params *params);
+
+/* Create a solver bound to CUDA device `device` able to hold `batch_max` instances of up
+ * to `n_max` knots (2 <= n_max <= 256). Owns device buffers for inputs, outputs and the
+ * per-instance warm state (scaled x, z, y and rho; the OSQP workspace of
+ * base_solver.hpp:62). */
+int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32_t device,
+               pqp_handle **out);
+int pqp_destroy(pqp_handle *h);
+
+/* Cold solve of in->batch instances (BaseSolver::solve). Host buffers; H2D, kernel, D2H. */
+int pqp_solve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out);
+
+/* Warm re-solve (BaseSolver::updateProblemFormulationAndSolve): `in` carries the new
+ * linearisation point in its L/PSI/K fields (the reference passes the previous result,
+ * path_optimizer.cpp:153). If in == NULL the previous solution held on the device is
+ * used as the new linearisation point (no H2D). Warm x,z,y,rho persist per instance. */
+int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out);
+
+/* Same, with DEVICE pointers and the caller's stream (a cudaStream_t passed as void*,
+ * NULL = default stream). Asynchronous: no host synchronisation inside. */
+int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
+                     void *stream);
+int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
+                       void *stream);
+
+/* BaseSolver::getOptimizedPath (base_solver.cpp:263-288) for a batch, FP64, on device
+ * pointers: ref_xyh[(b*3+f)*n_max+i] f=0:x 1:y 2:heading of the reference states;
+ * sol as produced above; out_xyh same layout as ref_xyh (x, y, heading of the result). */
+int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *n,
+                                   const double *ref_xyh, const double *sol,
+                                   double *out_xyh, void *stream);
+int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n,
+                            const double *ref_xyh, const double *sol, double *out_xyh);
+
+/* Device time (ms) of the last solve/resolve kernel launched through the host-pointer
+ * API (CUDA events on the launching stream), and the number of kernel launches the
+ * handle has issued so far. */
+int pqp_last_kernel_ms(pqp_handle *h, float *ms);
+int pqp_launch_count(pqp_handle *h, int64_t *count);
+
+/* Device-side properties, for occupancy reporting: SM count, resident warps per SM of
+ * the solve kernel, dynamic shared memory per warp in bytes. */
+int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm,
+                    int32_t *smem_per_warp);
+
+const char *pqp_last_error(const pqp_handle *h); /* h may be NULL: last create error */
+int pqp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQP_H_ */
