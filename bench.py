@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — path-QP solves/s on B200 (contract in the task statement).
+
+One "step" = one pass of the hot path (assemble + OSQP-style ADMM to the reference's
+eps = 2e-3 + solution write-back, i.e. one `BaseSolver::solve` per instance) over one batch
+of synthetic instances. Default workload: BASELINE.json configs[2] — batch 8192 paths,
+240 knots, per-instance clearance bounds — per GPU (weak scaling: configs[3] = 8 x 8192).
+
+  value      : solves/s, inputs resident in HBM, kernel launched through the C ABI's
+               device-pointer entry point, CUDA events on the launching stream, max over ranks
+  e2e        : same metric through the host-buffer C ABI call (pinned host buffers, H2D + D2H
+               inside the timed region)
+  roofline   : algorithmic bytes (104 n + 56 per cold solve) / kernel time vs the
+               measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline: the oracle port (OSQP-algorithm restatement) on the host cores, bounded sample
+
+`--impl reference` times that CPU path alone (kind "port": OSQP itself is not available).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from path_optimizer_2_b200 import abi, synthetic  # noqa: E402
+
+METRIC = "path-QP solves/sec (N knots, batch B)"
+UNIT = "solves/s"
+CFG_ID = 3
+
+
+def algorithmic_bytes(n, warm=False):
+    return (296 * n + 72) if warm else (104 * n + 56)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(params, hb, sample, threads):
+    from oracle import oracle
+    sub = hb.slice(0, min(sample, hb.batch))
+    res, secs = oracle.solve_batch(params, sub, nthreads=threads, mode=0, dense_assembly=True)
+    solved = int(np.sum(res.status == abi.PQP_SOLVED))
+    return {"value": sub.batch / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d instances of the same workload, oracle port (OSQP-algorithm restatement, "
+                      "reference-style dense assembly included), %d OpenMP threads, %.2f s wall, "
+                      "%d solved" % (sub.batch, threads, secs, solved)}, secs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path alone (rank 0 only under torchrun)."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    params = abi.default_params()
+    threads = oracle.max_threads()
+    sample = args.cpu_sample
+    hb = synthetic.make_batch(CFG_ID, sample, args.n)
+    for _ in range(args.warmup):
+        oracle.solve_batch(params, hb.slice(0, min(64, sample)), nthreads=threads)
+    t_tot = 0.0
+    for _ in range(args.steps):
+        _, secs = oracle.solve_batch(params, hb, nthreads=threads, mode=0, dense_assembly=True)
+        t_tot += secs
+    value = sample * args.steps / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: batch 8192 paths, 240 knots, per-instance clearance "
+                               "bounds (each step = a bounded sample of %d instances)" % sample,
+                   "n_knots": args.n, "batch_per_step": sample, "cold_solve": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d instances per step, OSQP-algorithm restatement (real OSQP is not "
+                                   "vendored by the reference and not installable here)" % sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step")
+    ap.add_argument("--n", type=int, default=240, help="knots per path")
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from path_optimizer_2_b200 import solver
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    params = abi.default_params()
+    B, n = args.batch, args.n
+    # this rank's shard of the global batch (weak scaling: B instances per GPU)
+    hb = synthetic.make_batch(CFG_ID, B, n, first=rank * B)
+    sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
+
+    # ---- device-resident inputs/outputs (torch owns the memory, the C ABI gets raw pointers)
+    d_knots = torch.from_numpy(hb.knots).to(dev)
+    d_inst = torch.from_numpy(hb.inst).to(dev)
+    d_n = torch.from_numpy(hb.n).to(dev)
+    d_sol = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
+    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
+    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
+    bin_s = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+    bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
+                             None, None, None, None)
+    # gathered per-instance results {cost f64, status i32, iters i32} = 16 B / instance
+    packed = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    gathered = torch.zeros((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device():
+        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
+        if world > 1:
+            packed[:, 0] = d_cost
+            packed[:, 1] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sv.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
+        kev[i][1].record()
+        if world > 1:
+            packed[:, 0] = d_cost
+            packed[:, 1] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
+            dist.all_gather_into_tensor(gathered, packed)
+        ev[i + 1].record()
+    barrier()
+    launches = sv.launch_count - launches0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+    status = d_status.cpu().numpy()
+    iters = d_iters.cpu().numpy()
+
+    # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed)
+    e2e_steps = args.e2e_steps or args.steps
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    p_knots, p_inst, p_n = pin(hb.knots), pin(hb.inst), pin(hb.n)
+    hbp = abi.HostBatch(p_knots.numpy(), p_inst.numpy(), p_n.numpy())
+    hres = abi.HostResult(B, n, full=False, info=False)
+    p_sol, p_cost = pin(hres.sol), pin(hres.cost)
+    p_status, p_iters = pin(hres.status), pin(hres.iters)
+    hres.sol, hres.cost, hres.status, hres.iters = p_sol.numpy(), p_cost.numpy(), p_status.numpy(), p_iters.numpy()
+    for _ in range(2):
+        sv.solve(hbp, out=hres)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sv.solve(hbp, out=hres)  # synchronous: returns after the D2H copy completed
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * B * e2e_steps / e2e_s
+    h2d = int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes)
+    d2h = int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes)
+    assert np.array_equal(hres.status, status), "host-API and device-API runs disagree"
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bytes_per_launch = B * algorithmic_bytes(n)
+        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        info = sv.kernel_info
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "BASELINE configs[2] per GPU: batch %d paths, %d knots, per-instance clearance "
+                            "bounds, cold BaseSolver::solve (configs[3] = 8 GPUs x 8192)" % (B, n),
+                "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                "eps_abs": params.eps_abs, "eps_rel": params.eps_rel, "max_iter": params.max_iter,
+                "l2_policy": "inputs larger than L2 (%.0f MB per step vs 126 MB)" % (hb.knots.nbytes / 1e6),
+                "collective": "all_gather of {cost,status,iters} (16 B/instance)" if world > 1 else "none",
+                "mean_admm_iters": float(np.mean(iters)),
+                "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
+                "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "pqp_admm_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "note": "state is shared-memory resident; the path is latency/issue bound, "
+                                 "not HBM bound (see DESIGN.md)"},
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle
+            cb, _ = cpu_baseline(params, hb, args.cpu_sample, oracle.max_threads())
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    sv.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,480 @@
+// pqp_api.cu — C ABI (include/pqp.h) of the batched path-QP solver for B200 (sm_100a).
+//
+// Host side: handle with device buffers + per-instance warm state, H2D/D2H staging for the
+// host-pointer entry points, launches. Device side: the kernel entry (one warp = one CTA =
+// one QP instance; the instance's knot block is staged into shared memory with one TMA
+// bulk copy + mbarrier) around the QpWarp<C> solver of pqp_kernel.cuh, and the FP64
+// Frenet->Cartesian epilogue kernel (base_solver.cpp:263-288).
+//
+// There is no CPU fallback in this library: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "pqp_host_common.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------ device: TMA staging
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ device: kernel entry
+// One CTA = one warp = one QP instance. Dynamic shared memory: NFIELD*C*32 floats of
+// solver state (the factor region doubles as the FP64 input staging buffer) + 1 mbarrier.
+template <int C>
+__global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pqp::KernelArgs ka) {
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x;
+    const int qp = blockIdx.x;
+    if (qp >= ka.batch) return;
+    const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+    if (ka.use_tma) {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pqp::NFIELD * C * 32);
+        double *stage = reinterpret_cast<double *>(smem + pqp::FDI * C * 32);
+        const uint32_t bytes = (uint32_t)(PQP_NFIELDS * ka.n_max * sizeof(double));
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(stage, src, bytes, bar);
+        }
+        mbar_wait(bar, 0);
+        src = stage;
+    }
+    pqp::QpWarp<C> w(ka, smem, lane, qp);
+    w.run(src, ka.n_max);
+}
+
+// BaseSolver::getOptimizedPath (base_solver.cpp:263-288) in FP64, one thread per knot.
+__device__ __forceinline__ double constrain_angle(double a) {
+    while (a > M_PI) a -= 2 * M_PI;
+    while (a < -M_PI) a += 2 * M_PI;
+    return a;
+}
+__global__ void frenet_to_cartesian_kernel(int batch, int n_max, const int *__restrict__ n,
+                                           const double *__restrict__ ref, const double *__restrict__ sol,
+                                           double *__restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * n_max) return;
+    const int b = idx / n_max, i = idx - b * n_max;
+    if (i >= n[b]) return;
+    const size_t r = (size_t)b * 3 * n_max, s = (size_t)b * 4 * n_max;
+    const double angle = ref[r + 2 * n_max + i];
+    const double l = sol[s + i], psi = sol[s + n_max + i];
+    const double new_angle = constrain_angle(angle + M_PI_2);
+    out[r + i] = ref[r + i] + l * cos(new_angle);
+    out[r + n_max + i] = ref[r + n_max + i] + l * sin(new_angle);
+    out[r + 2 * n_max + i] = constrain_angle(angle + psi);
+}
+
+// previous solution -> linearisation fields of the device knot buffer
+__global__ void relinearise_kernel(int batch, int n_max, const double *__restrict__ sol,
+                                   double *__restrict__ knots) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * n_max) return;
+    const int b = idx / n_max, i = idx - b * n_max;
+    const size_t s = (size_t)b * 4 * n_max, k = (size_t)b * PQP_NFIELDS * n_max;
+    knots[k + (size_t)PQP_F_L * n_max + i] = sol[s + i];
+    knots[k + (size_t)PQP_F_PSI * n_max + i] = sol[s + n_max + i];
+    knots[k + (size_t)PQP_F_K * n_max + i] = sol[s + 2 * (size_t)n_max + i];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+struct pqp_handle {
+    pqp_params prm;
+    int n_max = 0, batch_max = 0, device = 0, chunk = 0;
+    int sm_count = 0, warps_per_sm = 0;
+    size_t smem_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device buffers owned by the handle
+    double *d_knots = nullptr, *d_inst = nullptr, *d_sol = nullptr, *d_cost = nullptr, *d_info = nullptr;
+    double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
+    int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    float *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    double *d_sol2 = nullptr;
+    int *d_n2 = nullptr;
+    bool solved = false, host_inputs_resident = false, d_p_valid = false;
+    int last_batch = 0;
+    float last_ms = 0.0f;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(pqp_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+int cuda_fail(pqp_handle *h, cudaError_t e, const char *what) {
+    return fail(h, PQP_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PQP_CUDA(h, call)                                         \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return cuda_fail((h), e_, #call);  \
+    } while (0)
+
+template <int C>
+cudaError_t launch(const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
+    pqp_admm_kernel<C><<<ka.batch, 32, smem, s>>>(ka);
+    return cudaGetLastError();
+}
+cudaError_t launch_chunk(int chunk, const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
+    switch (chunk) {
+        case 1: return launch<1>(ka, smem, s);
+        case 2: return launch<2>(ka, smem, s);
+        case 4: return launch<4>(ka, smem, s);
+        default: return launch<8>(ka, smem, s);
+    }
+}
+template <int C>
+cudaError_t prepare(size_t smem, int *blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, pqp_admm_kernel<C>, 32, smem);
+}
+
+int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
+    if (!h) return PQP_E_INVALID;
+    if (!in || !out) return fail(h, PQP_E_INVALID, "null batch");
+    if (!in->knots || !in->inst || !in->n || !out->sol) return fail(h, PQP_E_INVALID, "null buffer");
+    if (in->batch < 1 || in->batch > h->batch_max) return fail(h, PQP_E_INVALID, "batch out of range");
+    if (in->n_max != h->n_max) return fail(h, PQP_E_INVALID, "n_max differs from the handle's");
+    return PQP_OK;
+}
+
+// device pointers in `in`/`out`; asynchronous
+int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode,
+               cudaStream_t s, bool timed) {
+    pqp::KernelArgs ka;
+    ka.prm = pqp::make_dev_params(h->prm);
+    ka.batch = in->batch;
+    ka.n_max = in->n_max;
+    ka.mode = mode;
+    const size_t block_bytes = (size_t)PQP_NFIELDS * in->n_max * sizeof(double);
+    ka.use_tma = ((block_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in->knots) % 16) == 0) ? 1 : 0;
+    ka.knots = in->knots;
+    ka.inst = in->inst;
+    ka.n = in->n;
+    ka.p = in->p;
+    ka.sol = out->sol;
+    ka.cost = out->cost;
+    ka.status = out->status;
+    ka.iters = out->iters;
+    ka.x_full = out->x_full;
+    ka.y_full = out->y_full;
+    ka.z_full = out->z_full;
+    ka.info = out->info;
+    ka.warm = h->d_warm;
+    ka.scal = h->d_scal;
+    ka.dy = h->d_dy;
+    ka.rho_state = h->d_rho;
+    if (timed) PQP_CUDA(h, cudaEventRecord(h->ev0, s));
+    PQP_CUDA(h, launch_chunk(h->chunk, ka, h->smem_bytes, s));
+    if (timed) PQP_CUDA(h, cudaEventRecord(h->ev1, s));
+    h->launches++;
+    h->solved = true;
+    h->last_batch = in->batch;
+    return PQP_OK;
+}
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
+}
+
+int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode) {
+    int rc;
+    const int nmax = h->n_max;
+    cudaStream_t s = h->stream;
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    int B;
+    if (in) {
+        rc = validate_batch(h, in, out);
+        if (rc) return rc;
+        B = in->batch;
+        for (int b = 0; b < B; ++b) {
+            if (in->n[b] < 2 || in->n[b] > nmax) return fail(h, PQP_E_INVALID, "n[b] must be in [2, n_max]");
+            if (in->p && (in->p[b] < 0 || in->p[b] > in->n[b])) return fail(h, PQP_E_INVALID, "p[b] must be in [0, n[b]]");
+        }
+        if (mode == 1 && (!h->solved || B != h->last_batch)) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_knots, in->knots, (size_t)B * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, s));
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_inst, in->inst, (size_t)B * PQP_NINST * sizeof(double), cudaMemcpyHostToDevice, s));
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_n, in->n, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (in->p) PQP_CUDA(h, cudaMemcpyAsync(h->d_p, in->p, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+        h->host_inputs_resident = true;
+        h->d_p_valid = in->p != nullptr;
+    } else {
+        if (mode != 1) return fail(h, PQP_E_INVALID, "null batch");
+        if (!out || !out->sol) return fail(h, PQP_E_INVALID, "null output");
+        if (!h->solved || !h->host_inputs_resident) return fail(h, PQP_E_STATE, "resolve(NULL) needs a previous host-API solve");
+        B = h->last_batch;
+        const int threads = 256, blocks = (B * nmax + threads - 1) / threads;
+        relinearise_kernel<<<blocks, threads, 0, s>>>(B, nmax, h->d_sol, h->d_knots);
+        PQP_CUDA(h, cudaGetLastError());
+        h->launches++;
+    }
+    // optional full outputs are allocated on first use
+    const size_t nvm = 6 * (size_t)nmax - 1, mm = 6 * (size_t)nmax + 2;
+    if (out->x_full && !h->d_xf) PQP_CUDA(h, dmalloc(&h->d_xf, (size_t)h->batch_max * nvm));
+    if (out->y_full && !h->d_yf) PQP_CUDA(h, dmalloc(&h->d_yf, (size_t)h->batch_max * mm));
+    if (out->z_full && !h->d_zf) PQP_CUDA(h, dmalloc(&h->d_zf, (size_t)h->batch_max * mm));
+    if (out->x_full) PQP_CUDA(h, cudaMemsetAsync(h->d_xf, 0, (size_t)B * nvm * sizeof(double), s));
+    if (out->y_full) PQP_CUDA(h, cudaMemsetAsync(h->d_yf, 0, (size_t)B * mm * sizeof(double), s));
+    if (out->z_full) PQP_CUDA(h, cudaMemsetAsync(h->d_zf, 0, (size_t)B * mm * sizeof(double), s));
+    pqp_batch_in din;
+    din.batch = B;
+    din.n_max = nmax;
+    din.knots = h->d_knots;
+    din.inst = h->d_inst;
+    din.n = h->d_n;
+    din.p = h->d_p_valid ? h->d_p : nullptr;
+    pqp_batch_out dout;
+    dout.sol = h->d_sol;
+    dout.cost = h->d_cost;
+    dout.status = h->d_status;
+    dout.iters = h->d_iters;
+    dout.x_full = out->x_full ? h->d_xf : nullptr;
+    dout.y_full = out->y_full ? h->d_yf : nullptr;
+    dout.z_full = out->z_full ? h->d_zf : nullptr;
+    dout.info = h->d_info;
+    rc = run_device(h, &din, &dout, mode, s, true);
+    if (rc) return rc;
+    PQP_CUDA(h, cudaMemcpyAsync(out->sol, h->d_sol, (size_t)B * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost, h->d_cost, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status, h->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out->iters) PQP_CUDA(h, cudaMemcpyAsync(out->iters, h->d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out->info) PQP_CUDA(h, cudaMemcpyAsync(out->info, h->d_info, (size_t)B * PQP_NINFO * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->x_full) PQP_CUDA(h, cudaMemcpyAsync(out->x_full, h->d_xf, (size_t)B * nvm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->y_full) PQP_CUDA(h, cudaMemcpyAsync(out->y_full, h->d_yf, (size_t)B * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full, h->d_zf, (size_t)B * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PQP_CUDA(h, cudaStreamSynchronize(s));
+    PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return PQP_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int pqp_version(void) { return PQP_VERSION; }
+
+int pqp_default_params(pqp_params *params) {
+    if (!params) return PQP_E_INVALID;
+    pqp::default_params(params);
+    return PQP_OK;
+}
+
+const char *pqp_last_error(const pqp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32_t device,
+               pqp_handle **out) {
+    if (!out) return fail(nullptr, PQP_E_INVALID, "out is null");
+    *out = nullptr;
+    if (!params || !pqp::params_valid(*params)) return fail(nullptr, PQP_E_INVALID, "invalid params");
+    if (n_max < 2 || n_max > 32 * pqp::kMaxChunk - 1) return fail(nullptr, PQP_E_INVALID, "n_max must be in [2, 255]");
+    if (batch_max < 1) return fail(nullptr, PQP_E_INVALID, "batch_max must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PQP_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, PQP_E_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, PQP_E_NO_DEVICE, "this library is built for sm_100a (B200) only; found sm_" +
+                                                  std::to_string(prop.major) + std::to_string(prop.minor));
+    pqp_handle *h = new (std::nothrow) pqp_handle;
+    if (!h) return fail(nullptr, PQP_E_INVALID, "out of host memory");
+    h->prm = *params;
+    h->n_max = n_max;
+    h->batch_max = batch_max;
+    h->device = device;
+    h->chunk = pqp::chunk_for(n_max);
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_bytes = pqp::smem_floats(h->chunk) * sizeof(float) + 16;
+#define PQP_CREATE_CUDA(call)                                                     \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) {                                                  \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_);  \
+            pqp_destroy(h);                                                       \
+            return PQP_E_CUDA;                                                    \
+        }                                                                         \
+    } while (0)
+    PQP_CREATE_CUDA(cudaSetDevice(device));
+    int bps = 0;
+    switch (h->chunk) {
+        case 1: PQP_CREATE_CUDA(prepare<1>(h->smem_bytes, &bps)); break;
+        case 2: PQP_CREATE_CUDA(prepare<2>(h->smem_bytes, &bps)); break;
+        case 4: PQP_CREATE_CUDA(prepare<4>(h->smem_bytes, &bps)); break;
+        default: PQP_CREATE_CUDA(prepare<8>(h->smem_bytes, &bps)); break;
+    }
+    h->warps_per_sm = bps;
+    PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PQP_CREATE_CUDA(cudaEventCreate(&h->ev0));
+    PQP_CREATE_CUDA(cudaEventCreate(&h->ev1));
+    const size_t B = batch_max, c = h->chunk;
+    PQP_CREATE_CUDA(dmalloc(&h->d_knots, B * PQP_NFIELDS * n_max));
+    PQP_CREATE_CUDA(dmalloc(&h->d_inst, B * PQP_NINST));
+    PQP_CREATE_CUDA(dmalloc(&h->d_n, B));
+    PQP_CREATE_CUDA(dmalloc(&h->d_p, B));
+    PQP_CREATE_CUDA(dmalloc(&h->d_sol, B * 4 * n_max));
+    PQP_CREATE_CUDA(dmalloc(&h->d_cost, B));
+    PQP_CREATE_CUDA(dmalloc(&h->d_status, B));
+    PQP_CREATE_CUDA(dmalloc(&h->d_iters, B));
+    PQP_CREATE_CUDA(dmalloc(&h->d_info, B * PQP_NINFO));
+    PQP_CREATE_CUDA(dmalloc(&h->d_warm, B * pqp::warm_floats(c)));
+    PQP_CREATE_CUDA(dmalloc(&h->d_scal, B * pqp::scal_floats(c)));
+    PQP_CREATE_CUDA(dmalloc(&h->d_dy, B * pqp::dy_floats(c)));
+    PQP_CREATE_CUDA(dmalloc(&h->d_rho, B));
+    PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * sizeof(float)));
+    PQP_CREATE_CUDA(cudaMemset(h->d_sol, 0, B * 4 * n_max * sizeof(double)));
+#undef PQP_CREATE_CUDA
+    *out = h;
+    return PQP_OK;
+}
+
+int pqp_destroy(pqp_handle *h) {
+    if (!h) return PQP_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_knots); cudaFree(h->d_inst); cudaFree(h->d_n); cudaFree(h->d_p);
+    cudaFree(h->d_sol); cudaFree(h->d_cost); cudaFree(h->d_status); cudaFree(h->d_iters);
+    cudaFree(h->d_info); cudaFree(h->d_xf); cudaFree(h->d_yf); cudaFree(h->d_zf);
+    cudaFree(h->d_ref); cudaFree(h->d_xy); cudaFree(h->d_sol2); cudaFree(h->d_n2);
+    cudaFree(h->d_warm); cudaFree(h->d_scal); cudaFree(h->d_dy); cudaFree(h->d_rho);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PQP_OK;
+}
+
+int pqp_solve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
+    if (!h) return PQP_E_INVALID;
+    if (!in) return fail(h, PQP_E_INVALID, "null batch");
+    return run_host(h, in, out, 0);
+}
+
+int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
+    if (!h) return PQP_E_INVALID;
+    return run_host(h, in, out, 1);
+}
+
+int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, void *stream) {
+    int rc = validate_batch(h, in, out);
+    if (rc) return rc;
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    h->host_inputs_resident = false;
+    return run_device(h, in, out, 0, static_cast<cudaStream_t>(stream), false);
+}
+
+int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, void *stream) {
+    int rc = validate_batch(h, in, out);
+    if (rc) return rc;
+    if (!h->solved || in->batch != h->last_batch) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    return run_device(h, in, out, 1, static_cast<cudaStream_t>(stream), false);
+}
+
+int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *n, const double *ref_xyh,
+                                   const double *sol, double *out_xyh, void *stream) {
+    if (!h) return PQP_E_INVALID;
+    if (!n || !ref_xyh || !sol || !out_xyh || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
+    frenet_to_cartesian_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, n, ref_xyh, sol, out_xyh);
+    PQP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return PQP_OK;
+}
+
+int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n, const double *ref_xyh,
+                            const double *sol, double *out_xyh) {
+    if (!h) return PQP_E_INVALID;
+    if (!n || !ref_xyh || !sol || !out_xyh || batch < 1 || batch > h->batch_max) return fail(h, PQP_E_INVALID, "bad arguments");
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    const size_t B = batch, nm = h->n_max;
+    if (!h->d_ref) PQP_CUDA(h, dmalloc(&h->d_ref, (size_t)h->batch_max * 3 * nm));
+    if (!h->d_xy) PQP_CUDA(h, dmalloc(&h->d_xy, (size_t)h->batch_max * 3 * nm));
+    if (!h->d_sol2) PQP_CUDA(h, dmalloc(&h->d_sol2, (size_t)h->batch_max * 4 * nm));
+    if (!h->d_n2) PQP_CUDA(h, dmalloc(&h->d_n2, (size_t)h->batch_max));
+    cudaStream_t s = h->stream;
+    PQP_CUDA(h, cudaMemcpyAsync(h->d_ref, ref_xyh, B * 3 * nm * sizeof(double), cudaMemcpyHostToDevice, s));
+    PQP_CUDA(h, cudaMemcpyAsync(h->d_sol2, sol, B * 4 * nm * sizeof(double), cudaMemcpyHostToDevice, s));
+    PQP_CUDA(h, cudaMemcpyAsync(h->d_n2, n, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    PQP_CUDA(h, cudaMemsetAsync(h->d_xy, 0, B * 3 * nm * sizeof(double), s));
+    int rc = pqp_frenet_to_cartesian_device(h, batch, h->d_n2, h->d_ref, h->d_sol2, h->d_xy, s);
+    if (rc) return rc;
+    PQP_CUDA(h, cudaMemcpyAsync(out_xyh, h->d_xy, B * 3 * nm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PQP_CUDA(h, cudaStreamSynchronize(s));
+    return PQP_OK;
+}
+
+int pqp_last_kernel_ms(pqp_handle *h, float *ms) {
+    if (!h || !ms) return PQP_E_INVALID;
+    *ms = h->last_ms;
+    return PQP_OK;
+}
+
+int pqp_launch_count(pqp_handle *h, int64_t *count) {
+    if (!h || !count) return PQP_E_INVALID;
+    *count = h->launches;
+    return PQP_OK;
+}
+
+int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm, int32_t *smem_per_warp) {
+    if (!h) return PQP_E_INVALID;
+    if (sm_count) *sm_count = h->sm_count;
+    if (warps_per_sm) *warps_per_sm = h->warps_per_sm;
+    if (smem_per_warp) *smem_per_warp = (int32_t)h->smem_bytes;
+    return PQP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1303 @@
+// pqp_kernel.cuh — one warp per path-QP: assembly + OSQP-style ADMM, state in shared memory.
+//
+// What it computes (reference file:line it replaces):
+//   assembly of P, A, l, u             /root/reference/src/solver/base_solver.cpp:119-261,290-296
+//   OSQP setup (Ruiz scaling, rho vec) base_solver.cpp:87   (osqp_setup through osqp-eigen)
+//   OSQP ADMM loop, termination, rho   base_solver.cpp:88,110
+//   warm update of A and bounds        base_solver.cpp:102-107
+// How (B200 design):
+//   * one warp per QP instance, lane L owns the C consecutive stages [L*C, L*C+C) of the
+//     stage chain (stage 0 is a virtual stage whose outgoing rows are the x0 rows, stage
+//     g>=1 is knot g-1, the last knot's outgoing rows are the two end-state rows);
+//   * all per-stage data lives in shared memory as [field][k][lane] (conflict-free);
+//   * the x-update solves the reduced SPD system (P + S + A'RA) x = rhs exactly:
+//     controls and slacks are eliminated in closed form, leaving a block-tridiagonal
+//     system in (l, psi, kappa) with 3x3 blocks. It is factored as block LDL' in a
+//     nested-dissection order: each lane eliminates its C-1 interior stages serially,
+//     the 32 separator stages are eliminated by block cyclic reduction across lanes
+//     with warp shuffles;
+//   * iterates are kept in *unscaled* variables; OSQP's Ruiz scaling (D, E, c) appears as
+//     per-row weights R_i = rho_i e_i^2 / c and per-variable weights S_j = sigma/(c d_j^2),
+//     which is algebraically identical to OSQP's iteration on the scaled problem;
+//   * the dual is stored scaled (yhat = y / R) so the z/y update needs no division.
+//
+// This header is also compiled for the host by tests/emu (PQP_EMU) where a warp is 32
+// cooperative fibers; that build exists only to test this source on the GPU-less build
+// box and is never linked into the product.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef PQP_EMU
+#include <cmath>
+#include "warp_emu.h"
+#define PQP_DEV inline
+#define PQP_RESTRICT
+#else
+#include <cuda_runtime.h>
+#define PQP_DEV __device__ __forceinline__
+#define PQP_RESTRICT __restrict__
+#endif
+
+namespace pqp {
+
+// ------------------------------------------------------------------ constants (OSQP 0.6.x)
+constexpr float kOsqpInfty = 1e30f;
+constexpr float kMinScaling = 1e-4f;
+constexpr float kMaxScaling = 1e4f;
+constexpr float kRhoMin = 1e-6f;
+constexpr float kRhoMax = 1e6f;
+constexpr float kRhoEqOverIneq = 1e3f;
+constexpr float kRhoTol = 1e-4f;
+
+// status codes: keep in sync with include/pqp.h
+constexpr int kSolved = 0, kMaxIter = 1, kPrimInf = 2, kDualInf = 3, kSolvedInacc = 4,
+              kPrimInfInacc = 5, kNumerical = 7, kUnsolved = 10;
+
+// ------------------------------------------------------------------ shared-memory field map
+// element (field f, local stage k, lane) lives at sm[(f*C + k)*32 + lane]
+enum : int {
+    FX = 0,     // 6: l, psi, kappa, u, s0, s1           (primal iterate x)
+    FA = 6,     // 6: a00 a01 a10 a11 a12 ds             (stage transition coefficients)
+    FS = 12,    // 6: S_j = sigma / (c d_j^2)            (proximal weights)
+    FE = 18,    // 6: bu bs0 bs1 1/m_u 1/m_s0 1/m_s1     (closed-form elimination constants)
+    FOB = 24,   // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
+    FOY = 27,   // 3: outgoing-row scaled dual yhat
+    FOR_ = 30,  // 3: outgoing-row weight R
+    FKZ = 33, FKY = 34, FKR = 35,                       // kappa box row: z, yhat, R
+    FCLO = 36, FCHI = 38, FCZ = 40, FCY = 42, FCR = 44,  // clearance rows (2 each)
+    FCLS = 46,  // row class bitmask (int bits 2r..2r+1: 0 ineq, 1 eq, 2 loose, 3 inactive)
+    FDI = 47,   // 6: inverse pivot block (sym)
+    FG = 53,    // 9: multiplier to the next stage
+    FF = 62,    // 9: multiplier to the left separator (fill)
+    NFIELD = 71
+};
+// global per-QP scratch, same [field][k][lane] layout
+enum : int {
+    WX = 0,    // 6 scaled primal
+    WOZ = 6,   // 3 scaled z of outgoing rows
+    WOY = 9,   // 3 scaled y of outgoing rows
+    WKZ = 12, WKY = 13,
+    WCZ = 14, WCY = 16,
+    NWARM = 18,
+    GD = 0, GE = 6, NSCAL = 12,  // D (6 vars), E (6 rows)
+    NDY = 6
+};
+
+struct DevParams {
+    double front_length, rear_length, kappa_limit, safety_margin, end_l_lb, end_l_ub;
+    float w_l, w_kappa, w_dkappa, w_slack;
+    float rho0, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, rho_tol;
+    int max_iter, check_every, scaling, adaptive_rho, adaptive_interval;
+    int factor_fp64;
+};
+
+struct KernelArgs {
+    DevParams prm;
+    int batch, n_max, mode, use_tma;  // mode 0 cold, 1 warm
+    const double *knots, *inst;
+    const int *n, *p;
+    double *sol, *cost;
+    int *status, *iters;
+    double *x_full, *y_full, *z_full, *info;
+    float *warm, *scal, *dy, *rho_state;
+};
+
+// ------------------------------------------------------------------ warp primitives
+#ifdef PQP_EMU
+template <typename T> PQP_DEV T shfl_up(T v, int d, int lane) {
+    return warp_emu::exchange(v, lane, lane - d);
+}
+template <typename T> PQP_DEV T shfl_down(T v, int d, int lane) {
+    return warp_emu::exchange(v, lane, lane + d);
+}
+template <typename T> PQP_DEV T shfl_xor(T v, int m, int lane) {
+    return warp_emu::exchange(v, lane, lane ^ m);
+}
+PQP_DEV void sync_warp(int lane) { warp_emu::current()->barrier(lane); }
+PQP_DEV float frsqrt(float x) { return 1.0f / std::sqrt(x); }
+PQP_DEV float fdivf(float a, float b) { return a / b; }
+using std::fabs;
+using std::fmax;
+using std::fmin;
+using std::sqrt;
+#else
+template <typename T> PQP_DEV T shfl_up(T v, int d, int) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <typename T> PQP_DEV T shfl_down(T v, int d, int) { return __shfl_down_sync(0xffffffffu, v, d); }
+template <typename T> PQP_DEV T shfl_xor(T v, int m, int) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PQP_DEV void sync_warp(int) { __syncwarp(); }
+PQP_DEV float frsqrt(float x) { return 1.0f / sqrtf(x); }
+PQP_DEV float fdivf(float a, float b) { return a / b; }
+#endif
+
+PQP_DEV float warp_max(float v, int lane) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, shfl_xor(v, m, lane));
+    return v;
+}
+PQP_DEV float warp_sum(float v, int lane) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor(v, m, lane);
+    return v;
+}
+
+PQP_DEV float limit_scaling(float v) {
+    v = v < kMinScaling ? 1.0f : v;
+    return v > kMaxScaling ? kMaxScaling : v;
+}
+PQP_DEV float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ------------------------------------------------------------------ 3x3 helpers
+// symmetric 3x3 as [6] = (00,01,02,11,12,22); general 3x3 row-major [9]
+PQP_DEV constexpr int SI(int i, int j) {
+    return i <= j ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : (j == 0 ? i : (j == 1 ? 2 + i : 5));
+}
+
+// inverse of an SPD 3x3 through its Cholesky factor; returns false on a non-positive pivot
+template <typename T> PQP_DEV bool inv_sym3(const T (&a)[6], T (&o)[6]) {
+    bool ok = true;
+    T p0 = a[0];
+    ok = ok && (p0 > T(0));
+    T i00 = T(1) / sqrt(p0);
+    T l10 = a[1] * i00, l20 = a[2] * i00;
+    T p1 = a[3] - l10 * l10;
+    ok = ok && (p1 > T(0));
+    T i11 = T(1) / sqrt(p1);
+    T l21 = (a[4] - l20 * l10) * i11;
+    T p2 = a[5] - l20 * l20 - l21 * l21;
+    ok = ok && (p2 > T(0));
+    T i22 = T(1) / sqrt(p2);
+    T i10 = -l10 * i00 * i11;
+    T i21 = -l21 * i11 * i22;
+    T i20 = -(l20 * i00 + l21 * i10) * i22;
+    o[0] = i00 * i00 + i10 * i10 + i20 * i20;
+    o[1] = i10 * i11 + i20 * i21;
+    o[2] = i20 * i22;
+    o[3] = i11 * i11 + i21 * i21;
+    o[4] = i21 * i22;
+    o[5] = i22 * i22;
+    return ok;
+}
+// out = M * S (general x symmetric)
+template <typename T> PQP_DEV void mul_ms(const T (&m)[9], const T (&s)[6], T (&o)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            o[3 * r + c] = m[3 * r] * s[SI(0, c)] + m[3 * r + 1] * s[SI(1, c)] + m[3 * r + 2] * s[SI(2, c)];
+}
+// out = A * B' (general)
+template <typename T> PQP_DEV void mul_abt(const T (&a)[9], const T (&b)[9], T (&o)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            o[3 * r + c] = a[3 * r] * b[3 * c] + a[3 * r + 1] * b[3 * c + 1] + a[3 * r + 2] * b[3 * c + 2];
+}
+// symmetric part of A * B' when the product is known to be symmetric
+template <typename T> PQP_DEV void mul_abt_sym(const T (&a)[9], const T (&b)[9], T (&o)[6]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c)
+            o[SI(r, c)] = a[3 * r] * b[3 * c] + a[3 * r + 1] * b[3 * c + 1] + a[3 * r + 2] * b[3 * c + 2];
+}
+
+// ------------------------------------------------------------------ per-stage predicates
+struct StagePred {
+    bool real, mid, last, act0, act1;
+    float gn, a22, h0, h1;
+};
+PQP_DEV StagePred stage_pred(int g, int n, int p, float lf, float lr) {
+    StagePred s;
+    s.real = (g >= 1) && (g <= n);
+    s.mid = (g >= 1) && (g <= n - 1);
+    s.last = (g == n);
+    s.act0 = s.real;
+    s.act1 = (g >= 1) && (g <= p);
+    s.gn = (g <= n - 1) ? -1.0f : 0.0f;
+    s.a22 = s.mid ? 1.0f : 0.0f;
+    s.h0 = s.act1 ? lf : 0.0f;  // front row for precise stages, centre row (h = 0) otherwise
+    s.h1 = s.act1 ? lr : 0.0f;
+    return s;
+}
+
+PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, double &oub) {
+    const double clearance = ub - lb;
+    double remain = clearance - 2 * margin;
+    remain = remain > 0.1 ? remain : 0.1;
+    double shrink = (clearance - remain) / 2.0;
+    shrink = shrink > 0.0 ? shrink : 0.0;
+    olb = lb + shrink;
+    oub = ub - shrink;
+}
+
+// =========================================================================================
+template <int C>
+struct QpWarp {
+    const KernelArgs &ka;
+    float *sm;
+    const int lane, qp;
+    int n, p;
+    float lf, lr, kmax;
+    // end rows (valid on the lane/stage that owns knot n-1)
+    float zend[2], endw[2];
+    // separator (cyclic reduction) factors of this lane
+    float crAinv[6], crGm[9], crGp[9];
+    // Ruiz cost scaling and current rho
+    float cscale, rho;
+    // per-QP global scratch
+    float *gwarm, *gscal, *gdy;
+
+    PQP_DEV QpWarp(const KernelArgs &k, float *s, int l, int q) : ka(k), sm(s), lane(l), qp(q) {}
+
+    PQP_DEV float &S(int f, int k) { return sm[(f * C + k) * 32 + lane]; }
+    PQP_DEV float &SL(int f, int k, int ln) { return sm[(f * C + k) * 32 + ln]; }
+    PQP_DEV int &SI32(int f, int k) { return reinterpret_cast<int *>(sm)[(f * C + k) * 32 + lane]; }
+    PQP_DEV float &G(float *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
+    PQP_DEV float &GL(float *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
+    PQP_DEV StagePred pred(int k) const { return stage_pred(lane * C + k, n, p, lf, lr); }
+
+    // -------------------------------------------------------------- assembly
+    // base_solver.cpp:150-261 for the stage chain; src = this instance's knot block
+    PQP_DEV void assemble(const double *src, int stride) {
+        const DevParams &P = ka.prm;
+        const double *in = ka.inst + (size_t)qp * 5;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int g = lane * C + k;
+            float a[6] = {0, 0, 0, 0, 0, 0};
+            float ob[3] = {0, 0, 0};
+            float clo[2] = {0, 0}, chi[2] = {0, 0};
+            if (g == 0) {
+                ob[0] = (float)(-in[0]);
+                ob[1] = (float)(-in[1]);
+                ob[2] = (float)(-in[2]);
+            } else if (g <= n - 1) {
+                const int i = g - 1;
+                const double xl = src[2 * stride + i], xp = src[3 * stride + i], xk = src[4 * stride + i];
+                const double xkn = src[4 * stride + i + 1];
+                const double ds = src[i + 1] - src[i];
+                const double kref = src[1 * stride + i];
+                const double cp = cos(xp), tp = tan(xp);
+                const double f00 = -xk * tp, f01 = (1 - xk * xl) / (cp * cp);
+                const double f10 = -xk * xk / cp, f11 = (1 - xk * xl) * xk * tp / cp,
+                             f12 = (1 - xk * xl) / cp;
+                a[0] = (float)(ds * f00 + 1.0);
+                a[1] = (float)(ds * f01);
+                a[2] = (float)(ds * f10);
+                a[3] = (float)(ds * f11 + 1.0);
+                a[4] = (float)(ds * f12);
+                a[5] = (float)ds;
+                const double u_in = (xkn - xk) / ds;
+                const double g0 = (1 - xk * xl) * tp;
+                const double g1 = (1 - xk * xl) * xk / cp - kref;
+                const double c0 = ds * (g0 - (f00 * xl + f01 * xp));
+                const double c1 = ds * (g1 - (f10 * xl + f11 * xp + f12 * xk));
+                const double c2 = ds * (u_in - u_in);
+                ob[0] = (float)(-c0);
+                ob[1] = (float)(-c1);
+                ob[2] = (float)(-c2);
+            } else if (g == n) {
+                a[0] = 1.0f;  // end-l row:   1 * l_{n-1}
+                a[3] = 1.0f;  // end-psi row: 1 * psi_{n-1}
+                ob[0] = (float)P.end_l_lb;
+                endw[0] = (float)(P.end_l_ub - P.end_l_lb);
+                ob[1] = (float)in[3];
+                endw[1] = (float)(in[4] - in[3]);
+            }
+            if (g >= 1 && g <= n) {
+                const int i = g - 1;
+                double lo, hi;
+                soft_bounds(src[5 * stride + i], src[6 * stride + i], P.safety_margin, lo, hi);
+                clo[0] = (float)lo;
+                chi[0] = (float)hi;
+                if (g <= p) {
+                    soft_bounds(src[7 * stride + i], src[8 * stride + i], P.safety_margin, lo, hi);
+                    clo[1] = (float)lo;
+                    chi[1] = (float)hi;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) S(FA + j, k) = a[j];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) S(FOB + r, k) = ob[r];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                S(FCLO + j, k) = clo[j];
+                S(FCHI + j, k) = chi[j];
+            }
+        }
+    }
+
+    // -------------------------------------------------------------- Ruiz equilibration
+    // OSQP scale_data on the structured matrix; leaves D, E in global
+    // scratch, and row weights R / classes / S in shared memory.
+    PQP_DEV void scale_and_classify() {
+        const DevParams &P = ka.prm;
+        float d[C][6], e[C][6];
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { d[k][j] = 1.0f; e[k][j] = 1.0f; }
+        float c = 1.0f;
+        const float nv_inv = 1.0f / (float)(3 * n + (n - 1) + (p + n));
+        for (int pass = 0; pass < P.scaling; ++pass) {
+            // neighbour data: e of the left stage's outgoing rows, d of the right stage's x
+            float eLb[3], dRb[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                eLb[r] = shfl_up(e[C - 1][r], 1, lane);
+                dRb[r] = shfl_down(d[0][r], 1, lane);
+            }
+            if (lane == 0) { eLb[0] = eLb[1] = eLb[2] = 0.0f; }
+            if (lane == 31) { dRb[0] = dRb[1] = dRb[2] = 0.0f; }
+            float dn[C][6], en[C][6];
+            float psum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const StagePred sp = pred(k);
+                const float a00 = fabsf(S(FA + 0, k)), a01 = fabsf(S(FA + 1, k)), a10 = fabsf(S(FA + 2, k)),
+                            a11 = fabsf(S(FA + 3, k)), a12 = fabsf(S(FA + 4, k)), ds = fabsf(S(FA + 5, k));
+                const float gn = fabsf(sp.gn), h0 = fabsf(sp.h0), h1 = fabsf(sp.h1);
+                const float *dk = d[k], *ek = e[k];
+                float eL[3], dR[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    eL[r] = (k == 0) ? eLb[r] : e[k > 0 ? k - 1 : 0][r];
+                    dR[r] = (k == C - 1) ? dRb[r] : d[k < C - 1 ? k + 1 : k][r];
+                }
+                // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
+                const float hasL = sp.real ? 1.0f : 0.0f;
+                const float ec0 = sp.act0 ? ek[4] : 0.0f, ec1 = sp.act1 ? ek[5] : 0.0f;
+                const float ekap = sp.real ? ek[3] : 0.0f;
+                // column norms of [P; A]
+                float cn[6];
+                cn[0] = dk[0] * fmaxf(fmaxf(a00 * ek[0], a10 * ek[1]), fmaxf(hasL * eL[0], fmaxf(ec0, ec1)));
+                cn[1] = dk[1] * fmaxf(fmaxf(a01 * ek[0], a11 * ek[1]), fmaxf(hasL * eL[1], fmaxf(h0 * ec0, h1 * ec1)));
+                cn[2] = dk[2] * fmaxf(fmaxf(a12 * ek[1], sp.a22 * ek[2]), fmaxf(hasL * eL[2], ekap));
+                cn[3] = dk[3] * ds * ek[2];
+                cn[4] = dk[4] * ec0;
+                cn[5] = dk[5] * ec1;
+                const float pw[6] = {sp.real ? P.w_l : 0.0f, 0.0f, sp.real ? P.w_kappa : 0.0f,
+                                     sp.mid ? P.w_dkappa : 0.0f, sp.act0 ? P.w_slack : 0.0f,
+                                     sp.act1 ? P.w_slack : 0.0f};
+#pragma unroll
+                for (int j = 0; j < 6; ++j) cn[j] = fmaxf(cn[j], c * dk[j] * dk[j] * pw[j]);
+                // row norms of A
+                float rn[6];
+                rn[0] = ek[0] * fmaxf(fmaxf(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
+                rn[1] = ek[1] * fmaxf(fmaxf(a10 * dk[0], a11 * dk[1]), fmaxf(a12 * dk[2], gn * dR[1]));
+                rn[2] = ek[2] * fmaxf(fmaxf(sp.a22 * dk[2], ds * dk[3]), gn * dR[2]);
+                rn[3] = ekap * dk[2];
+                rn[4] = ec0 * fmaxf(fmaxf(dk[0], h0 * dk[1]), dk[4]);
+                rn[5] = ec1 * fmaxf(fmaxf(dk[0], h1 * dk[1]), dk[5]);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    dn[k][j] = dk[j] * frsqrt(limit_scaling(cn[j]));
+                    en[k][j] = ek[j] * frsqrt(limit_scaling(rn[j]));
+                    psum += dn[k][j] * dn[k][j] * pw[j];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { d[k][j] = dn[k][j]; e[k][j] = en[k][j]; }
+            // cost normalisation: c_temp = 1 / limit(max(mean_j |Pbar_jj|, 1))   (q = 0 -> 1)
+            const float mean = c * warp_sum(psum, lane) * nv_inv;
+            float ct = fmaxf(mean, 1.0f);
+            ct = limit_scaling(ct);
+            c = c / ct;
+        }
+        cscale = c;
+        // weights, classes, S; D and E to global scratch
+        const float cinv = 1.0f / c;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            int cls = 0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                G(gscal, GD + j, k) = d[k][j];
+                G(gscal, GE + j, k) = e[k][j];
+                S(FS + j, k) = ka.prm.sigma * cinv / (d[k][j] * d[k][j]);
+            }
+            // dummy variables get an identity pivot
+            if (!sp.real) { S(FS + 0, k) = 1.0f; S(FS + 1, k) = 1.0f; S(FS + 2, k) = 1.0f; S(FS + 4, k) = 1.0f; }
+            if (!sp.mid) S(FS + 3, k) = 1.0f;
+            if (!sp.act1) S(FS + 5, k) = 1.0f;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                float lo, hi;
+                bool act;
+                if (r < 3) {
+                    lo = S(FOB + r, k);
+                    hi = lo + ((sp.last && r < 2) ? endw[r] : 0.0f);
+                    act = (lane * C + k <= n - 1) || (sp.last && r < 2);
+                } else if (r == 3) {
+                    lo = -kmax; hi = kmax; act = sp.real;
+                } else {
+                    lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k);
+                    act = (r == 4) ? sp.act0 : sp.act1;
+                }
+                const float ls = lo * e[k][r], hs = hi * e[k][r];
+                int cl;
+                if (!act) cl = 3;
+                else if (ls < -kOsqpInfty * kMinScaling && hs > kOsqpInfty * kMinScaling) cl = 2;
+                else if (hs - ls < kRhoTol) cl = 1;
+                else cl = 0;
+                cls |= cl << (2 * r);
+                const float base = (cl == 3) ? 0.0f : (cl == 2 ? kRhoMin : (cl == 1 ? kRhoEqOverIneq * rho : rho));
+                const float Rw = base * e[k][r] * e[k][r] * cinv;
+                if (r < 3) S(FOR_ + r, k) = Rw;
+                else if (r == 3) S(FKR, k) = Rw;
+                else S(FCR + r - 4, k) = Rw;
+            }
+            SI32(FCLS, k) = cls;
+        }
+    }
+
+    // -------------------------------------------------------------- iterates: cold / warm
+    PQP_DEV void init_iterates(bool warm) {
+        const float c = cscale;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            if (!warm) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) S(FX + j, k) = 0.0f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) S(FOY + r, k) = 0.0f;
+                S(FKZ, k) = 0.0f; S(FKY, k) = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { S(FCZ + j, k) = 0.0f; S(FCY + j, k) = 0.0f; }
+                if (sp.last) { zend[0] = 0.0f; zend[1] = 0.0f; }
+            } else {
+                // scaled iterates of the previous solve are re-interpreted in the NEW scaling
+                // (OSQP keeps work->x/z/y untouched across osqp_update_A's re-scaling)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) S(FX + j, k) = G(gwarm, WX + j, k) * G(gscal, GD + j, k);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float e = G(gscal, GE + r, k), R = S(FOR_ + r, k);
+                    const float y = G(gwarm, WOY + r, k) * e / c;
+                    S(FOY + r, k) = R > 0.0f ? y / R : 0.0f;
+                }
+                {
+                    const float e = G(gscal, GE + 3, k), R = S(FKR, k);
+                    S(FKZ, k) = G(gwarm, WKZ, k) / e;
+                    S(FKY, k) = R > 0.0f ? (G(gwarm, WKY, k) * e / c) / R : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float e = G(gscal, GE + 4 + j, k), R = S(FCR + j, k);
+                    S(FCZ + j, k) = G(gwarm, WCZ + j, k) / e;
+                    S(FCY + j, k) = R > 0.0f ? (G(gwarm, WCY + j, k) * e / c) / R : 0.0f;
+                }
+                if (sp.last) {
+                    zend[0] = G(gwarm, WOZ + 0, k) / G(gscal, GE + 0, k);
+                    zend[1] = G(gwarm, WOZ + 1, k) / G(gscal, GE + 1, k);
+                }
+            }
+        }
+    }
+
+    // z of outgoing row r at the start of a (warm) solve, before the first iteration
+    PQP_DEV float z0_out(bool warm, int r, int k) {
+        return warm ? G(gwarm, WOZ + r, k) / G(gscal, GE + r, k) : 0.0f;
+    }
+
+    // -------------------------------------------------------------- factorisation
+    // Block LDL' of the reduced system in nested-dissection order (see header comment).
+    template <typename T>
+    PQP_DEV bool factor() {
+        const DevParams &P = ka.prm;
+        bool ok = true;
+        // 1. closed-form elimination constants and the effective weights of each stage
+        T Rt[C][3];      // effective outgoing-row weights (row 2 after eliminating u)
+        T Dg[C][6];      // diagonal block of the reduced system (own contributions)
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const T a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                    a12 = S(FA + 4, k), ds = S(FA + 5, k), a22 = sp.a22;
+            const T R0 = S(FOR_ + 0, k), R1 = S(FOR_ + 1, k), R2 = S(FOR_ + 2, k);
+            const T pu = sp.mid ? T(P.w_dkappa) : T(0);
+            const T mu = pu + T(S(FS + 3, k)) + R2 * ds * ds;
+            const T bu = R2 * ds / mu;
+            S(FE + 0, k) = (float)bu;
+            S(FE + 3, k) = (float)(T(1) / mu);
+            const T R2t = R2 - bu * R2 * ds;
+            Rt[k][0] = R0; Rt[k][1] = R1; Rt[k][2] = R2t;
+            T Rc[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool act = j == 0 ? sp.act0 : sp.act1;
+                const T ps = act ? T(P.w_slack) : T(0);
+                const T Rcj = S(FCR + j, k);
+                const T ms = ps + T(S(FS + 4 + j, k)) + Rcj;
+                const T bs = Rcj / ms;
+                S(FE + 1 + j, k) = (float)bs;
+                S(FE + 4 + j, k) = (float)(T(1) / ms);
+                Rc[j] = Rcj - bs * Rcj;
+            }
+            const T h0 = sp.h0, h1 = sp.h1;
+            const T pk = sp.real ? T(P.w_kappa) : T(0), pl = sp.real ? T(P.w_l) : T(0);
+            T *D = Dg[k];
+            D[0] = T(S(FS + 0, k)) + pl + R0 * a00 * a00 + R1 * a10 * a10 + Rc[0] + Rc[1];
+            D[1] = R0 * a00 * a01 + R1 * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
+            D[2] = R1 * a10 * a12;
+            D[3] = T(S(FS + 1, k)) + R0 * a01 * a01 + R1 * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1;
+            D[4] = R1 * a11 * a12;
+            D[5] = T(S(FS + 2, k)) + pk + R1 * a12 * a12 + R2t * a22 * a22 + T(S(FKR, k));
+        }
+        // contribution of the left stage's outgoing rows (-1 entries): diag(Rt_left)
+        T RtL[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) RtL[r] = shfl_up(Rt[C - 1][r], 1, lane);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            if (sp.real) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) Dg[k][SI(r, r)] += (k == 0) ? RtL[r] : Rt[k > 0 ? k - 1 : 0][r];
+            }
+        }
+        // coupling block between stage k and k+1: O[r][c] = gn * Rt_r * Ahat[r][c]
+        auto coupling = [&](int k, T(&O)[9]) {
+            const StagePred sp = pred(k);
+            const T gn = sp.gn;
+            O[0] = gn * Rt[k][0] * T(S(FA + 0, k));
+            O[1] = gn * Rt[k][0] * T(S(FA + 1, k));
+            O[2] = T(0);
+            O[3] = gn * Rt[k][1] * T(S(FA + 2, k));
+            O[4] = gn * Rt[k][1] * T(S(FA + 3, k));
+            O[5] = gn * Rt[k][1] * T(S(FA + 4, k));
+            O[6] = T(0);
+            O[7] = T(0);
+            O[8] = gn * Rt[k][2] * T(sp.a22);
+        };
+        // 2. interior elimination with fill towards the left separator
+        T OL[9];
+        {
+            T Olast[9];
+            coupling(C - 1, Olast);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) OL[j] = shfl_up(Olast[j], 1, lane);
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) OL[j] = T(0);
+            }
+        }
+        T Phi[9];  // M~[SL, current]  (rows: left separator, cols: current stage) = OL'
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Phi[3 * r + c] = OL[3 * c + r];
+        T dA[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        T Dt[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Dt[j] = Dg[0][j];
+#pragma unroll
+        for (int k = 0; k < C - 1; ++k) {
+            T Dinv[6], O[9], Gh[9], Fh[9];
+            ok = inv_sym3(Dt, Dinv) && ok;
+            coupling(k, O);
+            mul_ms(O, Dinv, Gh);
+            mul_ms(Phi, Dinv, Fh);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) S(FDI + j, k) = (float)Dinv[j];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { S(FG + j, k) = (float)Gh[j]; S(FF + j, k) = (float)Fh[j]; }
+            T t6[6], t9[9];
+            mul_abt_sym(Fh, Phi, t6);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) dA[j] += t6[j];
+            mul_abt(Fh, O, t9);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) Phi[j] = -t9[j];
+            mul_abt_sym(Gh, O, t6);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) Dt[j] = Dg[k + 1][j] - t6[j];
+        }
+        // 3. separators: A = own Schur complement - fill from the right neighbour's interior
+        T Acr[6], Ccr[9];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            T dr = shfl_down(dA[j], 1, lane);
+            if (lane == 31) dr = T(0);
+            Acr[j] = Dt[j] - dr;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Ccr[3 * r + c] = Phi[3 * c + r];  // M^[S_l, S_{l-1}]
+        // 4. block cyclic reduction over the 32 separators
+        T myAinv[6] = {T(1), T(0), T(0), T(1), T(0), T(1)};
+        T myGm[9], myGp[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { myGm[j] = T(0); myGp[j] = T(0); }
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int h = 1 << t;
+            const bool elim = (lane & (2 * h - 1)) == h;
+            const bool surv = (lane & (2 * h - 1)) == 0;
+            T Cr[9];  // left coupling of lane+h = M^[l+h, l]
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                Cr[j] = shfl_down(Ccr[j], h, lane);
+                if (lane + h > 31) Cr[j] = T(0);
+            }
+            T Ainv[6], Gm[9], Gp[9], Ct[9];
+            const bool okl = inv_sym3(Acr, Ainv);
+            if (elim) ok = ok && okl;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Ct[3 * r + c] = Ccr[3 * c + r];
+            mul_ms(Ct, Ainv, Gm);  // G- = M^[l-h, l] Ainv = C_l' Ainv
+            mul_ms(Cr, Ainv, Gp);  // G+ = M^[l+h, l] Ainv = C_{l+h} Ainv
+            T Um[6], Up[6], W[9];
+            mul_abt_sym(Gm, Ct, Um);  // G- M^[l, l-h] = G- C_l    = G- (Ct)'
+            mul_abt_sym(Gp, Cr, Up);  // G+ M^[l, l+h] = G+ Cr'
+            mul_abt(Gp, Ct, W);       // G+ C_l = G+ (Ct)'
+            if (elim) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) myAinv[j] = Ainv[j];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) { myGm[j] = Gm[j]; myGp[j] = Gp[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                T fr = shfl_down(elim ? Um[j] : T(0), h, lane);  // from lane+h: its G- C
+                T fl = shfl_up(elim ? Up[j] : T(0), h, lane);    // from lane-h: its G+ Cr'
+                if (lane + h > 31) fr = T(0);
+                if (lane < h) fl = T(0);
+                if (surv) Acr[j] -= fr + fl;
+            }
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                T w = shfl_up(elim ? W[j] : T(0), h, lane);  // from lane-h: G+ C_{l-h}
+                if (lane < h) w = T(0);
+                if (surv) Ccr[j] = -w;
+            }
+        }
+        if (lane == 0) {
+            T Ainv[6];
+            ok = inv_sym3(Acr, Ainv) && ok;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) myAinv[j] = Ainv[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) crAinv[j] = (float)myAinv[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { crGm[j] = (float)myGm[j]; crGp[j] = (float)myGp[j]; }
+        // all lanes must agree
+        float bad = ok ? 0.0f : 1.0f;
+        bad = warp_max(bad, lane);
+        return bad == 0.0f;
+    }
+
+    // -------------------------------------------------------------- solve  M_red x = b (in place)
+    PQP_DEV void solve(float (&b)[C][3]) {
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int k = 0; k < C - 1; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                b[k + 1][r] -= S(FG + 3 * r, k) * b[k][0] + S(FG + 3 * r + 1, k) * b[k][1] + S(FG + 3 * r + 2, k) * b[k][2];
+                acc[r] += S(FF + 3 * r, k) * b[k][0] + S(FF + 3 * r + 1, k) * b[k][1] + S(FF + 3 * r + 2, k) * b[k][2];
+            }
+        }
+        float bs[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float fr = shfl_down(acc[r], 1, lane);
+            if (lane == 31) fr = 0.0f;
+            bs[r] = b[C - 1][r] - fr;
+        }
+        // cyclic reduction, forward
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int h = 1 << t;
+            const bool elim = (lane & (2 * h - 1)) == h;
+            const bool surv = (lane & (2 * h - 1)) == 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
+                float vp = crGp[3 * r] * bs[0] + crGp[3 * r + 1] * bs[1] + crGp[3 * r + 2] * bs[2];
+                vm = elim ? vm : 0.0f;
+                vp = elim ? vp : 0.0f;
+                float fr = shfl_down(vm, h, lane);
+                float fl = shfl_up(vp, h, lane);
+                if (lane + h > 31) fr = 0.0f;
+                if (lane < h) fl = 0.0f;
+                // note: bs is updated after the loop over r would be wrong (vm/vp use old bs)
+                acc[r] = surv ? (fr + fl) : 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) bs[r] -= acc[r];
+        }
+        float ts[3], xs[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            ts[r] = crAinv[SI(r, 0)] * bs[0] + crAinv[SI(r, 1)] * bs[1] + crAinv[SI(r, 2)] * bs[2];
+            xs[r] = ts[r];
+        }
+        // cyclic reduction, backward
+#pragma unroll
+        for (int t = 4; t >= 0; --t) {
+            const int h = 1 << t;
+            const bool elim = (lane & (2 * h - 1)) == h;
+            float xl[3], xr[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                xl[r] = shfl_up(xs[r], h, lane);
+                xr[r] = shfl_down(xs[r], h, lane);
+                if (lane + h > 31) xr[r] = 0.0f;
+            }
+            if (elim) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    xs[c] = ts[c] - (crGm[c] * xl[0] + crGm[3 + c] * xl[1] + crGm[6 + c] * xl[2]) -
+                            (crGp[c] * xr[0] + crGp[3 + c] * xr[1] + crGp[6 + c] * xr[2]);
+            }
+        }
+        // local backward substitution
+        float xSL[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            xSL[r] = shfl_up(xs[r], 1, lane);
+            if (lane == 0) xSL[r] = 0.0f;
+            b[C - 1][r] = xs[r];
+        }
+#pragma unroll
+        for (int k = C - 2; k >= 0; --k) {
+            float t[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                t[r] = S(FDI + SI(r, 0), k) * b[k][0] + S(FDI + SI(r, 1), k) * b[k][1] + S(FDI + SI(r, 2), k) * b[k][2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                b[k][c] = t[c] -
+                          (S(FG + c, k) * b[k + 1][0] + S(FG + 3 + c, k) * b[k + 1][1] + S(FG + 6 + c, k) * b[k + 1][2]) -
+                          (S(FF + c, k) * xSL[0] + S(FF + 3 + c, k) * xSL[1] + S(FF + 6 + c, k) * xSL[2]);
+        }
+    }
+
+    // -------------------------------------------------------------- right-hand side from w
+    // wo[k][0..2]: w of the outgoing rows (row 2 already includes the u-condensation),
+    // partial b holds the stage-local part; adds the left neighbour's rows.
+    PQP_DEV void finish_rhs(float (&b)[C][3], const float (&wo)[C][3]) {
+        float wL[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) wL[r] = shfl_up(wo[C - 1][r], 1, lane);
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            if (sp.real) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) b[k][r] -= (k == 0) ? wL[r] : wo[k > 0 ? k - 1 : 0][r];
+            }
+        }
+    }
+
+    // stage-local part of rhs from the row vectors w (wo: outgoing, wk: kappa, wc: clearance)
+    PQP_DEV void local_rhs(int k, const StagePred &sp, float (&wo)[3], float wk, float (&wc)[2],
+                           float (&bk)[3], float (&aux)[3]) {
+        const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                    a12 = S(FA + 4, k), ds = S(FA + 5, k);
+        const float rhs_u = S(FS + 3, k) * S(FX + 3, k) + ds * wo[2];
+        wo[2] -= S(FE + 0, k) * rhs_u;
+        aux[0] = rhs_u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float rhs_s = S(FS + 4 + j, k) * S(FX + 4 + j, k) + wc[j];
+            wc[j] -= S(FE + 1 + j, k) * rhs_s;
+            aux[1 + j] = rhs_s;
+        }
+        bk[0] = S(FS + 0, k) * S(FX + 0, k) + a00 * wo[0] + a10 * wo[1] + wc[0] + wc[1];
+        bk[1] = S(FS + 1, k) * S(FX + 1, k) + a01 * wo[0] + a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
+        bk[2] = S(FS + 2, k) * S(FX + 2, k) + a12 * wo[1] + sp.a22 * wo[2] + wk;
+    }
+
+    // rhs from the iterates held in shared memory (initial rhs and after a rho update).
+    // `initial`: the outgoing rows' z is z0 (cold: 0, warm: previous z), not yet the bound.
+    PQP_DEV void build_rhs(float (&b)[C][3], float (&aux)[C][3], bool initial, bool warm) {
+        float wo[C][3];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            float wk, wc[2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float z;
+                if (sp.last && r < 2) z = zend[r];
+                else z = initial ? z0_out(warm, r, k) : S(FOB + r, k);
+                wo[k][r] = S(FOR_ + r, k) * (z - S(FOY + r, k));
+            }
+            wk = S(FKR, k) * (S(FKZ, k) - S(FKY, k));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) wc[j] = S(FCR + j, k) * (S(FCZ + j, k) - S(FCY + j, k));
+            local_rhs(k, sp, wo[k], wk, wc, b[k], aux[k]);
+        }
+        finish_rhs(b, wo);
+    }
+
+    // fold z0 != bound of the equality outgoing rows into yhat (exact)
+    PQP_DEV void fold_initial_z(bool warm) {
+        const float oma = 1.0f - ka.prm.alpha;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (!(sp.last && r < 2)) S(FOY + r, k) += oma * (z0_out(warm, r, k) - S(FOB + r, k));
+            }
+        }
+    }
+
+    // -------------------------------------------------------------- one ADMM update
+    // in: b = x~ (state part), aux = rhs of (u, s0, s1) used by that solve
+    // out: iterates advanced in shared memory, b/aux = rhs of the next solve
+    template <bool kStoreDy>
+    PQP_DEV void admm_update(float (&b)[C][3], float (&aux)[C][3]) {
+        const float alpha = ka.prm.alpha, oma = 1.0f - alpha;
+        float xn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            xn[c] = shfl_down(b[0][c], 1, lane);
+            if (lane == 31) xn[c] = 0.0f;
+        }
+        float wo[C][3];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                        a12 = S(FA + 4, k), ds = S(FA + 5, k);
+            const float lt = b[k][0], pt = b[k][1], kt = b[k][2];
+            const float ln = (k == C - 1) ? xn[0] : b[k < C - 1 ? k + 1 : k][0];
+            const float pn = (k == C - 1) ? xn[1] : b[k < C - 1 ? k + 1 : k][1];
+            const float kn = (k == C - 1) ? xn[2] : b[k < C - 1 ? k + 1 : k][2];
+            // recover the eliminated variables of x~
+            const float ut = aux[k][0] * S(FE + 3, k) - S(FE + 0, k) * (sp.a22 * kt + sp.gn * kn);
+            const float s0t = aux[k][1] * S(FE + 4, k) - S(FE + 1, k) * (lt + sp.h0 * pt);
+            const float s1t = aux[k][2] * S(FE + 5, k) - S(FE + 2, k) * (lt + sp.h1 * pt);
+            // z~ = A x~
+            float zo[3];
+            zo[0] = a00 * lt + a01 * pt + sp.gn * ln;
+            zo[1] = a10 * lt + a11 * pt + a12 * kt + sp.gn * pn;
+            zo[2] = sp.a22 * kt + ds * ut + sp.gn * kn;
+            const float zk = sp.real ? kt : 0.0f;
+            float zc[2];
+            zc[0] = sp.act0 ? (lt + sp.h0 * pt + s0t) : 0.0f;
+            zc[1] = sp.act1 ? (lt + sp.h1 * pt + s1t) : 0.0f;
+            // x+ = alpha x~ + (1 - alpha) x
+            const float xt6[6] = {lt, pt, kt, ut, s0t, s1t};
+#pragma unroll
+            for (int j = 0; j < 6; ++j) S(FX + j, k) = alpha * xt6[j] + oma * S(FX + j, k);
+            // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
+            float wk, wc[2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float bnd = S(FOB + r, k), yh = S(FOY + r, k), R = S(FOR_ + r, k);
+                float zn, yn;
+                if (sp.last && r < 2) {
+                    const float zh = alpha * zo[r] + oma * zend[r] + yh;
+                    zn = clampf(zh, bnd, bnd + endw[r]);
+                    yn = zh - zn;
+                    zend[r] = zn;
+                } else {
+                    const float zh = alpha * zo[r] + oma * bnd + yh;
+                    zn = bnd;
+                    yn = zh - bnd;
+                }
+                S(FOY + r, k) = yn;
+                wo[k][r] = R * (zn - yn);
+                if (kStoreDy) G(gdy, r, k) = R * (yn - yh);
+            }
+            {
+                const float z = S(FKZ, k), yh = S(FKY, k), R = S(FKR, k);
+                const float zh = alpha * zk + oma * z + yh;
+                const float zn = clampf(zh, -kmax, kmax);
+                const float yn = zh - zn;
+                S(FKZ, k) = zn;
+                S(FKY, k) = yn;
+                wk = R * (zn - yn);
+                if (kStoreDy) G(gdy, 3, k) = R * (yn - yh);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float z = S(FCZ + j, k), yh = S(FCY + j, k), R = S(FCR + j, k);
+                const float zh = alpha * zc[j] + oma * z + yh;
+                const float zn = clampf(zh, S(FCLO + j, k), S(FCHI + j, k));
+                const float yn = zh - zn;
+                S(FCZ + j, k) = zn;
+                S(FCY + j, k) = yn;
+                wc[j] = R * (zn - yn);
+                if (kStoreDy) G(gdy, 4 + j, k) = R * (yn - yh);
+            }
+            local_rhs(k, sp, wo[k], wk, wc, b[k], aux[k]);
+        }
+        finish_rhs(b, wo);
+    }
+
+    // -------------------------------------------------------------- residuals (OSQP update_info)
+    struct Norms {
+        float pri, ax, z, dua, px, aty;          // unscaled inf-norms
+        float spri, sax, sz, sdua, spx, saty;    // scaled (for the rho estimate)
+    };
+    // y of the left stage's outgoing row r as seen from local stage k
+    PQP_DEV float left_out_y(int r, int k) {
+        if (k > 0) return S(FOR_ + r, k - 1) * S(FOY + r, k - 1);
+        if (lane == 0) return 0.0f;
+        return SL(FOR_ + r, C - 1, lane - 1) * SL(FOY + r, C - 1, lane - 1);
+    }
+    PQP_DEV float next_x(int c, int k) {
+        if (k < C - 1) return S(FX + c, k + 1);
+        if (lane == 31) return 0.0f;
+        return SL(FX + c, 0, lane + 1);
+    }
+    PQP_DEV Norms residuals() {
+        const DevParams &P = ka.prm;
+        sync_warp(lane);
+        float m[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) m[j] = 0.0f;
+        const float c = cscale;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                        a12 = S(FA + 4, k), ds = S(FA + 5, k);
+            const float l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
+                        s0 = S(FX + 4, k), s1 = S(FX + 5, k);
+            const float ln = next_x(0, k), pn = next_x(1, k), kn = next_x(2, k);
+            float ax[6], z[6], y[6];
+            ax[0] = a00 * l + a01 * ps + sp.gn * ln;
+            ax[1] = a10 * l + a11 * ps + a12 * kp + sp.gn * pn;
+            ax[2] = sp.a22 * kp + ds * u + sp.gn * kn;
+            ax[3] = sp.real ? kp : 0.0f;
+            ax[4] = sp.act0 ? (l + sp.h0 * ps + s0) : 0.0f;
+            ax[5] = sp.act1 ? (l + sp.h1 * ps + s1) : 0.0f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                z[r] = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
+                y[r] = S(FOR_ + r, k) * S(FOY + r, k);
+            }
+            z[3] = S(FKZ, k); y[3] = S(FKR, k) * S(FKY, k);
+            z[4] = S(FCZ + 0, k); y[4] = S(FCR + 0, k) * S(FCY + 0, k);
+            z[5] = S(FCZ + 1, k); y[5] = S(FCR + 1, k) * S(FCY + 1, k);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const float e = G(gscal, GE + r, k);
+                const float rp = fabsf(ax[r] - z[r]);
+                m[0] = fmaxf(m[0], rp); m[1] = fmaxf(m[1], fabsf(ax[r])); m[2] = fmaxf(m[2], fabsf(z[r]));
+                m[6] = fmaxf(m[6], e * rp); m[7] = fmaxf(m[7], e * fabsf(ax[r])); m[8] = fmaxf(m[8], e * fabsf(z[r]));
+            }
+            const float hasL = sp.real ? 1.0f : 0.0f;
+            float aty[6], px[6];
+            aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - hasL * left_out_y(0, k);
+            aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - hasL * left_out_y(1, k);
+            aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - hasL * left_out_y(2, k);
+            aty[3] = ds * y[2];
+            aty[4] = sp.act0 ? y[4] : 0.0f;
+            aty[5] = sp.act1 ? y[5] : 0.0f;
+            px[0] = sp.real ? P.w_l * l : 0.0f;
+            px[1] = 0.0f;
+            px[2] = sp.real ? P.w_kappa * kp : 0.0f;
+            px[3] = sp.mid ? P.w_dkappa * u : 0.0f;
+            px[4] = sp.act0 ? P.w_slack * s0 : 0.0f;
+            px[5] = sp.act1 ? P.w_slack * s1 : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float d = c * G(gscal, GD + j, k);
+                const float rd = fabsf(px[j] + aty[j]);
+                m[3] = fmaxf(m[3], rd); m[4] = fmaxf(m[4], fabsf(px[j])); m[5] = fmaxf(m[5], fabsf(aty[j]));
+                m[9] = fmaxf(m[9], d * rd); m[10] = fmaxf(m[10], d * fabsf(px[j])); m[11] = fmaxf(m[11], d * fabsf(aty[j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) m[j] = warp_max(m[j], lane);
+        Norms nr;
+        nr.pri = m[0]; nr.ax = m[1]; nr.z = m[2]; nr.dua = m[3]; nr.px = m[4]; nr.aty = m[5];
+        nr.spri = m[6]; nr.sax = m[7]; nr.sz = m[8]; nr.sdua = m[9]; nr.spx = m[10]; nr.saty = m[11];
+        return nr;
+    }
+
+    // OSQP is_primal_infeasible on the delta_y stored by the last admm_update<true>
+    PQP_DEV bool primal_infeasible(float eps) {
+        sync_warp(lane);
+        const float c = cscale;
+        float nrm = 0.0f, lhs = 0.0f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const int cls = SI32(FCLS, k);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                float dy = G(gdy, r, k);
+                float lo, hi;
+                if (r < 3) { lo = S(FOB + r, k); hi = lo + ((sp.last && r < 2) ? endw[r] : 0.0f); }
+                else if (r == 3) { lo = -kmax; hi = kmax; }
+                else { lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k); }
+                const float e = G(gscal, GE + r, k);
+                const bool hinf = hi * e > kOsqpInfty * kMinScaling, linf = lo * e < -kOsqpInfty * kMinScaling;
+                if (hinf) dy = linf ? 0.0f : fminf(dy, 0.0f);
+                else if (linf) dy = fmaxf(dy, 0.0f);
+                if (((cls >> (2 * r)) & 3) == 3) dy = 0.0f;
+                G(gdy, r, k) = dy;
+                nrm = fmaxf(nrm, fabsf(dy));
+                lhs += (dy > 0.0f ? hi * dy : 0.0f) + (dy < 0.0f ? lo * dy : 0.0f);
+            }
+        }
+        nrm = warp_max(nrm, lane);
+        lhs = warp_sum(lhs, lane);
+        if (!(c * nrm > eps)) return false;
+        if (!(lhs < -eps * nrm)) return false;
+        sync_warp(lane);
+        float mx = 0.0f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                        a12 = S(FA + 4, k), ds = S(FA + 5, k);
+            float y[6], yl[3];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) y[r] = G(gdy, r, k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (k > 0) yl[r] = G(gdy, r, k - 1);
+                else yl[r] = lane == 0 ? 0.0f : GL(gdy, r, C - 1, lane - 1);
+                if (!sp.real) yl[r] = 0.0f;
+            }
+            float aty[6];
+            aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - yl[0];
+            aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - yl[1];
+            aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - yl[2];
+            aty[3] = ds * y[2];
+            aty[4] = y[4];
+            aty[5] = y[5];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) mx = fmaxf(mx, fabsf(aty[j]));
+        }
+        mx = warp_max(mx, lane);
+        return mx < eps * nrm;
+    }
+
+    // OSQP check_termination; returns status or kUnsolved
+    PQP_DEV int check_termination(const Norms &nr, bool approx) {
+        const DevParams &P = ka.prm;
+        float ea = P.eps_abs, er = P.eps_rel, epi = P.eps_pinf;
+        if (!(nr.pri <= kOsqpInfty) || !(nr.dua <= kOsqpInfty)) return kNumerical;
+        if (approx) { ea *= 10.0f; er *= 10.0f; epi *= 10.0f; }
+        const float eps_prim = ea + er * fmaxf(nr.ax, nr.z);
+        const float eps_dual = ea + er * fmaxf(nr.px, nr.aty);
+        const bool pok = nr.pri < eps_prim, dok = nr.dua < eps_dual;
+        bool pinf = false;
+        if (!pok) pinf = primal_infeasible(epi);
+        // dual infeasibility needs q' dx < 0; q = 0 on this path, so it can never trigger
+        if (pok && dok) return approx ? kSolvedInacc : kSolved;
+        if (pinf) return approx ? kPrimInfInacc : kPrimInf;
+        return kUnsolved;
+    }
+
+    // OSQP compute_rho_estimate + update; returns true if rho changed (and refactors)
+    PQP_DEV bool adapt_rho(const Norms &nr, bool &factor_ok) {
+        const DevParams &P = ka.prm;
+        const float pri = nr.spri / (fmaxf(nr.sz, nr.sax) + 1e-10f);
+        const float dua = nr.sdua / (fmaxf(nr.saty, nr.spx) + 1e-10f);
+        float est = rho * sqrtf(pri / (dua + 1e-10f));
+        est = fminf(fmaxf(est, kRhoMin), kRhoMax);
+        if (!(est > rho * P.rho_tol || est < rho / P.rho_tol)) return false;
+        const float ratio = est / rho, rinv = rho / est;
+        rho = est;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int cls = SI32(FCLS, k);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const int cl = (cls >> (2 * r)) & 3;
+                if (cl <= 1) {
+                    if (r < 3) { S(FOR_ + r, k) *= ratio; S(FOY + r, k) *= rinv; }
+                    else if (r == 3) { S(FKR, k) *= ratio; S(FKY, k) *= rinv; }
+                    else { S(FCR + r - 4, k) *= ratio; S(FCY + r - 4, k) *= rinv; }
+                }
+            }
+        }
+        factor_ok = ka.prm.factor_fp64 ? factor<double>() : factor<float>();
+        return true;
+    }
+
+    // -------------------------------------------------------------- whole solve
+    PQP_DEV void run(const double *src, int stride) {
+        const DevParams &P = ka.prm;
+        n = ka.n[qp];
+        p = ka.p ? ka.p[qp] : n;
+        p = p < 0 ? 0 : (p > n ? n : p);
+        lf = (float)P.front_length;
+        lr = (float)P.rear_length;
+        kmax = (float)P.kappa_limit;
+        const size_t plane = (size_t)C * 32;
+        gwarm = ka.warm + (size_t)qp * NWARM * plane;
+        gscal = ka.scal + (size_t)qp * NSCAL * plane;
+        gdy = ka.dy + (size_t)qp * NDY * plane;
+        zend[0] = zend[1] = endw[0] = endw[1] = 0.0f;
+        const bool warm = ka.mode == 1;
+        rho = warm ? ka.rho_state[qp] : P.rho0;
+        rho = fminf(fmaxf(rho, kRhoMin), kRhoMax);
+
+        assemble(src, stride);
+        sync_warp(lane);
+        scale_and_classify();
+        sync_warp(lane);
+        init_iterates(warm);
+        bool fok = P.factor_fp64 ? factor<double>() : factor<float>();
+        sync_warp(lane);
+
+        float b[C][3], aux[C][3];
+        build_rhs(b, aux, true, warm);
+        fold_initial_z(warm);
+
+        int status = fok ? kUnsolved : kNumerical;
+        int iter = 0, rho_updates = 0;
+        Norms nr;
+        nr.pri = nr.dua = 0.0f;
+        bool checked = false;
+        if (fok) {
+            for (iter = 1; iter <= P.max_iter; ++iter) {
+                solve(b);
+                const bool can_check = P.check_every > 0 && (iter % P.check_every == 0);
+                const bool can_adapt = P.adaptive_rho && P.adaptive_interval > 0 &&
+                                       (iter % P.adaptive_interval == 0);
+                if (can_check) admm_update<true>(b, aux);
+                else admm_update<false>(b, aux);
+                checked = false;
+                if (can_check || can_adapt) {
+                    nr = residuals();
+                    if (can_check) {
+                        checked = true;
+                        status = check_termination(nr, false);
+                        if (status != kUnsolved) break;
+                    }
+                    if (can_adapt) {
+                        bool ok2 = true;
+                        if (adapt_rho(nr, ok2)) {
+                            ++rho_updates;
+                            if (!ok2) { status = kNumerical; break; }
+                            sync_warp(lane);
+                            build_rhs(b, aux, false, warm);
+                        }
+                    }
+                }
+            }
+            if (iter > P.max_iter) iter = P.max_iter;
+            if (status == kUnsolved) {
+                if (!checked) {
+                    nr = residuals();
+                    status = check_termination(nr, false);
+                }
+                if (status == kUnsolved) {
+                    status = check_termination(nr, true);
+                    if (status == kUnsolved) status = kMaxIter;
+                }
+            }
+        }
+        epilogue(status, iter, rho_updates, nr);
+    }
+
+    // -------------------------------------------------------------- outputs + warm state
+    PQP_DEV void epilogue(int status, int iter, int rho_updates, const Norms &nr) {
+        const DevParams &P = ka.prm;
+        const int nmax = ka.n_max;
+        const float c = cscale;
+        double *sol = ka.sol + (size_t)qp * 4 * nmax;
+        float cost = 0.0f;
+        const int nvm = 6 * nmax - 1, mm = 6 * nmax + 2;
+        double *xf = ka.x_full ? ka.x_full + (size_t)qp * nvm : nullptr;
+        double *yf = ka.y_full ? ka.y_full + (size_t)qp * mm : nullptr;
+        double *zf = ka.z_full ? ka.z_full + (size_t)qp * mm : nullptr;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const int g = lane * C + k;
+            const StagePred sp = pred(k);
+            const float l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
+                        s0 = S(FX + 4, k), s1 = S(FX + 5, k);
+            if (sp.real) {
+                const int i = g - 1;
+                sol[0 * nmax + i] = (double)l;
+                sol[1 * nmax + i] = (double)ps;
+                sol[2 * nmax + i] = (double)kp;
+                sol[3 * nmax + i] = sp.mid ? (double)u : 0.0;
+                cost += 0.5f * (P.w_l * l * l + P.w_kappa * kp * kp + (sp.mid ? P.w_dkappa * u * u : 0.0f) +
+                                P.w_slack * s0 * s0 + (sp.act1 ? P.w_slack * s1 * s1 : 0.0f));
+                if (xf) {
+                    xf[3 * i] = l; xf[3 * i + 1] = ps; xf[3 * i + 2] = kp;
+                    if (sp.mid) xf[3 * n + i] = u;
+                    if (sp.act1) { xf[4 * n - 1 + 2 * i] = s0; xf[4 * n - 1 + 2 * i + 1] = s1; }
+                    else xf[4 * n - 1 + 2 * p + (i - p)] = s0;
+                }
+            }
+            // rows in the reference's order
+            if (yf || zf) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    int row = -1;
+                    if (g <= n - 1) row = 3 * g + r;           // outgoing rows of stage g = block g
+                    else if (sp.last && r < 2) row = (4 * n + p + n) + r;  // m-2, m-1
+                    if (row >= 0) {
+                        const float z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
+                        if (yf) yf[row] = (double)(S(FOR_ + r, k) * S(FOY + r, k));
+                        if (zf) zf[row] = (double)z;
+                    }
+                }
+                if (sp.real) {
+                    const int i = g - 1;
+                    if (yf) yf[3 * n + i] = (double)(S(FKR, k) * S(FKY, k));
+                    if (zf) zf[3 * n + i] = (double)S(FKZ, k);
+                    const int r0 = sp.act1 ? 4 * n + 2 * i : 4 * n + 2 * p + (i - p);
+                    if (yf) yf[r0] = (double)(S(FCR + 0, k) * S(FCY + 0, k));
+                    if (zf) zf[r0] = (double)S(FCZ + 0, k);
+                    if (sp.act1) {
+                        if (yf) yf[r0 + 1] = (double)(S(FCR + 1, k) * S(FCY + 1, k));
+                        if (zf) zf[r0 + 1] = (double)S(FCZ + 1, k);
+                    }
+                }
+            }
+            // warm state: scaled iterates (x/d, e z, c y / e)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) G(gwarm, WX + j, k) = S(FX + j, k) / G(gscal, GD + j, k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float e = G(gscal, GE + r, k);
+                const float z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
+                G(gwarm, WOZ + r, k) = e * z;
+                G(gwarm, WOY + r, k) = c * S(FOR_ + r, k) * S(FOY + r, k) / e;
+            }
+            {
+                const float e = G(gscal, GE + 3, k);
+                G(gwarm, WKZ, k) = e * S(FKZ, k);
+                G(gwarm, WKY, k) = c * S(FKR, k) * S(FKY, k) / e;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float e = G(gscal, GE + 4 + j, k);
+                G(gwarm, WCZ + j, k) = e * S(FCZ + j, k);
+                G(gwarm, WCY + j, k) = c * S(FCR + j, k) * S(FCY + j, k) / e;
+            }
+        }
+        cost = warp_sum(cost, lane);
+        if (lane == 0) {
+            if (ka.cost) ka.cost[qp] = (double)cost;
+            if (ka.status) ka.status[qp] = status;
+            if (ka.iters) ka.iters[qp] = iter;
+            if (ka.info) {
+                double *inf = ka.info + (size_t)qp * 4;
+                inf[0] = nr.pri; inf[1] = nr.dua; inf[2] = rho; inf[3] = rho_updates;
+            }
+            ka.rho_state[qp] = rho;
+        }
+    }
+};
+
+}  // namespace pqp

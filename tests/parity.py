@@ -1,0 +1,67 @@
+"""Parity checks shared by the emulator tests (CPU) and the GPU tests.
+
+Parity definition (iterates of two ADMM runs are not comparable bit for bit,
+the converged point is): for every instance
+  (1) status equals the oracle's status;
+  (2) when solved, the returned (x, y, z) passes OSQP's own unscaled termination test with
+      the reference's eps_abs = eps_rel = 2e-3 (base_solver.cpp:61-62), evaluated in FP64 on
+      the ORACLE-assembled (P, A, l, u), with a 1.25x allowance for the kernel's FP32 norms;
+  (3) the objective agrees with the oracle's within 1 % (+1e-3 absolute);
+  (4) x agrees with the oracle's x at the same tolerance within max(1e-2, 2 x the oracle's own
+      distance to the eps=1e-9 minimiser) when a high-accuracy solution is supplied;
+  (5) sol (l, psi, kappa, u per knot) is consistent with x_full.
+"""
+import numpy as np
+
+from oracle import oracle
+from path_optimizer_2_b200 import abi
+
+
+def oracle_reference(params, hb, b, warm_from=None):
+    p = None if hb.p is None else int(hb.p[b])
+    s = oracle.OracleSolver(params, hb.knots[b], hb.inst[b], int(hb.n[b]), p)
+    s.solve()
+    if warm_from is not None:
+        s.update(warm_from[0], warm_from[1], warm_from[2])
+        s.solve()
+    return s
+
+
+def check_instance(params, hb, res, b, *, oracle_solver, x_star=None, label=""):
+    s = oracle_solver
+    n = int(hb.n[b])
+    nv, m = s.nv, s.m
+    tag = "%s inst %d (n=%d)" % (label, b, n)
+    assert int(res.status[b]) == s.status, "%s: status %d vs oracle %d" % (tag, res.status[b], s.status)
+    if s.status != abi.PQP_SOLVED:
+        return dict(iters=int(res.iters[b]), oracle_iters=s.iters)
+    Pd, A, l, u = s.problem()
+    x, y, z = res.x_full[b, :nv], res.y_full[b, :m], res.z_full[b, :m]
+    rep = oracle.osqp_termination_report(Pd, A, l, u, x, y, z, params.eps_abs, params.eps_rel)
+    assert rep["pri_res"] < 1.25 * rep["eps_pri"], "%s: primal residual %g > %g" % (tag, rep["pri_res"], rep["eps_pri"])
+    assert rep["dua_res"] < 1.25 * rep["eps_dua"], "%s: dual residual %g > %g" % (tag, rep["dua_res"], rep["eps_dua"])
+    span = np.maximum(1.0, np.maximum(np.abs(l), np.abs(u)))
+    finite = (np.abs(l) < 1e29) & (np.abs(u) < 1e29)
+    assert np.all((z >= l - 1e-5 * span)[finite]) and np.all((z <= u + 1e-5 * span)[finite]), tag + ": z outside [l, u]"
+    cost_gpu = 0.5 * float(np.dot(Pd * x, x))
+    assert abs(cost_gpu - res.cost[b]) <= 1e-3 * max(1.0, abs(cost_gpu)), tag + ": reported cost inconsistent"
+    assert abs(cost_gpu - s.cost) <= 0.01 * abs(s.cost) + 1e-3, "%s: cost %g vs oracle %g" % (tag, cost_gpu, s.cost)
+    dx = float(np.max(np.abs(x - s.x())))
+    if x_star is not None:
+        env = max(1e-2, 2.0 * float(np.max(np.abs(s.x() - x_star))))
+        d_star = float(np.max(np.abs(x - x_star)))
+        assert d_star <= env, "%s: |x - x*| = %g > envelope %g" % (tag, d_star, env)
+    # sol block vs x_full
+    sol = res.sol[b]
+    assert np.allclose(sol[0, :n], x[0:3 * n:3], atol=1e-12)
+    assert np.allclose(sol[1, :n], x[1:3 * n:3], atol=1e-12)
+    assert np.allclose(sol[2, :n], x[2:3 * n:3], atol=1e-12)
+    assert np.allclose(sol[3, :n - 1], x[3 * n:4 * n - 1], atol=1e-12)
+    return dict(iters=int(res.iters[b]), oracle_iters=s.iters, dx=dx, pri=rep["pri_res"], dua=rep["dua_res"])
+
+
+def high_accuracy_x(params_hi, hb, b):
+    p = None if hb.p is None else int(hb.p[b])
+    s = oracle.OracleSolver(params_hi, hb.knots[b], hb.inst[b], int(hb.n[b]), p)
+    s.solve()
+    return s.x()

@@ -1,0 +1,128 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+from path_optimizer_2_b200 import abi, synthetic
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver_mod():
+    from path_optimizer_2_b200 import solver
+    return solver
+
+
+def _run_and_check(solver_mod, hb, params, label, warm=True, check_all=True, max_check=16):
+    sv = solver_mod.PathQpSolver(params, n_max=hb.n_max, batch_max=hb.batch)
+    res = sv.solve(hb, full=True)
+    idx = range(hb.batch) if check_all else range(0, hb.batch, max(1, hb.batch // max_check))
+    stats = []
+    for b in idx:
+        s = parity.oracle_reference(params, hb, b)
+        stats.append(parity.check_instance(params, hb, res, b, oracle_solver=s, label=label))
+    if warm:
+        hb2 = hb.with_linearisation(res.sol)
+        res2 = sv.resolve(hb2, full=True)
+        for b in idx:
+            s = parity.oracle_reference(params, hb, b)
+            if s.status != abi.PQP_SOLVED:
+                continue
+            sol = s.sol()
+            s.update(sol[0], sol[1], sol[2])
+            s.solve()
+            parity.check_instance(params, hb2, res2, b, oracle_solver=s, label=label + " warm")
+    assert sv.launch_count >= 1
+    sv.close()
+    return stats
+
+
+@pytest.mark.parametrize("n", [2, 3, 20, 31, 32, 63, 64, 120, 127, 128, 240, 255])
+def test_cold_and_warm_parity(solver_mod, n):
+    hb = synthetic.make_batch(100 + n, 6, n)
+    _run_and_check(solver_mod, hb, abi.default_params(), "n=%d" % n)
+
+
+def test_ragged_batch(solver_mod):
+    hb = synthetic.make_batch(7, 24, 120, ragged=True)
+    assert len(set(hb.n.tolist())) > 4
+    _run_and_check(solver_mod, hb, abi.default_params(), "ragged")
+
+
+def test_rough_constraints(solver_mod):
+    hb = synthetic.make_batch(8, 6, 90)
+    hb.p = np.array([30, 60, 0, 90, 1, 89], dtype=np.int32)
+    _run_and_check(solver_mod, hb, abi.default_params(), "rough")
+
+
+def test_odd_n_max_uses_plain_loads(solver_mod):
+    hb = synthetic.make_batch(9, 4, 121)  # 9*121*8 bytes is not a multiple of 16 -> no TMA
+    _run_and_check(solver_mod, hb, abi.default_params(), "odd")
+
+
+def test_max_iter_status(solver_mod):
+    params = abi.default_params(max_iter=50)
+    hb = synthetic.make_batch(3, 8, 240)
+    _run_and_check(solver_mod, hb, params, "cap50", warm=False)
+
+
+def test_envelope_against_high_accuracy(solver_mod):
+    params = abi.default_params()
+    hi = abi.default_params(eps_abs=1e-9, eps_rel=1e-9, max_iter=200000)
+    hb = synthetic.make_batch(3, 6, 120)
+    sv = solver_mod.PathQpSolver(params, n_max=120, batch_max=6)
+    res = sv.solve(hb, full=True)
+    for b in range(hb.batch):
+        s = parity.oracle_reference(params, hb, b)
+        parity.check_instance(params, hb, res, b, oracle_solver=s, x_star=parity.high_accuracy_x(hi, hb, b))
+    sv.close()
+
+
+def test_config3_sampled(solver_mod):
+    """BASELINE config[2] (B=8192, n=240) at full size: every instance must report a status,
+    solved instances are spot-checked against the oracle."""
+    params = abi.default_params()
+    hb = synthetic.make_batch(3, 8192, 240)
+    sv = solver_mod.PathQpSolver(params, n_max=240, batch_max=8192)
+    res = sv.solve(hb, full=True)
+    assert np.all(res.status != abi.PQP_UNSOLVED)
+    assert np.mean(res.status == abi.PQP_SOLVED) > 0.95
+    for b in range(0, 8192, 512):
+        s = parity.oracle_reference(params, hb, b)
+        parity.check_instance(params, hb, res, b, oracle_solver=s, label="cfg3")
+    sv.close()
+
+
+def test_frenet_to_cartesian(solver_mod):
+    from oracle import oracle
+    hb, ref = synthetic.make_batch(3, 4, 120, with_ref=True)
+    sv = solver_mod.PathQpSolver(abi.default_params(), n_max=120, batch_max=4)
+    res = sv.solve(hb)
+    out = sv.frenet_to_cartesian(hb.n, ref, res.sol)
+    for b in range(4):
+        n = int(hb.n[b])
+        exp = oracle.frenet_to_cartesian(ref[b][:, :n], res.sol[b, 0, :n], res.sol[b, 1, :n])
+        assert np.allclose(out[b][:, :n], exp, atol=1e-12, rtol=0)
+    sv.close()
+
+
+def test_api_errors(solver_mod):
+    params = abi.default_params()
+    with pytest.raises(solver_mod.PqpError):
+        solver_mod.PathQpSolver(params, n_max=1, batch_max=4)
+    with pytest.raises(solver_mod.PqpError):
+        solver_mod.PathQpSolver(params, n_max=300, batch_max=4)
+    sv = solver_mod.PathQpSolver(params, n_max=60, batch_max=2)
+    hb = synthetic.make_batch(3, 2, 60)
+    with pytest.raises(solver_mod.PqpError):  # resolve before solve
+        sv.resolve(hb)
+    bad = synthetic.make_batch(3, 2, 60)
+    bad.n[0] = 1
+    with pytest.raises(solver_mod.PqpError):
+        sv.solve(bad)
+    with pytest.raises(solver_mod.PqpError):  # batch too large
+        sv.solve(synthetic.make_batch(3, 3, 60))
+    sv.solve(hb)
+    sv.resolve(None, batch=2)  # relinearise about the device-resident solution
+    sv.close()
