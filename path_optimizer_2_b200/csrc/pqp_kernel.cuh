@@ -901,41 +901,44 @@ struct QpWarp {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const float bnd = S(FOB + r, k), yh = S(FOY + r, k), R = S(FOR_ + r, k);
-                float zn, yn;
+                float zn, yn, zt;
                 if (sp.last && r < 2) {
-                    const float zh = alpha * zo[r] + oma * zend[r] + yh;
+                    zt = alpha * zo[r] + oma * zend[r];
+                    const float zh = zt + yh;
                     zn = clampf(zh, bnd, bnd + endw[r]);
                     yn = zh - zn;
                     zend[r] = zn;
                 } else {
-                    const float zh = alpha * zo[r] + oma * bnd + yh;
+                    zt = alpha * zo[r] + oma * bnd;
                     zn = bnd;
-                    yn = zh - bnd;
+                    yn = (zt + yh) - bnd;
                 }
                 S(FOY + r, k) = yn;
                 wo[k][r] = R * (zn - yn);
-                if (kStoreDy) G(gdy, r, k) = R * (yn - yh);
+                if (kStoreDy) G(gdy, r, k) = R * (zt - zn);  // delta_y without cancellation
             }
             {
                 const float z = S(FKZ, k), yh = S(FKY, k), R = S(FKR, k);
-                const float zh = alpha * zk + oma * z + yh;
+                const float zt = alpha * zk + oma * z;
+                const float zh = zt + yh;
                 const float zn = clampf(zh, -kmax, kmax);
                 const float yn = zh - zn;
                 S(FKZ, k) = zn;
                 S(FKY, k) = yn;
                 wk = R * (zn - yn);
-                if (kStoreDy) G(gdy, 3, k) = R * (yn - yh);
+                if (kStoreDy) G(gdy, 3, k) = R * (zt - zn);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const float z = S(FCZ + j, k), yh = S(FCY + j, k), R = S(FCR + j, k);
-                const float zh = alpha * zc[j] + oma * z + yh;
+                const float zt = alpha * zc[j] + oma * z;
+                const float zh = zt + yh;
                 const float zn = clampf(zh, S(FCLO + j, k), S(FCHI + j, k));
                 const float yn = zh - zn;
                 S(FCZ + j, k) = zn;
                 S(FCY + j, k) = yn;
                 wc[j] = R * (zn - yn);
-                if (kStoreDy) G(gdy, 4 + j, k) = R * (yn - yh);
+                if (kStoreDy) G(gdy, 4 + j, k) = R * (zt - zn);
             }
             local_rhs(k, sp, wo[k], wk, wc, b[k], aux[k]);
         }
@@ -1053,6 +1056,9 @@ struct QpWarp {
         }
         nrm = warp_max(nrm, lane);
         lhs = warp_sum(lhs, lane);
+#ifdef PQP_EMU_DEBUG
+        if (lane == 0) printf("  pinf: c*nrm=%g lhs=%g thr=%g\n", c * nrm, lhs, -eps * nrm);
+#endif
         if (!(c * nrm > eps)) return false;
         if (!(lhs < -eps * nrm)) return false;
         sync_warp(lane);
@@ -1082,6 +1088,9 @@ struct QpWarp {
             for (int j = 0; j < 6; ++j) mx = fmaxf(mx, fabsf(aty[j]));
         }
         mx = warp_max(mx, lane);
+#ifdef PQP_EMU_DEBUG
+        if (lane == 0) printf("  pinf: |A'dy|=%g thr=%g\n", mx, eps * nrm);
+#endif
         return mx < eps * nrm;
     }
 

@@ -1,0 +1,68 @@
+"""The C-ABI shared library: loads on a CPU-only box, exports every symbol declared in
+include/pqp.h, agrees with the Python mirror of the parameter struct, and fails loudly (no CPU
+fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from path_optimizer_2_b200 import abi, solver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    solver.build_library()
+    return solver.load_library()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pqp.h")).read()
+    declared = set(re.findall(r"\b(pqp_[a-z_0-9]+)\s*\(", header))
+    declared -= {"pqp_handle", "pqp_params", "pqp_batch_in", "pqp_batch_out"}
+    assert declared == set(solver.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.pqp_version() == 1
+
+
+def test_default_params_match_python_mirror(lib):
+    p = abi.PqpParams()
+    assert lib.pqp_default_params(C.byref(p)) == 0
+    q = abi.default_params()
+    for name, _ in abi.PqpParams._fields_:
+        assert getattr(p, name) == pytest.approx(getattr(q, name)), name
+    assert C.sizeof(abi.PqpParams) == 19 * 8 + 6 * 4
+
+
+def test_library_contains_sm100a_code_and_tma():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", solver.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", solver.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk global->shared (TMA 1-D bulk copy)
+    assert "SHFL" in sass            # warp-shuffle cyclic reduction / norm reductions
+
+
+def test_no_cpu_fallback_without_device(lib):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(solver.PqpError) as ei:
+        solver.PathQpSolver(n_max=120, batch_max=4)
+    assert ei.value.code == abi.PQP_E_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "path_optimizer_2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "pqp_oracle", "libpqp_oracle", "pqo_"):
+                    assert needle not in text, "%s mentions %s" % (f, needle)
