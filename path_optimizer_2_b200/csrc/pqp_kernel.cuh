@@ -16,6 +16,8 @@
 //     nested-dissection order: each lane eliminates its C-1 interior stages serially,
 //     the 32 separator stages are eliminated by block cyclic reduction across lanes
 //     with warp shuffles;
+//   * per-stage loops are rolled and the solve vectors live in shared memory so that the hot
+//     loop is a few hundred instructions (the unrolled first version was I-cache bound);
 //   * iterates are kept in *unscaled* variables; OSQP's Ruiz scaling (D, E, c) appears as
 //     per-row weights R_i = rho_i e_i^2 / c and per-variable weights S_j = sigma/(c d_j^2),
 //     which is algebraically identical to OSQP's iteration on the scaled problem;
@@ -60,17 +62,19 @@ enum : int {
     FX = 0,     // 6: l, psi, kappa, u, s0, s1           (primal iterate x)
     FA = 6,     // 6: a00 a01 a10 a11 a12 ds             (stage transition coefficients)
     FS = 12,    // 6: S_j = sigma / (c d_j^2)            (proximal weights)
-    FE = 18,    // 6: bu bs0 bs1 1/m_u 1/m_s0 1/m_s1     (closed-form elimination constants)
-    FOB = 24,   // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
-    FOY = 27,   // 3: outgoing-row scaled dual yhat
-    FOR_ = 30,  // 3: outgoing-row weight R
-    FKZ = 33, FKY = 34, FKR = 35,                       // kappa box row: z, yhat, R
-    FCLO = 36, FCHI = 38, FCZ = 40, FCY = 42, FCR = 44,  // clearance rows (2 each)
-    FCLS = 46,  // row class bitmask (int bits 2r..2r+1: 0 ineq, 1 eq, 2 loose, 3 inactive)
-    FDI = 47,   // 6: inverse pivot block (sym)
-    FG = 53,    // 9: multiplier to the next stage
-    FF = 62,    // 9: multiplier to the left separator (fill)
-    NFIELD = 71
+    FE = 18,    // 3: 1/m_u 1/m_s0 1/m_s1                (closed-form elimination constants)
+    FOB = 21,   // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
+    FOY = 24,   // 3: outgoing-row scaled dual yhat
+    FOR_ = 27,  // 3: outgoing-row weight R
+    FKZ = 30, FKY = 31, FKR = 32,                       // kappa box row: z, yhat, R
+    FCLO = 33, FCHI = 35, FCZ = 37, FCY = 39, FCR = 41,  // clearance rows (2 each)
+    FB = 43,    // 3: rhs of the reduced system / x~ after the solve
+    FAUX = 46,  // 3: rhs of the eliminated variables (u, s0, s1)
+    FDI = 49,   // 6: inverse pivot block (sym)
+    FG = 55,    // 9: multiplier to the next stage
+    FF = 64,    // 9: multiplier to the left separator (fill)
+    NFIELD = 73,
+    FT = FDI    // the 24 factor fields double as input staging and as Ruiz scratch
 };
 // global per-QP scratch, same [field][k][lane] layout
 enum : int {
@@ -80,7 +84,7 @@ enum : int {
     WKZ = 12, WKY = 13,
     WCZ = 14, WCY = 16,
     NWARM = 18,
-    GD = 0, GE = 6, NSCAL = 12,  // D (6 vars), E (6 rows)
+    GD = 0, GE = 6, GCLS = 12, NSCAL = 13,  // D (6 vars), E (6 rows), row-class bitmask (int)
     NDY = 6
 };
 
@@ -233,6 +237,11 @@ PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, doubl
 }
 
 // =========================================================================================
+// All per-stage loops are deliberately NOT unrolled (#pragma unroll 1): the first version of
+// this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction
+// cache (40 % no_inst stalls in profiles/r1/ncu_v1_unrolled_summary.txt).
+#define PQP_ROLL _Pragma("unroll 1")
+
 template <int C>
 struct QpWarp {
     const KernelArgs &ka;
@@ -253,9 +262,9 @@ struct QpWarp {
 
     PQP_DEV float &S(int f, int k) { return sm[(f * C + k) * 32 + lane]; }
     PQP_DEV float &SL(int f, int k, int ln) { return sm[(f * C + k) * 32 + ln]; }
-    PQP_DEV int &SI32(int f, int k) { return reinterpret_cast<int *>(sm)[(f * C + k) * 32 + lane]; }
     PQP_DEV float &G(float *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
     PQP_DEV float &GL(float *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
+    PQP_DEV int &GCLSI(int k) { return reinterpret_cast<int *>(gscal)[(GCLS * C + k) * 32 + lane]; }
     PQP_DEV StagePred pred(int k) const { return stage_pred(lane * C + k, n, p, lf, lr); }
 
     // -------------------------------------------------------------- assembly
@@ -263,7 +272,7 @@ struct QpWarp {
     PQP_DEV void assemble(const double *src, int stride) {
         const DevParams &P = ka.prm;
         const double *in = ka.inst + (size_t)qp * 5;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const int g = lane * C + k;
             float a[6] = {0, 0, 0, 0, 0, 0};
@@ -331,47 +340,41 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- Ruiz equilibration
-    // OSQP scale_data on the structured matrix; leaves D, E in global
-    // scratch, and row weights R / classes / S in shared memory.
+    // OSQP scale_data on the structured matrix. d and e ping-pong between
+    // two halves of the (still unused) factor region; D, E end up in global scratch, row
+    // weights R / classes / S in shared memory.
     PQP_DEV void scale_and_classify() {
         const DevParams &P = ka.prm;
-        float d[C][6], e[C][6];
+        PQP_ROLL
+        for (int k = 0; k < C; ++k) {
 #pragma unroll
-        for (int k = 0; k < C; ++k)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) { d[k][j] = 1.0f; e[k][j] = 1.0f; }
+            for (int j = 0; j < 12; ++j) S(FT + j, k) = 1.0f;
+        }
         float c = 1.0f;
         const float nv_inv = 1.0f / (float)(3 * n + (n - 1) + (p + n));
+        int cur = 0;
         for (int pass = 0; pass < P.scaling; ++pass) {
-            // neighbour data: e of the left stage's outgoing rows, d of the right stage's x
-            float eLb[3], dRb[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                eLb[r] = shfl_up(e[C - 1][r], 1, lane);
-                dRb[r] = shfl_down(d[0][r], 1, lane);
-            }
-            if (lane == 0) { eLb[0] = eLb[1] = eLb[2] = 0.0f; }
-            if (lane == 31) { dRb[0] = dRb[1] = dRb[2] = 0.0f; }
-            float dn[C][6], en[C][6];
+            sync_warp(lane);
+            const int FD0 = FT + 12 * cur, FE0 = FD0 + 6, FD1 = FT + 12 * (1 - cur), FE1 = FD1 + 6;
             float psum = 0.0f;
-#pragma unroll
+            PQP_ROLL
             for (int k = 0; k < C; ++k) {
                 const StagePred sp = pred(k);
                 const float a00 = fabsf(S(FA + 0, k)), a01 = fabsf(S(FA + 1, k)), a10 = fabsf(S(FA + 2, k)),
                             a11 = fabsf(S(FA + 3, k)), a12 = fabsf(S(FA + 4, k)), ds = fabsf(S(FA + 5, k));
                 const float gn = fabsf(sp.gn), h0 = fabsf(sp.h0), h1 = fabsf(sp.h1);
-                const float *dk = d[k], *ek = e[k];
-                float eL[3], dR[3];
+                float dk[6], ek[6], eL[3], dR[3];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { dk[j] = S(FD0 + j, k); ek[j] = S(FE0 + j, k); }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    eL[r] = (k == 0) ? eLb[r] : e[k > 0 ? k - 1 : 0][r];
-                    dR[r] = (k == C - 1) ? dRb[r] : d[k < C - 1 ? k + 1 : k][r];
+                    eL[r] = (k > 0) ? S(FE0 + r, k > 0 ? k - 1 : 0) : (lane > 0 ? SL(FE0 + r, C - 1, lane > 0 ? lane - 1 : 0) : 0.0f);
+                    dR[r] = (k < C - 1) ? S(FD0 + r, k < C - 1 ? k + 1 : k) : (lane < 31 ? SL(FD0 + r, 0, lane < 31 ? lane + 1 : lane) : 0.0f);
                 }
                 // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
                 const float hasL = sp.real ? 1.0f : 0.0f;
                 const float ec0 = sp.act0 ? ek[4] : 0.0f, ec1 = sp.act1 ? ek[5] : 0.0f;
                 const float ekap = sp.real ? ek[3] : 0.0f;
-                // column norms of [P; A]
                 float cn[6];
                 cn[0] = dk[0] * fmaxf(fmaxf(a00 * ek[0], a10 * ek[1]), fmaxf(hasL * eL[0], fmaxf(ec0, ec1)));
                 cn[1] = dk[1] * fmaxf(fmaxf(a01 * ek[0], a11 * ek[1]), fmaxf(hasL * eL[1], fmaxf(h0 * ec0, h1 * ec1)));
@@ -384,7 +387,6 @@ struct QpWarp {
                                      sp.act1 ? P.w_slack : 0.0f};
 #pragma unroll
                 for (int j = 0; j < 6; ++j) cn[j] = fmaxf(cn[j], c * dk[j] * dk[j] * pw[j]);
-                // row norms of A
                 float rn[6];
                 rn[0] = ek[0] * fmaxf(fmaxf(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
                 rn[1] = ek[1] * fmaxf(fmaxf(a10 * dk[0], a11 * dk[1]), fmaxf(a12 * dk[2], gn * dR[1]));
@@ -394,33 +396,35 @@ struct QpWarp {
                 rn[5] = ec1 * fmaxf(fmaxf(dk[0], h1 * dk[1]), dk[5]);
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    dn[k][j] = dk[j] * frsqrt(limit_scaling(cn[j]));
-                    en[k][j] = ek[j] * frsqrt(limit_scaling(rn[j]));
-                    psum += dn[k][j] * dn[k][j] * pw[j];
+                    const float dnw = dk[j] * frsqrt(limit_scaling(cn[j]));
+                    S(FD1 + j, k) = dnw;
+                    S(FE1 + j, k) = ek[j] * frsqrt(limit_scaling(rn[j]));
+                    psum += dnw * dnw * pw[j];
                 }
             }
-#pragma unroll
-            for (int k = 0; k < C; ++k)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { d[k][j] = dn[k][j]; e[k][j] = en[k][j]; }
             // cost normalisation: c_temp = 1 / limit(max(mean_j |Pbar_jj|, 1))   (q = 0 -> 1)
             const float mean = c * warp_sum(psum, lane) * nv_inv;
             float ct = fmaxf(mean, 1.0f);
             ct = limit_scaling(ct);
             c = c / ct;
+            cur = 1 - cur;
         }
+        sync_warp(lane);
         cscale = c;
-        // weights, classes, S; D and E to global scratch
+        const int FDc = FT + 12 * cur, FEc = FDc + 6;
         const float cinv = 1.0f / c;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             int cls = 0;
+            float e[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                G(gscal, GD + j, k) = d[k][j];
-                G(gscal, GE + j, k) = e[k][j];
-                S(FS + j, k) = ka.prm.sigma * cinv / (d[k][j] * d[k][j]);
+                const float d = S(FDc + j, k);
+                e[j] = S(FEc + j, k);
+                G(gscal, GD + j, k) = d;
+                G(gscal, GE + j, k) = e[j];
+                S(FS + j, k) = ka.prm.sigma * cinv / (d * d);
             }
             // dummy variables get an identity pivot
             if (!sp.real) { S(FS + 0, k) = 1.0f; S(FS + 1, k) = 1.0f; S(FS + 2, k) = 1.0f; S(FS + 4, k) = 1.0f; }
@@ -440,7 +444,7 @@ struct QpWarp {
                     lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k);
                     act = (r == 4) ? sp.act0 : sp.act1;
                 }
-                const float ls = lo * e[k][r], hs = hi * e[k][r];
+                const float ls = lo * e[r], hs = hi * e[r];
                 int cl;
                 if (!act) cl = 3;
                 else if (ls < -kOsqpInfty * kMinScaling && hs > kOsqpInfty * kMinScaling) cl = 2;
@@ -448,19 +452,19 @@ struct QpWarp {
                 else cl = 0;
                 cls |= cl << (2 * r);
                 const float base = (cl == 3) ? 0.0f : (cl == 2 ? kRhoMin : (cl == 1 ? kRhoEqOverIneq * rho : rho));
-                const float Rw = base * e[k][r] * e[k][r] * cinv;
+                const float Rw = base * e[r] * e[r] * cinv;
                 if (r < 3) S(FOR_ + r, k) = Rw;
                 else if (r == 3) S(FKR, k) = Rw;
                 else S(FCR + r - 4, k) = Rw;
             }
-            SI32(FCLS, k) = cls;
+            GCLSI(k) = cls;
         }
     }
 
     // -------------------------------------------------------------- iterates: cold / warm
     PQP_DEV void init_iterates(bool warm) {
         const float c = cscale;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             if (!warm) {
@@ -508,85 +512,83 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- factorisation
+    // effective outgoing-row weights of stage k (row 2 after eliminating u); also stores the
+    // elimination constants of u when `store`
+    template <typename T>
+    PQP_DEV void stage_rt(int k, const StagePred &sp, T (&Rt)[3], bool store) {
+        const DevParams &P = ka.prm;
+        const T ds = S(FA + 5, k);
+        const T R2 = S(FOR_ + 2, k);
+        const T pu = sp.mid ? T(P.w_dkappa) : T(0);
+        const T mu = pu + T(S(FS + 3, k)) + R2 * ds * ds;
+        const T miu = T(1) / mu;
+        if (store) S(FE + 0, k) = (float)miu;
+        Rt[0] = S(FOR_ + 0, k);
+        Rt[1] = S(FOR_ + 1, k);
+        Rt[2] = R2 - (R2 * ds * miu) * R2 * ds;
+    }
+    // diagonal block of the reduced system of stage k (own rows + diag(RtL) of the left stage)
+    template <typename T>
+    PQP_DEV void stage_diag(int k, const StagePred &sp, const T (&Rt)[3], const T (&RtL)[3], T (&D)[6]) {
+        const DevParams &P = ka.prm;
+        const T a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+                a12 = S(FA + 4, k), a22 = sp.a22;
+        T Rc[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool act = j == 0 ? sp.act0 : sp.act1;
+            const T ps = act ? T(P.w_slack) : T(0);
+            const T Rcj = S(FCR + j, k);
+            const T ms = ps + T(S(FS + 4 + j, k)) + Rcj;
+            const T mis = T(1) / ms;
+            S(FE + 1 + j, k) = (float)mis;
+            Rc[j] = Rcj - (Rcj * mis) * Rcj;
+        }
+        const T h0 = sp.h0, h1 = sp.h1;
+        const T pk = sp.real ? T(P.w_kappa) : T(0), pl = sp.real ? T(P.w_l) : T(0);
+        const T hasL = sp.real ? T(1) : T(0);
+        D[0] = T(S(FS + 0, k)) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
+        D[1] = Rt[0] * a00 * a01 + Rt[1] * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
+        D[2] = Rt[1] * a10 * a12;
+        D[3] = T(S(FS + 1, k)) + Rt[0] * a01 * a01 + Rt[1] * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1 + hasL * RtL[1];
+        D[4] = Rt[1] * a11 * a12;
+        D[5] = T(S(FS + 2, k)) + pk + Rt[1] * a12 * a12 + Rt[2] * a22 * a22 + T(S(FKR, k)) + hasL * RtL[2];
+    }
+    // coupling block between stage k and k+1: O[r][c] = gn * Rt_r * Ahat[r][c]
+    template <typename T>
+    PQP_DEV void stage_coupling(int k, const StagePred &sp, const T (&Rt)[3], T (&O)[9]) {
+        const T gn = sp.gn;
+        O[0] = gn * Rt[0] * T(S(FA + 0, k));
+        O[1] = gn * Rt[0] * T(S(FA + 1, k));
+        O[2] = T(0);
+        O[3] = gn * Rt[1] * T(S(FA + 2, k));
+        O[4] = gn * Rt[1] * T(S(FA + 3, k));
+        O[5] = gn * Rt[1] * T(S(FA + 4, k));
+        O[6] = T(0);
+        O[7] = T(0);
+        O[8] = gn * Rt[2] * T(sp.a22);
+    }
+
     // Block LDL' of the reduced system in nested-dissection order (see header comment).
     template <typename T>
     PQP_DEV bool factor() {
-        const DevParams &P = ka.prm;
         bool ok = true;
-        // 1. closed-form elimination constants and the effective weights of each stage
-        T Rt[C][3];      // effective outgoing-row weights (row 2 after eliminating u)
-        T Dg[C][6];      // diagonal block of the reduced system (own contributions)
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-            const T a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
-                    a12 = S(FA + 4, k), ds = S(FA + 5, k), a22 = sp.a22;
-            const T R0 = S(FOR_ + 0, k), R1 = S(FOR_ + 1, k), R2 = S(FOR_ + 2, k);
-            const T pu = sp.mid ? T(P.w_dkappa) : T(0);
-            const T mu = pu + T(S(FS + 3, k)) + R2 * ds * ds;
-            const T bu = R2 * ds / mu;
-            S(FE + 0, k) = (float)bu;
-            S(FE + 3, k) = (float)(T(1) / mu);
-            const T R2t = R2 - bu * R2 * ds;
-            Rt[k][0] = R0; Rt[k][1] = R1; Rt[k][2] = R2t;
-            T Rc[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const bool act = j == 0 ? sp.act0 : sp.act1;
-                const T ps = act ? T(P.w_slack) : T(0);
-                const T Rcj = S(FCR + j, k);
-                const T ms = ps + T(S(FS + 4 + j, k)) + Rcj;
-                const T bs = Rcj / ms;
-                S(FE + 1 + j, k) = (float)bs;
-                S(FE + 4 + j, k) = (float)(T(1) / ms);
-                Rc[j] = Rcj - bs * Rcj;
-            }
-            const T h0 = sp.h0, h1 = sp.h1;
-            const T pk = sp.real ? T(P.w_kappa) : T(0), pl = sp.real ? T(P.w_l) : T(0);
-            T *D = Dg[k];
-            D[0] = T(S(FS + 0, k)) + pl + R0 * a00 * a00 + R1 * a10 * a10 + Rc[0] + Rc[1];
-            D[1] = R0 * a00 * a01 + R1 * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
-            D[2] = R1 * a10 * a12;
-            D[3] = T(S(FS + 1, k)) + R0 * a01 * a01 + R1 * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1;
-            D[4] = R1 * a11 * a12;
-            D[5] = T(S(FS + 2, k)) + pk + R1 * a12 * a12 + R2t * a22 * a22 + T(S(FKR, k));
-        }
-        // contribution of the left stage's outgoing rows (-1 entries): diag(Rt_left)
-        T RtL[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) RtL[r] = shfl_up(Rt[C - 1][r], 1, lane);
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-            if (sp.real) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) Dg[k][SI(r, r)] += (k == 0) ? RtL[r] : Rt[k > 0 ? k - 1 : 0][r];
-            }
-        }
-        // coupling block between stage k and k+1: O[r][c] = gn * Rt_r * Ahat[r][c]
-        auto coupling = [&](int k, T(&O)[9]) {
-            const StagePred sp = pred(k);
-            const T gn = sp.gn;
-            O[0] = gn * Rt[k][0] * T(S(FA + 0, k));
-            O[1] = gn * Rt[k][0] * T(S(FA + 1, k));
-            O[2] = T(0);
-            O[3] = gn * Rt[k][1] * T(S(FA + 2, k));
-            O[4] = gn * Rt[k][1] * T(S(FA + 3, k));
-            O[5] = gn * Rt[k][1] * T(S(FA + 4, k));
-            O[6] = T(0);
-            O[7] = T(0);
-            O[8] = gn * Rt[k][2] * T(sp.a22);
-        };
-        // 2. interior elimination with fill towards the left separator
-        T OL[9];
+        // left neighbour's last stage: its Rt (for our first diagonal block) and coupling
+        T RtL[3], OL[9];
         {
-            T Olast[9];
-            coupling(C - 1, Olast);
+            const StagePred spl = pred(C - 1);
+            T RtLast[3], Olast[9];
+            stage_rt<T>(C - 1, spl, RtLast, false);
+            stage_coupling<T>(C - 1, spl, RtLast, Olast);
 #pragma unroll
-            for (int j = 0; j < 9; ++j) OL[j] = shfl_up(Olast[j], 1, lane);
-            if (lane == 0) {
+            for (int r = 0; r < 3; ++r) {
+                RtL[r] = shfl_up(RtLast[r], 1, lane);
+                if (lane == 0) RtL[r] = T(0);
+            }
 #pragma unroll
-                for (int j = 0; j < 9; ++j) OL[j] = T(0);
+            for (int j = 0; j < 9; ++j) {
+                OL[j] = shfl_up(Olast[j], 1, lane);
+                if (lane == 0) OL[j] = T(0);
             }
         }
         T Phi[9];  // M~[SL, current]  (rows: left separator, cols: current stage) = OL'
@@ -595,14 +597,19 @@ struct QpWarp {
 #pragma unroll
             for (int c = 0; c < 3; ++c) Phi[3 * r + c] = OL[3 * c + r];
         T dA[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-        T Dt[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) Dt[j] = Dg[0][j];
-#pragma unroll
+        T Dt[6], Rt[3];
+        {
+            const StagePred sp0 = pred(0);
+            stage_rt<T>(0, sp0, Rt, true);
+            stage_diag<T>(0, sp0, Rt, RtL, Dt);
+        }
+        // interior elimination with fill towards the left separator
+        PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
+            const StagePred sp = pred(k);
             T Dinv[6], O[9], Gh[9], Fh[9];
             ok = inv_sym3(Dt, Dinv) && ok;
-            coupling(k, O);
+            stage_coupling<T>(k, sp, Rt, O);
             mul_ms(O, Dinv, Gh);
             mul_ms(Phi, Dinv, Fh);
 #pragma unroll
@@ -617,10 +624,16 @@ struct QpWarp {
 #pragma unroll
             for (int j = 0; j < 9; ++j) Phi[j] = -t9[j];
             mul_abt_sym(Gh, O, t6);
+            // next stage's own block (its left neighbour is stage k)
+            const StagePred spn = pred(k + 1);
+            T RtPrev[3] = {Rt[0], Rt[1], Rt[2]};
+            stage_rt<T>(k + 1, spn, Rt, true);
+            T Dn[6];
+            stage_diag<T>(k + 1, spn, Rt, RtPrev, Dn);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) Dt[j] = Dg[k + 1][j] - t6[j];
+            for (int j = 0; j < 6; ++j) Dt[j] = Dn[j] - t6[j];
         }
-        // 3. separators: A = own Schur complement - fill from the right neighbour's interior
+        // separators: A = own Schur complement - fill from the right neighbour's interior
         T Acr[6], Ccr[9];
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -632,12 +645,12 @@ struct QpWarp {
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c) Ccr[3 * r + c] = Phi[3 * c + r];  // M^[S_l, S_{l-1}]
-        // 4. block cyclic reduction over the 32 separators
+        // block cyclic reduction over the 32 separators
         T myAinv[6] = {T(1), T(0), T(0), T(1), T(0), T(1)};
         T myGm[9], myGp[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) { myGm[j] = T(0); myGp[j] = T(0); }
-#pragma unroll
+        PQP_ROLL
         for (int t = 0; t < 5; ++t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -658,9 +671,9 @@ struct QpWarp {
             mul_ms(Ct, Ainv, Gm);  // G- = M^[l-h, l] Ainv = C_l' Ainv
             mul_ms(Cr, Ainv, Gp);  // G+ = M^[l+h, l] Ainv = C_{l+h} Ainv
             T Um[6], Up[6], W[9];
-            mul_abt_sym(Gm, Ct, Um);  // G- M^[l, l-h] = G- C_l    = G- (Ct)'
-            mul_abt_sym(Gp, Cr, Up);  // G+ M^[l, l+h] = G+ Cr'
-            mul_abt(Gp, Ct, W);       // G+ C_l = G+ (Ct)'
+            mul_abt_sym(Gm, Ct, Um);  // G- M^[l, l-h]
+            mul_abt_sym(Gp, Cr, Up);  // G+ M^[l, l+h]
+            mul_abt(Gp, Ct, W);       // G+ C_l
             if (elim) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) myAinv[j] = Ainv[j];
@@ -692,36 +705,42 @@ struct QpWarp {
         for (int j = 0; j < 6; ++j) crAinv[j] = (float)myAinv[j];
 #pragma unroll
         for (int j = 0; j < 9; ++j) { crGm[j] = (float)myGm[j]; crGp[j] = (float)myGp[j]; }
-        // all lanes must agree
         float bad = ok ? 0.0f : 1.0f;
         bad = warp_max(bad, lane);
         return bad == 0.0f;
     }
 
-    // -------------------------------------------------------------- solve  M_red x = b (in place)
-    PQP_DEV void solve(float (&b)[C][3]) {
+    // -------------------------------------------------------------- solve  M_red x = b
+    // b lives in shared memory (FB); overwritten by the solution.
+    PQP_DEV void solve() {
         float acc[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
+        float bk[3] = {S(FB + 0, 0), S(FB + 1, 0), S(FB + 2, 0)};
+        PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
+            float bn[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                b[k + 1][r] -= S(FG + 3 * r, k) * b[k][0] + S(FG + 3 * r + 1, k) * b[k][1] + S(FG + 3 * r + 2, k) * b[k][2];
-                acc[r] += S(FF + 3 * r, k) * b[k][0] + S(FF + 3 * r + 1, k) * b[k][1] + S(FF + 3 * r + 2, k) * b[k][2];
+                bn[r] = S(FB + r, k + 1) -
+                        (S(FG + 3 * r, k) * bk[0] + S(FG + 3 * r + 1, k) * bk[1] + S(FG + 3 * r + 2, k) * bk[2]);
+                acc[r] += S(FF + 3 * r, k) * bk[0] + S(FF + 3 * r + 1, k) * bk[1] + S(FF + 3 * r + 2, k) * bk[2];
             }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { S(FB + r, k + 1) = bn[r]; bk[r] = bn[r]; }
         }
         float bs[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             float fr = shfl_down(acc[r], 1, lane);
             if (lane == 31) fr = 0.0f;
-            bs[r] = b[C - 1][r] - fr;
+            bs[r] = bk[r] - fr;
         }
         // cyclic reduction, forward
-#pragma unroll
+        PQP_ROLL
         for (int t = 0; t < 5; ++t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
             const bool surv = (lane & (2 * h - 1)) == 0;
+            float upd[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 float vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
@@ -732,11 +751,10 @@ struct QpWarp {
                 float fl = shfl_up(vp, h, lane);
                 if (lane + h > 31) fr = 0.0f;
                 if (lane < h) fl = 0.0f;
-                // note: bs is updated after the loop over r would be wrong (vm/vp use old bs)
-                acc[r] = surv ? (fr + fl) : 0.0f;
+                upd[r] = surv ? (fr + fl) : 0.0f;
             }
 #pragma unroll
-            for (int r = 0; r < 3; ++r) bs[r] -= acc[r];
+            for (int r = 0; r < 3; ++r) bs[r] -= upd[r];
         }
         float ts[3], xs[3];
 #pragma unroll
@@ -745,7 +763,7 @@ struct QpWarp {
             xs[r] = ts[r];
         }
         // cyclic reduction, backward
-#pragma unroll
+        PQP_ROLL
         for (int t = 4; t >= 0; --t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -764,90 +782,91 @@ struct QpWarp {
             }
         }
         // local backward substitution
-        float xSL[3];
+        float xSL[3], xn[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             xSL[r] = shfl_up(xs[r], 1, lane);
             if (lane == 0) xSL[r] = 0.0f;
-            b[C - 1][r] = xs[r];
+            S(FB + r, C - 1) = xs[r];
+            xn[r] = xs[r];
         }
-#pragma unroll
+        PQP_ROLL
         for (int k = C - 2; k >= 0; --k) {
-            float t[3];
+            const float b0 = S(FB + 0, k), b1 = S(FB + 1, k), b2 = S(FB + 2, k);
+            float xk[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-                t[r] = S(FDI + SI(r, 0), k) * b[k][0] + S(FDI + SI(r, 1), k) * b[k][1] + S(FDI + SI(r, 2), k) * b[k][2];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                b[k][c] = t[c] -
-                          (S(FG + c, k) * b[k + 1][0] + S(FG + 3 + c, k) * b[k + 1][1] + S(FG + 6 + c, k) * b[k + 1][2]) -
-                          (S(FF + c, k) * xSL[0] + S(FF + 3 + c, k) * xSL[1] + S(FF + 6 + c, k) * xSL[2]);
-        }
-    }
-
-    // -------------------------------------------------------------- right-hand side from w
-    // wo[k][0..2]: w of the outgoing rows (row 2 already includes the u-condensation),
-    // partial b holds the stage-local part; adds the left neighbour's rows.
-    PQP_DEV void finish_rhs(float (&b)[C][3], const float (&wo)[C][3]) {
-        float wL[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) wL[r] = shfl_up(wo[C - 1][r], 1, lane);
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-            if (sp.real) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) b[k][r] -= (k == 0) ? wL[r] : wo[k > 0 ? k - 1 : 0][r];
+            for (int c = 0; c < 3; ++c) {
+                const float t = S(FDI + SI(c, 0), k) * b0 + S(FDI + SI(c, 1), k) * b1 + S(FDI + SI(c, 2), k) * b2;
+                xk[c] = t - (S(FG + c, k) * xn[0] + S(FG + 3 + c, k) * xn[1] + S(FG + 6 + c, k) * xn[2]) -
+                        (S(FF + c, k) * xSL[0] + S(FF + 3 + c, k) * xSL[1] + S(FF + 6 + c, k) * xSL[2]);
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { S(FB + c, k) = xk[c]; xn[c] = xk[c]; }
         }
     }
 
-    // stage-local part of rhs from the row vectors w (wo: outgoing, wk: kappa, wc: clearance)
-    PQP_DEV void local_rhs(int k, const StagePred &sp, float (&wo)[3], float wk, float (&wc)[2],
-                           float (&bk)[3], float (&aux)[3]) {
+    // -------------------------------------------------------------- right-hand side
+    // stage-local part of the rhs from the row vectors w (wo: outgoing, wk: kappa, wc:
+    // clearance); on return wo[2] includes the u-condensation (what the right neighbour sees)
+    PQP_DEV void local_rhs(int k, const StagePred &sp, float (&wo)[3], float wk, float (&wc)[2], float (&bk)[3]) {
         const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                     a12 = S(FA + 4, k), ds = S(FA + 5, k);
         const float rhs_u = S(FS + 3, k) * S(FX + 3, k) + ds * wo[2];
-        wo[2] -= S(FE + 0, k) * rhs_u;
-        aux[0] = rhs_u;
+        wo[2] -= (S(FOR_ + 2, k) * ds * S(FE + 0, k)) * rhs_u;
+        S(FAUX + 0, k) = rhs_u;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const float rhs_s = S(FS + 4 + j, k) * S(FX + 4 + j, k) + wc[j];
-            wc[j] -= S(FE + 1 + j, k) * rhs_s;
-            aux[1 + j] = rhs_s;
+            wc[j] -= (S(FCR + j, k) * S(FE + 1 + j, k)) * rhs_s;
+            S(FAUX + 1 + j, k) = rhs_s;
         }
         bk[0] = S(FS + 0, k) * S(FX + 0, k) + a00 * wo[0] + a10 * wo[1] + wc[0] + wc[1];
         bk[1] = S(FS + 1, k) * S(FX + 1, k) + a01 * wo[0] + a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
         bk[2] = S(FS + 2, k) * S(FX + 2, k) + a12 * wo[1] + sp.a22 * wo[2] + wk;
     }
+    // subtract the left neighbour lane's last-stage rows from this lane's first stage
+    PQP_DEV void fix_first_stage(const float (&wlast)[3]) {
+        const StagePred sp0 = pred(0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float wL = shfl_up(wlast[r], 1, lane);
+            if (lane == 0 || !sp0.real) wL = 0.0f;
+            S(FB + r, 0) -= wL;
+        }
+    }
 
     // rhs from the iterates held in shared memory (initial rhs and after a rho update).
     // `initial`: the outgoing rows' z is z0 (cold: 0, warm: previous z), not yet the bound.
-    PQP_DEV void build_rhs(float (&b)[C][3], float (&aux)[C][3], bool initial, bool warm) {
-        float wo[C][3];
-#pragma unroll
+    PQP_DEV void build_rhs(bool initial, bool warm) {
+        float wprev[3] = {0.0f, 0.0f, 0.0f};
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            float wk, wc[2];
+            float wo[3], wk, wc[2], bk[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 float z;
                 if (sp.last && r < 2) z = zend[r];
                 else z = initial ? z0_out(warm, r, k) : S(FOB + r, k);
-                wo[k][r] = S(FOR_ + r, k) * (z - S(FOY + r, k));
+                wo[r] = S(FOR_ + r, k) * (z - S(FOY + r, k));
             }
             wk = S(FKR, k) * (S(FKZ, k) - S(FKY, k));
 #pragma unroll
             for (int j = 0; j < 2; ++j) wc[j] = S(FCR + j, k) * (S(FCZ + j, k) - S(FCY + j, k));
-            local_rhs(k, sp, wo[k], wk, wc, b[k], aux[k]);
+            local_rhs(k, sp, wo, wk, wc, bk);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                S(FB + r, k) = bk[r] - ((sp.real && k > 0) ? wprev[r] : 0.0f);
+                wprev[r] = wo[r];
+            }
         }
-        finish_rhs(b, wo);
+        fix_first_stage(wprev);
     }
 
     // fold z0 != bound of the equality outgoing rows into yhat (exact)
     PQP_DEV void fold_initial_z(bool warm) {
         const float oma = 1.0f - ka.prm.alpha;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
 #pragma unroll
@@ -858,31 +877,32 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- one ADMM update
-    // in: b = x~ (state part), aux = rhs of (u, s0, s1) used by that solve
-    // out: iterates advanced in shared memory, b/aux = rhs of the next solve
-    template <bool kStoreDy>
-    PQP_DEV void admm_update(float (&b)[C][3], float (&aux)[C][3]) {
+    // in: FB = x~ (state part), FAUX = rhs of (u, s0, s1) used by that solve
+    // out: iterates advanced in shared memory, FB/FAUX = rhs of the next solve
+    PQP_DEV void admm_update(bool store_dy) {
         const float alpha = ka.prm.alpha, oma = 1.0f - alpha;
-        float xn[3];
+        float xnb[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            xn[c] = shfl_down(b[0][c], 1, lane);
-            if (lane == 31) xn[c] = 0.0f;
+            xnb[c] = shfl_down(S(FB + c, 0), 1, lane);
+            if (lane == 31) xnb[c] = 0.0f;
         }
-        float wo[C][3];
-#pragma unroll
+        float wprev[3] = {0.0f, 0.0f, 0.0f};
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
-            const float lt = b[k][0], pt = b[k][1], kt = b[k][2];
-            const float ln = (k == C - 1) ? xn[0] : b[k < C - 1 ? k + 1 : k][0];
-            const float pn = (k == C - 1) ? xn[1] : b[k < C - 1 ? k + 1 : k][1];
-            const float kn = (k == C - 1) ? xn[2] : b[k < C - 1 ? k + 1 : k][2];
+            const float lt = S(FB + 0, k), pt = S(FB + 1, k), kt = S(FB + 2, k);
+            const int kn1 = k < C - 1 ? k + 1 : k;
+            const float ln = (k == C - 1) ? xnb[0] : S(FB + 0, kn1);
+            const float pn = (k == C - 1) ? xnb[1] : S(FB + 1, kn1);
+            const float kn = (k == C - 1) ? xnb[2] : S(FB + 2, kn1);
             // recover the eliminated variables of x~
-            const float ut = aux[k][0] * S(FE + 3, k) - S(FE + 0, k) * (sp.a22 * kt + sp.gn * kn);
-            const float s0t = aux[k][1] * S(FE + 4, k) - S(FE + 1, k) * (lt + sp.h0 * pt);
-            const float s1t = aux[k][2] * S(FE + 5, k) - S(FE + 2, k) * (lt + sp.h1 * pt);
+            const float miu = S(FE + 0, k), R2 = S(FOR_ + 2, k);
+            const float ut = miu * (S(FAUX + 0, k) - R2 * ds * (sp.a22 * kt + sp.gn * kn));
+            const float s0t = S(FE + 1, k) * (S(FAUX + 1, k) - S(FCR + 0, k) * (lt + sp.h0 * pt));
+            const float s1t = S(FE + 2, k) * (S(FAUX + 2, k) - S(FCR + 1, k) * (lt + sp.h1 * pt));
             // z~ = A x~
             float zo[3];
             zo[0] = a00 * lt + a01 * pt + sp.gn * ln;
@@ -897,7 +917,7 @@ struct QpWarp {
 #pragma unroll
             for (int j = 0; j < 6; ++j) S(FX + j, k) = alpha * xt6[j] + oma * S(FX + j, k);
             // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
-            float wk, wc[2];
+            float wo[3], wk, wc[2], bk[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const float bnd = S(FOB + r, k), yh = S(FOY + r, k), R = S(FOR_ + r, k);
@@ -914,8 +934,8 @@ struct QpWarp {
                     yn = (zt + yh) - bnd;
                 }
                 S(FOY + r, k) = yn;
-                wo[k][r] = R * (zn - yn);
-                if (kStoreDy) G(gdy, r, k) = R * (zt - zn);  // delta_y without cancellation
+                wo[r] = R * (zn - yn);
+                if (store_dy) G(gdy, r, k) = R * (zt - zn);  // delta_y without cancellation
             }
             {
                 const float z = S(FKZ, k), yh = S(FKY, k), R = S(FKR, k);
@@ -926,7 +946,7 @@ struct QpWarp {
                 S(FKZ, k) = zn;
                 S(FKY, k) = yn;
                 wk = R * (zn - yn);
-                if (kStoreDy) G(gdy, 3, k) = R * (zt - zn);
+                if (store_dy) G(gdy, 3, k) = R * (zt - zn);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -938,11 +958,16 @@ struct QpWarp {
                 S(FCZ + j, k) = zn;
                 S(FCY + j, k) = yn;
                 wc[j] = R * (zn - yn);
-                if (kStoreDy) G(gdy, 4 + j, k) = R * (zt - zn);
+                if (store_dy) G(gdy, 4 + j, k) = R * (zt - zn);
             }
-            local_rhs(k, sp, wo[k], wk, wc, b[k], aux[k]);
+            local_rhs(k, sp, wo, wk, wc, bk);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                S(FB + r, k) = bk[r] - ((sp.real && k > 0) ? wprev[r] : 0.0f);
+                wprev[r] = wo[r];
+            }
         }
-        finish_rhs(b, wo);
+        fix_first_stage(wprev);
     }
 
     // -------------------------------------------------------------- residuals (OSQP update_info)
@@ -968,7 +993,7 @@ struct QpWarp {
 #pragma unroll
         for (int j = 0; j < 12; ++j) m[j] = 0.0f;
         const float c = cscale;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
@@ -1028,15 +1053,15 @@ struct QpWarp {
         return nr;
     }
 
-    // OSQP is_primal_infeasible on the delta_y stored by the last admm_update<true>
+    // OSQP is_primal_infeasible on the delta_y stored by the last admm_update(true)
     PQP_DEV bool primal_infeasible(float eps) {
         sync_warp(lane);
         const float c = cscale;
         float nrm = 0.0f, lhs = 0.0f;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            const int cls = SI32(FCLS, k);
+            const int cls = GCLSI(k);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 float dy = G(gdy, r, k);
@@ -1056,14 +1081,11 @@ struct QpWarp {
         }
         nrm = warp_max(nrm, lane);
         lhs = warp_sum(lhs, lane);
-#ifdef PQP_EMU_DEBUG
-        if (lane == 0) printf("  pinf: c*nrm=%g lhs=%g thr=%g\n", c * nrm, lhs, -eps * nrm);
-#endif
         if (!(c * nrm > eps)) return false;
         if (!(lhs < -eps * nrm)) return false;
         sync_warp(lane);
         float mx = 0.0f;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
@@ -1088,9 +1110,6 @@ struct QpWarp {
             for (int j = 0; j < 6; ++j) mx = fmaxf(mx, fabsf(aty[j]));
         }
         mx = warp_max(mx, lane);
-#ifdef PQP_EMU_DEBUG
-        if (lane == 0) printf("  pinf: |A'dy|=%g thr=%g\n", mx, eps * nrm);
-#endif
         return mx < eps * nrm;
     }
 
@@ -1111,6 +1130,8 @@ struct QpWarp {
         return kUnsolved;
     }
 
+    PQP_DEV bool refactor() { return ka.prm.factor_fp64 ? factor<double>() : factor<float>(); }
+
     // OSQP compute_rho_estimate + update; returns true if rho changed (and refactors)
     PQP_DEV bool adapt_rho(const Norms &nr, bool &factor_ok) {
         const DevParams &P = ka.prm;
@@ -1121,9 +1142,9 @@ struct QpWarp {
         if (!(est > rho * P.rho_tol || est < rho / P.rho_tol)) return false;
         const float ratio = est / rho, rinv = rho / est;
         rho = est;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
-            const int cls = SI32(FCLS, k);
+            const int cls = GCLSI(k);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const int cl = (cls >> (2 * r)) & 3;
@@ -1134,7 +1155,7 @@ struct QpWarp {
                 }
             }
         }
-        factor_ok = ka.prm.factor_fp64 ? factor<double>() : factor<float>();
+        factor_ok = refactor();
         return true;
     }
 
@@ -1161,11 +1182,9 @@ struct QpWarp {
         scale_and_classify();
         sync_warp(lane);
         init_iterates(warm);
-        bool fok = P.factor_fp64 ? factor<double>() : factor<float>();
+        bool fok = refactor();
         sync_warp(lane);
-
-        float b[C][3], aux[C][3];
-        build_rhs(b, aux, true, warm);
+        build_rhs(true, warm);
         fold_initial_z(warm);
 
         int status = fok ? kUnsolved : kNumerical;
@@ -1174,13 +1193,13 @@ struct QpWarp {
         nr.pri = nr.dua = 0.0f;
         bool checked = false;
         if (fok) {
+            PQP_ROLL
             for (iter = 1; iter <= P.max_iter; ++iter) {
-                solve(b);
+                solve();
                 const bool can_check = P.check_every > 0 && (iter % P.check_every == 0);
                 const bool can_adapt = P.adaptive_rho && P.adaptive_interval > 0 &&
                                        (iter % P.adaptive_interval == 0);
-                if (can_check) admm_update<true>(b, aux);
-                else admm_update<false>(b, aux);
+                admm_update(can_check);
                 checked = false;
                 if (can_check || can_adapt) {
                     nr = residuals();
@@ -1195,7 +1214,7 @@ struct QpWarp {
                             ++rho_updates;
                             if (!ok2) { status = kNumerical; break; }
                             sync_warp(lane);
-                            build_rhs(b, aux, false, warm);
+                            build_rhs(false, warm);
                         }
                     }
                 }
@@ -1226,7 +1245,7 @@ struct QpWarp {
         double *xf = ka.x_full ? ka.x_full + (size_t)qp * nvm : nullptr;
         double *yf = ka.y_full ? ka.y_full + (size_t)qp * mm : nullptr;
         double *zf = ka.z_full ? ka.z_full + (size_t)qp * mm : nullptr;
-#pragma unroll
+        PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const int g = lane * C + k;
             const StagePred sp = pred(k);
