@@ -35,6 +35,7 @@
 #include "warp_emu.h"
 #define PQP_DEV inline
 #define PQP_RESTRICT
+struct alignas(16) float4 { float x, y, z, w; };
 #else
 #include <cuda_runtime.h>
 #define PQP_DEV __device__ __forceinline__
@@ -57,24 +58,32 @@ constexpr int kSolved = 0, kMaxIter = 1, kPrimInf = 2, kDualInf = 3, kSolvedInac
               kPrimInfInacc = 5, kNumerical = 7, kUnsolved = 10;
 
 // ------------------------------------------------------------------ shared-memory field map
-// element (field f, local stage k, lane) lives at sm[(f*C + k)*32 + lane]
+// Per-stage data is stored as 18 float4 groups; element (group g, local stage k, lane) is the
+// float4 at index (g*C + k)*32 + lane, so a warp's access to one group of one stage is one
+// conflict-free 512-byte LDS.128/STS.128. The logical field number f = 4*g + component.
+// Groups 0-6 are read-only inside the ADMM loop, 7-11 are read-write, 12-17 are the factor.
 enum : int {
-    FX = 0,     // 6: l, psi, kappa, u, s0, s1           (primal iterate x)
-    FA = 6,     // 6: a00 a01 a10 a11 a12 ds             (stage transition coefficients)
-    FS = 12,    // 6: S_j = sigma / (c d_j^2)            (proximal weights)
-    FE = 18,    // 3: 1/m_u 1/m_s0 1/m_s1                (closed-form elimination constants)
-    FOB = 21,   // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
-    FOY = 24,   // 3: outgoing-row scaled dual yhat
-    FOR_ = 27,  // 3: outgoing-row weight R
-    FKZ = 30, FKY = 31, FKR = 32,                       // kappa box row: z, yhat, R
-    FCLO = 33, FCHI = 35, FCZ = 37, FCY = 39, FCR = 41,  // clearance rows (2 each)
-    FB = 43,    // 3: rhs of the reduced system / x~ after the solve
-    FAUX = 46,  // 3: rhs of the eliminated variables (u, s0, s1)
-    FDI = 49,   // 6: inverse pivot block (sym)
-    FG = 55,    // 9: multiplier to the next stage
-    FF = 64,    // 9: multiplier to the left separator (fill)
-    NFIELD = 73,
-    FT = FDI    // the 24 factor fields double as input staging and as Ruiz scratch
+    FA = 0,     // 6: a00 a01 a10 a11 | a12 ds        (stage transition coefficients)
+    FE = 6,     // 3: 1/m_u 1/m_s0 | 1/m_s1            (closed-form elimination constants)
+    FOB = 9,    // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
+    FOR_ = 12,  // 3: outgoing-row weight R
+    FKR = 15,   //    kappa-row weight R
+    FCLO = 16, FCHI = 18,  // clearance-row bounds (2 each)
+    FCR = 20,   // 2: clearance-row weights R
+    FS = 22,    // 6: S_j = sigma / (c d_j^2)          (proximal weights)
+    FX = 28,    // 6: l, psi, kappa, u | s0, s1        (primal iterate x)
+    FKZ = 34, FKY = 35,    // kappa box row: z, yhat
+    FOY = 36,   // 3: outgoing-row scaled dual yhat    (+1 pad)
+    FCZ = 40, FCY = 42,    // clearance rows: z, yhat (2 each)
+    FB = 44,    // 3: rhs of the reduced system / x~ after the solve (+1 pad)
+    FDI = 48,   // 6: inverse pivot block (sym)
+    FG = 54,    // 9: multiplier to the next stage
+    FF = 63,    // 9: multiplier to the left separator (fill)
+    NFIELD = 72,
+    FT = FDI,   // the 24 factor fields double as input staging and as Ruiz scratch
+    // float4 group numbers
+    GA0 = 0, GA1 = 1, GB2 = 2, GR3 = 3, GC4 = 4, GR5 = 5, GS6 = 6,
+    GX0 = 7, GX1 = 8, GOY = 9, GCZ = 10, GBV = 11, GF0 = 12
 };
 // global per-QP scratch, same [field][k][lane] layout
 enum : int {
@@ -260,8 +269,11 @@ struct QpWarp {
 
     PQP_DEV QpWarp(const KernelArgs &k, float *s, int l, int q) : ka(k), sm(s), lane(l), qp(q) {}
 
-    PQP_DEV float &S(int f, int k) { return sm[(f * C + k) * 32 + lane]; }
-    PQP_DEV float &SL(int f, int k, int ln) { return sm[(f * C + k) * 32 + ln]; }
+    // scalar view of logical field f (group f>>2, component f&3)
+    PQP_DEV float &S(int f, int k) { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
+    PQP_DEV float &SL(int f, int k, int ln) { return sm[(((f >> 2) * C + k) * 32 + ln) * 4 + (f & 3)]; }
+    // vector view of group g
+    PQP_DEV float4 &V(int g, int k) { return reinterpret_cast<float4 *>(sm)[(g * C + k) * 32 + lane]; }
     PQP_DEV float &G(float *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
     PQP_DEV float &GL(float *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
     PQP_DEV int &GCLSI(int k) { return reinterpret_cast<int *>(gscal)[(GCLS * C + k) * 32 + lane]; }
@@ -711,21 +723,35 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- solve  M_red x = b
-    // b lives in shared memory (FB); overwritten by the solution.
+    // b lives in shared memory (group GBV); overwritten by the solution. The factor of one
+    // stage is 6 float4 (Dinv[6] G[9] F[9] packed contiguously).
+    PQP_DEV void load_factor(int k, float (&f)[24], bool with_dinv) {
+#pragma unroll
+        for (int g = with_dinv ? 0 : 1; g < 6; ++g) {
+            const float4 v = V(GF0 + g, k);
+            f[4 * g] = v.x; f[4 * g + 1] = v.y; f[4 * g + 2] = v.z; f[4 * g + 3] = v.w;
+        }
+    }
     PQP_DEV void solve() {
         float acc[3] = {0.0f, 0.0f, 0.0f};
-        float bk[3] = {S(FB + 0, 0), S(FB + 1, 0), S(FB + 2, 0)};
+        float4 bv = V(GBV, 0);
+        float bk[3] = {bv.x, bv.y, bv.z};
         PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
-            float bn[3];
+            float f[24];
+            load_factor(k, f, false);
+            const float *Gm = f + 6, *Fm = f + 15;
+            float4 nv = V(GBV, k + 1);
+            float bn[3] = {nv.x, nv.y, nv.z};
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                bn[r] = S(FB + r, k + 1) -
-                        (S(FG + 3 * r, k) * bk[0] + S(FG + 3 * r + 1, k) * bk[1] + S(FG + 3 * r + 2, k) * bk[2]);
-                acc[r] += S(FF + 3 * r, k) * bk[0] + S(FF + 3 * r + 1, k) * bk[1] + S(FF + 3 * r + 2, k) * bk[2];
+                bn[r] -= Gm[3 * r] * bk[0] + Gm[3 * r + 1] * bk[1] + Gm[3 * r + 2] * bk[2];
+                acc[r] += Fm[3 * r] * bk[0] + Fm[3 * r + 1] * bk[1] + Fm[3 * r + 2] * bk[2];
             }
+            nv.x = bn[0]; nv.y = bn[1]; nv.z = bn[2];
+            V(GBV, k + 1) = nv;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) { S(FB + r, k + 1) = bn[r]; bk[r] = bn[r]; }
+            for (int r = 0; r < 3; ++r) bk[r] = bn[r];
         }
         float bs[3];
 #pragma unroll
@@ -787,185 +813,238 @@ struct QpWarp {
         for (int r = 0; r < 3; ++r) {
             xSL[r] = shfl_up(xs[r], 1, lane);
             if (lane == 0) xSL[r] = 0.0f;
-            S(FB + r, C - 1) = xs[r];
             xn[r] = xs[r];
+        }
+        {
+            float4 v = V(GBV, C - 1);
+            v.x = xs[0]; v.y = xs[1]; v.z = xs[2];
+            V(GBV, C - 1) = v;
         }
         PQP_ROLL
         for (int k = C - 2; k >= 0; --k) {
-            const float b0 = S(FB + 0, k), b1 = S(FB + 1, k), b2 = S(FB + 2, k);
+            float f[24];
+            load_factor(k, f, true);
+            const float *Di = f, *Gm = f + 6, *Fm = f + 15;
+            float4 v = V(GBV, k);
+            const float b0 = v.x, b1 = v.y, b2 = v.z;
             float xk[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float t = S(FDI + SI(c, 0), k) * b0 + S(FDI + SI(c, 1), k) * b1 + S(FDI + SI(c, 2), k) * b2;
-                xk[c] = t - (S(FG + c, k) * xn[0] + S(FG + 3 + c, k) * xn[1] + S(FG + 6 + c, k) * xn[2]) -
-                        (S(FF + c, k) * xSL[0] + S(FF + 3 + c, k) * xSL[1] + S(FF + 6 + c, k) * xSL[2]);
+                const float t = Di[SI(c, 0)] * b0 + Di[SI(c, 1)] * b1 + Di[SI(c, 2)] * b2;
+                xk[c] = t - (Gm[c] * xn[0] + Gm[3 + c] * xn[1] + Gm[6 + c] * xn[2]) -
+                        (Fm[c] * xSL[0] + Fm[3 + c] * xSL[1] + Fm[6 + c] * xSL[2]);
             }
+            v.x = xk[0]; v.y = xk[1]; v.z = xk[2];
+            V(GBV, k) = v;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { S(FB + c, k) = xk[c]; xn[c] = xk[c]; }
+            for (int c = 0; c < 3; ++c) xn[c] = xk[c];
         }
+    }
+
+    // -------------------------------------------------------------- per-stage data in registers
+    struct StageRO {  // read-only inside the ADMM loop (7 float4)
+        float a00, a01, a10, a11, a12, ds, miu, mis0, mis1, ob[3], Ro[3], Rk, clo[2], chi[2], Rc[2], Sw[6];
+    };
+    PQP_DEV void load_ro(int k, StageRO &q) {
+        const float4 g0 = V(GA0, k), g1 = V(GA1, k), g2 = V(GB2, k), g3 = V(GR3, k), g4 = V(GC4, k),
+                     g5 = V(GR5, k), g6 = V(GS6, k);
+        q.a00 = g0.x; q.a01 = g0.y; q.a10 = g0.z; q.a11 = g0.w;
+        q.a12 = g1.x; q.ds = g1.y; q.miu = g1.z; q.mis0 = g1.w;
+        q.mis1 = g2.x; q.ob[0] = g2.y; q.ob[1] = g2.z; q.ob[2] = g2.w;
+        q.Ro[0] = g3.x; q.Ro[1] = g3.y; q.Ro[2] = g3.z; q.Rk = g3.w;
+        q.clo[0] = g4.x; q.clo[1] = g4.y; q.chi[0] = g4.z; q.chi[1] = g4.w;
+        q.Rc[0] = g5.x; q.Rc[1] = g5.y; q.Sw[0] = g5.z; q.Sw[1] = g5.w;
+        q.Sw[2] = g6.x; q.Sw[3] = g6.y; q.Sw[4] = g6.z; q.Sw[5] = g6.w;
     }
 
     // -------------------------------------------------------------- right-hand side
     // stage-local part of the rhs from the row vectors w (wo: outgoing, wk: kappa, wc:
-    // clearance); on return wo[2] includes the u-condensation (what the right neighbour sees)
-    PQP_DEV void local_rhs(int k, const StagePred &sp, float (&wo)[3], float wk, float (&wc)[2], float (&bk)[3]) {
-        const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
-                    a12 = S(FA + 4, k), ds = S(FA + 5, k);
-        const float rhs_u = S(FS + 3, k) * S(FX + 3, k) + ds * wo[2];
-        wo[2] -= (S(FOR_ + 2, k) * ds * S(FE + 0, k)) * rhs_u;
-        S(FAUX + 0, k) = rhs_u;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float rhs_s = S(FS + 4 + j, k) * S(FX + 4 + j, k) + wc[j];
-            wc[j] -= (S(FCR + j, k) * S(FE + 1 + j, k)) * rhs_s;
-            S(FAUX + 1 + j, k) = rhs_s;
-        }
-        bk[0] = S(FS + 0, k) * S(FX + 0, k) + a00 * wo[0] + a10 * wo[1] + wc[0] + wc[1];
-        bk[1] = S(FS + 1, k) * S(FX + 1, k) + a01 * wo[0] + a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
-        bk[2] = S(FS + 2, k) * S(FX + 2, k) + a12 * wo[1] + sp.a22 * wo[2] + wk;
+    // clearance) and the iterate x; on return wo[2] includes the u-condensation (what the
+    // right neighbour sees)
+    PQP_DEV void local_rhs(const StageRO &q, const StagePred &sp, const float (&x)[6], float (&wo)[3],
+                           float wk, float (&wc)[2], float (&bk)[3]) {
+        const float rhs_u = q.Sw[3] * x[3] + q.ds * wo[2];
+        wo[2] -= (q.Ro[2] * q.ds * q.miu) * rhs_u;
+        const float rhs_s0 = q.Sw[4] * x[4] + wc[0];
+        wc[0] -= (q.Rc[0] * q.mis0) * rhs_s0;
+        const float rhs_s1 = q.Sw[5] * x[5] + wc[1];
+        wc[1] -= (q.Rc[1] * q.mis1) * rhs_s1;
+        bk[0] = q.Sw[0] * x[0] + q.a00 * wo[0] + q.a10 * wo[1] + wc[0] + wc[1];
+        bk[1] = q.Sw[1] * x[1] + q.a01 * wo[0] + q.a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
+        bk[2] = q.Sw[2] * x[2] + q.a12 * wo[1] + sp.a22 * wo[2] + wk;
     }
     // subtract the left neighbour lane's last-stage rows from this lane's first stage
     PQP_DEV void fix_first_stage(const float (&wlast)[3]) {
         const StagePred sp0 = pred(0);
+        float4 v = V(GBV, 0);
+        float wL[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            float wL = shfl_up(wlast[r], 1, lane);
-            if (lane == 0 || !sp0.real) wL = 0.0f;
-            S(FB + r, 0) -= wL;
+            wL[r] = shfl_up(wlast[r], 1, lane);
+            if (lane == 0 || !sp0.real) wL[r] = 0.0f;
         }
+        v.x -= wL[0]; v.y -= wL[1]; v.z -= wL[2];
+        V(GBV, 0) = v;
     }
 
-    // rhs from the iterates held in shared memory (initial rhs and after a rho update).
-    // `initial`: the outgoing rows' z is z0 (cold: 0, warm: previous z), not yet the bound.
+    // rhs from the iterates held in shared memory (before the first iteration and after a
+    // rho update). `initial`: the outgoing rows' z is z0 (cold: 0, warm: previous z), not yet
+    // the bound.
     PQP_DEV void build_rhs(bool initial, bool warm) {
         float wprev[3] = {0.0f, 0.0f, 0.0f};
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
+            StageRO q;
+            load_ro(k, q);
+            const float4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+            const float x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+            const float oyv[3] = {oy.x, oy.y, oy.z};
             float wo[3], wk, wc[2], bk[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 float z;
                 if (sp.last && r < 2) z = zend[r];
-                else z = initial ? z0_out(warm, r, k) : S(FOB + r, k);
-                wo[r] = S(FOR_ + r, k) * (z - S(FOY + r, k));
+                else z = initial ? z0_out(warm, r, k) : q.ob[r];
+                wo[r] = q.Ro[r] * (z - oyv[r]);
             }
-            wk = S(FKR, k) * (S(FKZ, k) - S(FKY, k));
+            wk = q.Rk * (x1.z - x1.w);
+            wc[0] = q.Rc[0] * (cz.x - cz.z);
+            wc[1] = q.Rc[1] * (cz.y - cz.w);
+            local_rhs(q, sp, x, wo, wk, wc, bk);
+            float4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : 0.0f);
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : 0.0f);
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : 0.0f);
+            bv.w = 0.0f;
+            V(GBV, k) = bv;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) wc[j] = S(FCR + j, k) * (S(FCZ + j, k) - S(FCY + j, k));
-            local_rhs(k, sp, wo, wk, wc, bk);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                S(FB + r, k) = bk[r] - ((sp.real && k > 0) ? wprev[r] : 0.0f);
-                wprev[r] = wo[r];
-            }
+            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
         }
         fix_first_stage(wprev);
     }
 
-    // fold z0 != bound of the equality outgoing rows into yhat (exact)
-    PQP_DEV void fold_initial_z(bool warm) {
-        const float oma = 1.0f - ka.prm.alpha;
-        PQP_ROLL
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                if (!(sp.last && r < 2)) S(FOY + r, k) += oma * (z0_out(warm, r, k) - S(FOB + r, k));
-            }
-        }
-    }
-
     // -------------------------------------------------------------- one ADMM update
-    // in: FB = x~ (state part), FAUX = rhs of (u, s0, s1) used by that solve
-    // out: iterates advanced in shared memory, FB/FAUX = rhs of the next solve
-    PQP_DEV void admm_update(bool store_dy) {
+    // in: GBV = x~ (state part); the rhs of the eliminated variables (u, s0, s1) used by that
+    // solve is recomputed from the (still unchanged) iterates instead of being stored.
+    // out: iterates advanced in shared memory, GBV = rhs of the next solve.
+    // kFirst: first iteration of a solve, where the outgoing equality rows' previous z is
+    // z0 (cold: 0, warm: the previous solve's z) rather than their bound.
+    template <bool kFirst>
+    PQP_DEV void admm_update(bool store_dy, bool warm) {
         const float alpha = ka.prm.alpha, oma = 1.0f - alpha;
         float xnb[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            xnb[c] = shfl_down(S(FB + c, 0), 1, lane);
-            if (lane == 31) xnb[c] = 0.0f;
+        {
+            const float4 v = V(GBV, 0);
+            xnb[0] = shfl_down(v.x, 1, lane);
+            xnb[1] = shfl_down(v.y, 1, lane);
+            xnb[2] = shfl_down(v.z, 1, lane);
+            if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = 0.0f; }
         }
         float wprev[3] = {0.0f, 0.0f, 0.0f};
+        float4 xt = V(GBV, 0);
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
-                        a12 = S(FA + 4, k), ds = S(FA + 5, k);
-            const float lt = S(FB + 0, k), pt = S(FB + 1, k), kt = S(FB + 2, k);
-            const int kn1 = k < C - 1 ? k + 1 : k;
-            const float ln = (k == C - 1) ? xnb[0] : S(FB + 0, kn1);
-            const float pn = (k == C - 1) ? xnb[1] : S(FB + 1, kn1);
-            const float kn = (k == C - 1) ? xnb[2] : S(FB + 2, kn1);
-            // recover the eliminated variables of x~
-            const float miu = S(FE + 0, k), R2 = S(FOR_ + 2, k);
-            const float ut = miu * (S(FAUX + 0, k) - R2 * ds * (sp.a22 * kt + sp.gn * kn));
-            const float s0t = S(FE + 1, k) * (S(FAUX + 1, k) - S(FCR + 0, k) * (lt + sp.h0 * pt));
-            const float s1t = S(FE + 2, k) * (S(FAUX + 2, k) - S(FCR + 1, k) * (lt + sp.h1 * pt));
+            StageRO q;
+            load_ro(k, q);
+            float4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+            const float4 xtn = V(GBV, k < C - 1 ? k + 1 : k);
+            const float lt = xt.x, pt = xt.y, kt = xt.z;
+            const float ln = (k == C - 1) ? xnb[0] : xtn.x;
+            const float pn = (k == C - 1) ? xnb[1] : xtn.y;
+            const float kn = (k == C - 1) ? xnb[2] : xtn.z;
+            // previous z of the outgoing rows
+            float zo_old[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (sp.last && r < 2) zo_old[r] = zend[r];
+                else zo_old[r] = kFirst ? z0_out(warm, r, k) : q.ob[r];
+            }
+            const float oyv[3] = {oy.x, oy.y, oy.z};
+            // recover the eliminated variables of x~ (rhs recomputed from the old iterates)
+            const float aux_u = q.Sw[3] * x0.w + q.ds * (q.Ro[2] * (zo_old[2] - oyv[2]));
+            const float aux_s0 = q.Sw[4] * x1.x + q.Rc[0] * (cz.x - cz.z);
+            const float aux_s1 = q.Sw[5] * x1.y + q.Rc[1] * (cz.y - cz.w);
+            const float ut = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * kt + sp.gn * kn));
+            const float s0t = q.mis0 * (aux_s0 - q.Rc[0] * (lt + sp.h0 * pt));
+            const float s1t = q.mis1 * (aux_s1 - q.Rc[1] * (lt + sp.h1 * pt));
             // z~ = A x~
             float zo[3];
-            zo[0] = a00 * lt + a01 * pt + sp.gn * ln;
-            zo[1] = a10 * lt + a11 * pt + a12 * kt + sp.gn * pn;
-            zo[2] = sp.a22 * kt + ds * ut + sp.gn * kn;
+            zo[0] = q.a00 * lt + q.a01 * pt + sp.gn * ln;
+            zo[1] = q.a10 * lt + q.a11 * pt + q.a12 * kt + sp.gn * pn;
+            zo[2] = sp.a22 * kt + q.ds * ut + sp.gn * kn;
             const float zk = sp.real ? kt : 0.0f;
-            float zc[2];
-            zc[0] = sp.act0 ? (lt + sp.h0 * pt + s0t) : 0.0f;
-            zc[1] = sp.act1 ? (lt + sp.h1 * pt + s1t) : 0.0f;
+            const float zc0 = sp.act0 ? (lt + sp.h0 * pt + s0t) : 0.0f;
+            const float zc1 = sp.act1 ? (lt + sp.h1 * pt + s1t) : 0.0f;
             // x+ = alpha x~ + (1 - alpha) x
-            const float xt6[6] = {lt, pt, kt, ut, s0t, s1t};
-#pragma unroll
-            for (int j = 0; j < 6; ++j) S(FX + j, k) = alpha * xt6[j] + oma * S(FX + j, k);
+            x0.x = alpha * lt + oma * x0.x;
+            x0.y = alpha * pt + oma * x0.y;
+            x0.z = alpha * kt + oma * x0.z;
+            x0.w = alpha * ut + oma * x0.w;
+            x1.x = alpha * s0t + oma * x1.x;
+            x1.y = alpha * s1t + oma * x1.y;
             // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
-            float wo[3], wk, wc[2], bk[3];
+            float wo[3], wk, wc[2], bk[3], oyn[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float bnd = S(FOB + r, k), yh = S(FOY + r, k), R = S(FOR_ + r, k);
-                float zn, yn, zt;
+                const float bnd = q.ob[r];
+                const float zt = alpha * zo[r] + oma * zo_old[r];
+                const float zh = zt + oyv[r];
+                float zn;
                 if (sp.last && r < 2) {
-                    zt = alpha * zo[r] + oma * zend[r];
-                    const float zh = zt + yh;
                     zn = clampf(zh, bnd, bnd + endw[r]);
-                    yn = zh - zn;
                     zend[r] = zn;
                 } else {
-                    zt = alpha * zo[r] + oma * bnd;
                     zn = bnd;
-                    yn = (zt + yh) - bnd;
                 }
-                S(FOY + r, k) = yn;
-                wo[r] = R * (zn - yn);
-                if (store_dy) G(gdy, r, k) = R * (zt - zn);  // delta_y without cancellation
+                oyn[r] = zh - zn;
+                wo[r] = q.Ro[r] * (zn - oyn[r]);
+                if (store_dy) G(gdy, r, k) = q.Ro[r] * (zt - zn);  // delta_y without cancellation
+            }
+            oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
+            {
+                const float zt = alpha * zk + oma * x1.z;
+                const float zh = zt + x1.w;
+                const float zn = clampf(zh, -kmax, kmax);
+                x1.z = zn;
+                x1.w = zh - zn;
+                wk = q.Rk * (zn - x1.w);
+                if (store_dy) G(gdy, 3, k) = q.Rk * (zt - zn);
             }
             {
-                const float z = S(FKZ, k), yh = S(FKY, k), R = S(FKR, k);
-                const float zt = alpha * zk + oma * z;
-                const float zh = zt + yh;
-                const float zn = clampf(zh, -kmax, kmax);
-                const float yn = zh - zn;
-                S(FKZ, k) = zn;
-                S(FKY, k) = yn;
-                wk = R * (zn - yn);
-                if (store_dy) G(gdy, 3, k) = R * (zt - zn);
+                const float zt = alpha * zc0 + oma * cz.x;
+                const float zh = zt + cz.z;
+                const float zn = clampf(zh, q.clo[0], q.chi[0]);
+                cz.x = zn;
+                cz.z = zh - zn;
+                wc[0] = q.Rc[0] * (zn - cz.z);
+                if (store_dy) G(gdy, 4, k) = q.Rc[0] * (zt - zn);
             }
+            {
+                const float zt = alpha * zc1 + oma * cz.y;
+                const float zh = zt + cz.w;
+                const float zn = clampf(zh, q.clo[1], q.chi[1]);
+                cz.y = zn;
+                cz.w = zh - zn;
+                wc[1] = q.Rc[1] * (zn - cz.w);
+                if (store_dy) G(gdy, 5, k) = q.Rc[1] * (zt - zn);
+            }
+            V(GX0, k) = x0;
+            V(GX1, k) = x1;
+            V(GOY, k) = oy;
+            V(GCZ, k) = cz;
+            const float x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+            local_rhs(q, sp, x, wo, wk, wc, bk);
+            float4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : 0.0f);
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : 0.0f);
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : 0.0f);
+            bv.w = 0.0f;
+            V(GBV, k) = bv;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float z = S(FCZ + j, k), yh = S(FCY + j, k), R = S(FCR + j, k);
-                const float zt = alpha * zc[j] + oma * z;
-                const float zh = zt + yh;
-                const float zn = clampf(zh, S(FCLO + j, k), S(FCHI + j, k));
-                const float yn = zh - zn;
-                S(FCZ + j, k) = zn;
-                S(FCY + j, k) = yn;
-                wc[j] = R * (zn - yn);
-                if (store_dy) G(gdy, 4 + j, k) = R * (zt - zn);
-            }
-            local_rhs(k, sp, wo, wk, wc, bk);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                S(FB + r, k) = bk[r] - ((sp.real && k > 0) ? wprev[r] : 0.0f);
-                wprev[r] = wo[r];
-            }
+            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
+            xt = xtn;
         }
         fix_first_stage(wprev);
     }
@@ -1185,7 +1264,6 @@ struct QpWarp {
         bool fok = refactor();
         sync_warp(lane);
         build_rhs(true, warm);
-        fold_initial_z(warm);
 
         int status = fok ? kUnsolved : kNumerical;
         int iter = 0, rho_updates = 0;
@@ -1199,7 +1277,8 @@ struct QpWarp {
                 const bool can_check = P.check_every > 0 && (iter % P.check_every == 0);
                 const bool can_adapt = P.adaptive_rho && P.adaptive_interval > 0 &&
                                        (iter % P.adaptive_interval == 0);
-                admm_update(can_check);
+                if (iter == 1) admm_update<true>(can_check, warm);
+                else admm_update<false>(can_check, warm);
                 checked = false;
                 if (can_check || can_adapt) {
                     nr = residuals();

@@ -7,7 +7,8 @@ the converged point is): for every instance
       the reference's eps_abs = eps_rel = 2e-3 (base_solver.cpp:61-62), evaluated in FP64 on
       the ORACLE-assembled (P, A, l, u), with a 1.25x allowance for the kernel's FP32 norms;
   (3) the objective lies within the envelope an eps=2e-3 OSQP solution itself exhibits around
-      the eps=1e-9 optimum: |f - f*| <= max(1 % f* + 1e-3, 2 |f_oracle - f*|);
+      the eps=1e-9 optimum: |f - f*| <= max(1 % f* + 1e-3, 2 |f_oracle - f*|)
+      + |y*|_1 r_prim + |x - x*|_1 r_dual (the duality slack the measured residuals allow);
   (4) likewise |x - x*|_inf <= max(1e-2, 2 |x_oracle - x*|_inf);
   (5) sol (l, psi, kappa, u per knot) is consistent with x_full.
 """
@@ -73,8 +74,14 @@ def check_instance(params, hb, res, b, *, oracle_solver, x_star=None, cost_star=
             hs.update(*s.lin)
         hs.solve()
         x_star, cost_star = hs.x(), hs.cost
-    env_f = max(0.01 * abs(cost_star) + 1e-3, 2.0 * abs(s.cost - cost_star))
-    assert abs(cost_gpu - cost_star) <= env_f, "%s: cost %g vs f* %g (oracle %g)" % (tag, cost_gpu, cost_star, s.cost)
+        oracle_solver.y_star = hs.y()
+    # weak duality: an eps-feasible point may undercut f* by about |y*|_1 * primal residual,
+    # an eps-stationary one may exceed it by about |x - x*|_1 * dual residual
+    y_star_l1 = float(np.sum(np.abs(getattr(oracle_solver, "y_star", np.zeros(1)))))
+    slack = y_star_l1 * rep["pri_res"] + float(np.sum(np.abs(x - x_star))) * rep["dua_res"]
+    env_f = max(0.01 * abs(cost_star) + 1e-3, 2.0 * abs(s.cost - cost_star)) + slack
+    assert abs(cost_gpu - cost_star) <= env_f, "%s: cost %g vs f* %g (oracle %g, envelope %g)" % (
+        tag, cost_gpu, cost_star, s.cost, env_f)
     dx = float(np.max(np.abs(x - s.x())))
     if x_star is not None:
         env = max(1e-2, 2.0 * float(np.max(np.abs(s.x() - x_star))))

@@ -29,9 +29,9 @@ def _check(hb, params, label, warm=True):
     return stats
 
 
-@pytest.mark.parametrize("n", [2, 3, 31, 32, 63, 64, 120, 127, 128, 240, 255])
+@pytest.mark.parametrize("n", [2, 3, 20, 31, 32, 63, 64, 120, 127, 128, 240, 255])
 def test_emulated_kernel_matches_oracle(n):
-    hb = synthetic.make_batch(100 + n, 3, n)
+    hb = synthetic.make_batch(100 + n, 6 if n <= 64 else 3, n)
     stats = _check(hb, abi.default_params(), "emu n=%d" % n)
     # same algorithm, same schedule: iteration counts track the FP64 oracle (they can differ by a
     # few check intervals when a rho-update decision sits on the 5x threshold)
