@@ -264,6 +264,8 @@ struct QpWarp {
     float crAinv[6], crGm[9], crGp[9];
     // Ruiz cost scaling and current rho
     float cscale, rho;
+    // per-lane partial sums of the primal-infeasibility certificate (last check iteration)
+    float cert_nrm, cert_lhs;
     // per-QP global scratch
     float *gwarm, *gscal, *gdy;
 
@@ -736,10 +738,12 @@ struct QpWarp {
         float acc[3] = {0.0f, 0.0f, 0.0f};
         float4 bv = V(GBV, 0);
         float bk[3] = {bv.x, bv.y, bv.z};
+        // forward sweep; the factor of stage k+1 is prefetched while stage k is processed
+        float f[24], fnx[24];
+        if (C > 1) load_factor(0, f, false);
         PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
-            float f[24];
-            load_factor(k, f, false);
+            if (k + 1 < C - 1) load_factor(k + 1, fnx, false);
             const float *Gm = f + 6, *Fm = f + 15;
             float4 nv = V(GBV, k + 1);
             float bn[3] = {nv.x, nv.y, nv.z};
@@ -752,6 +756,8 @@ struct QpWarp {
             V(GBV, k + 1) = nv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) bk[r] = bn[r];
+#pragma unroll
+            for (int j = 4; j < 24; ++j) f[j] = fnx[j];
         }
         float bs[3];
 #pragma unroll
@@ -760,8 +766,8 @@ struct QpWarp {
             if (lane == 31) fr = 0.0f;
             bs[r] = bk[r] - fr;
         }
-        // cyclic reduction, forward
-        PQP_ROLL
+        // cyclic reduction, forward (unrolled: lane masks become constants)
+#pragma unroll
         for (int t = 0; t < 5; ++t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -789,7 +795,7 @@ struct QpWarp {
             xs[r] = ts[r];
         }
         // cyclic reduction, backward
-        PQP_ROLL
+#pragma unroll
         for (int t = 4; t >= 0; --t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -820,13 +826,15 @@ struct QpWarp {
             v.x = xs[0]; v.y = xs[1]; v.z = xs[2];
             V(GBV, C - 1) = v;
         }
+        // backward sweep, same prefetch scheme (the rhs of the next stage rides along)
+        float4 vcur;
+        if (C > 1) { load_factor(C - 2, f, true); vcur = V(GBV, C - 2); }
         PQP_ROLL
         for (int k = C - 2; k >= 0; --k) {
-            float f[24];
-            load_factor(k, f, true);
+            float4 vnx;
+            if (k > 0) { load_factor(k - 1, fnx, true); vnx = V(GBV, k - 1); }
             const float *Di = f, *Gm = f + 6, *Fm = f + 15;
-            float4 v = V(GBV, k);
-            const float b0 = v.x, b1 = v.y, b2 = v.z;
+            const float b0 = vcur.x, b1 = vcur.y, b2 = vcur.z;
             float xk[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -834,10 +842,13 @@ struct QpWarp {
                 xk[c] = t - (Gm[c] * xn[0] + Gm[3 + c] * xn[1] + Gm[6 + c] * xn[2]) -
                         (Fm[c] * xSL[0] + Fm[3 + c] * xSL[1] + Fm[6 + c] * xSL[2]);
             }
-            v.x = xk[0]; v.y = xk[1]; v.z = xk[2];
-            V(GBV, k) = v;
+            vcur.x = xk[0]; vcur.y = xk[1]; vcur.z = xk[2];
+            V(GBV, k) = vcur;
 #pragma unroll
             for (int c = 0; c < 3; ++c) xn[c] = xk[c];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) f[j] = fnx[j];
+            vcur = vnx;
         }
     }
 
@@ -924,14 +935,28 @@ struct QpWarp {
         fix_first_stage(wprev);
     }
 
+    // -------------------------------------------------------------- infeasibility certificate terms
+    // delta_y of one row (computed without cancellation as R (zt - z+)), projected onto the polar
+    // of the recession cone of [lo, hi] (OSQP is_primal_infeasible); a bound counts as infinite
+    // when |b| >= 1e29 (OSQP_INFTY = 1e30 is the caller's "no bound" value). Accumulates
+    // |dy|_inf and u'max(dy,0) + l'min(dy,0); dy itself goes to global scratch for A'dy.
+    PQP_DEV void cert_row(int r, int k, float dy, float lo, float hi) {
+        const bool hinf = hi >= 1e29f, linf = lo <= -1e29f;
+        if (hinf) dy = linf ? 0.0f : fminf(dy, 0.0f);
+        else if (linf) dy = fmaxf(dy, 0.0f);
+        G(gdy, r, k) = dy;
+        cert_nrm = fmaxf(cert_nrm, fabsf(dy));
+        cert_lhs += (dy > 0.0f ? hi * dy : 0.0f) + (dy < 0.0f ? lo * dy : 0.0f);
+    }
+
     // -------------------------------------------------------------- one ADMM update
     // in: GBV = x~ (state part); the rhs of the eliminated variables (u, s0, s1) used by that
     // solve is recomputed from the (still unchanged) iterates instead of being stored.
     // out: iterates advanced in shared memory, GBV = rhs of the next solve.
-    // kFirst: first iteration of a solve, where the outgoing equality rows' previous z is
+    // first: first iteration of a solve, where the outgoing equality rows' previous z is
     // z0 (cold: 0, warm: the previous solve's z) rather than their bound.
-    template <bool kFirst>
-    PQP_DEV void admm_update(bool store_dy, bool warm) {
+    template <bool kCheck>
+    PQP_DEV void admm_update(bool first, bool warm) {
         const float alpha = ka.prm.alpha, oma = 1.0f - alpha;
         float xnb[3];
         {
@@ -941,6 +966,7 @@ struct QpWarp {
             xnb[2] = shfl_down(v.z, 1, lane);
             if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = 0.0f; }
         }
+        if (kCheck) { cert_nrm = 0.0f; cert_lhs = 0.0f; }
         float wprev[3] = {0.0f, 0.0f, 0.0f};
         float4 xt = V(GBV, 0);
         PQP_ROLL
@@ -959,7 +985,7 @@ struct QpWarp {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 if (sp.last && r < 2) zo_old[r] = zend[r];
-                else zo_old[r] = kFirst ? z0_out(warm, r, k) : q.ob[r];
+                else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
             }
             const float oyv[3] = {oy.x, oy.y, oy.z};
             // recover the eliminated variables of x~ (rhs recomputed from the old iterates)
@@ -1000,7 +1026,7 @@ struct QpWarp {
                 }
                 oyn[r] = zh - zn;
                 wo[r] = q.Ro[r] * (zn - oyn[r]);
-                if (store_dy) G(gdy, r, k) = q.Ro[r] * (zt - zn);  // delta_y without cancellation
+                if (kCheck) cert_row(r, k, q.Ro[r] * (zt - zn), bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
             }
             oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
             {
@@ -1010,7 +1036,7 @@ struct QpWarp {
                 x1.z = zn;
                 x1.w = zh - zn;
                 wk = q.Rk * (zn - x1.w);
-                if (store_dy) G(gdy, 3, k) = q.Rk * (zt - zn);
+                if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
             }
             {
                 const float zt = alpha * zc0 + oma * cz.x;
@@ -1019,7 +1045,7 @@ struct QpWarp {
                 cz.x = zn;
                 cz.z = zh - zn;
                 wc[0] = q.Rc[0] * (zn - cz.z);
-                if (store_dy) G(gdy, 4, k) = q.Rc[0] * (zt - zn);
+                if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
             }
             {
                 const float zt = alpha * zc1 + oma * cz.y;
@@ -1028,7 +1054,7 @@ struct QpWarp {
                 cz.y = zn;
                 cz.w = zh - zn;
                 wc[1] = q.Rc[1] * (zn - cz.w);
-                if (store_dy) G(gdy, 5, k) = q.Rc[1] * (zt - zn);
+                if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
             }
             V(GX0, k) = x0;
             V(GX1, k) = x1;
@@ -1075,6 +1101,10 @@ struct QpWarp {
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
+            // Ruiz scalings (global scratch): issued first so their latency overlaps the rest
+            float ev[6], dv[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { ev[j] = G(gscal, GE + j, k); dv[j] = c * G(gscal, GD + j, k); }
             const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
             const float l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
@@ -1097,7 +1127,7 @@ struct QpWarp {
             z[5] = S(FCZ + 1, k); y[5] = S(FCR + 1, k) * S(FCY + 1, k);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                const float e = G(gscal, GE + r, k);
+                const float e = ev[r];
                 const float rp = fabsf(ax[r] - z[r]);
                 m[0] = fmaxf(m[0], rp); m[1] = fmaxf(m[1], fabsf(ax[r])); m[2] = fmaxf(m[2], fabsf(z[r]));
                 m[6] = fmaxf(m[6], e * rp); m[7] = fmaxf(m[7], e * fabsf(ax[r])); m[8] = fmaxf(m[8], e * fabsf(z[r]));
@@ -1118,7 +1148,7 @@ struct QpWarp {
             px[5] = sp.act1 ? P.w_slack * s1 : 0.0f;
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const float d = c * G(gscal, GD + j, k);
+                const float d = dv[j];
                 const float rd = fabsf(px[j] + aty[j]);
                 m[3] = fmaxf(m[3], rd); m[4] = fmaxf(m[4], fabsf(px[j])); m[5] = fmaxf(m[5], fabsf(aty[j]));
                 m[9] = fmaxf(m[9], d * rd); m[10] = fmaxf(m[10], d * fabsf(px[j])); m[11] = fmaxf(m[11], d * fabsf(aty[j]));
@@ -1132,34 +1162,11 @@ struct QpWarp {
         return nr;
     }
 
-    // OSQP is_primal_infeasible on the delta_y stored by the last admm_update(true)
+    // OSQP is_primal_infeasible; |dy| and the bound term were accumulated by admm_update<true>
     PQP_DEV bool primal_infeasible(float eps) {
-        sync_warp(lane);
         const float c = cscale;
-        float nrm = 0.0f, lhs = 0.0f;
-        PQP_ROLL
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-            const int cls = GCLSI(k);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                float dy = G(gdy, r, k);
-                float lo, hi;
-                if (r < 3) { lo = S(FOB + r, k); hi = lo + ((sp.last && r < 2) ? endw[r] : 0.0f); }
-                else if (r == 3) { lo = -kmax; hi = kmax; }
-                else { lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k); }
-                const float e = G(gscal, GE + r, k);
-                const bool hinf = hi * e > kOsqpInfty * kMinScaling, linf = lo * e < -kOsqpInfty * kMinScaling;
-                if (hinf) dy = linf ? 0.0f : fminf(dy, 0.0f);
-                else if (linf) dy = fmaxf(dy, 0.0f);
-                if (((cls >> (2 * r)) & 3) == 3) dy = 0.0f;
-                G(gdy, r, k) = dy;
-                nrm = fmaxf(nrm, fabsf(dy));
-                lhs += (dy > 0.0f ? hi * dy : 0.0f) + (dy < 0.0f ? lo * dy : 0.0f);
-            }
-        }
-        nrm = warp_max(nrm, lane);
-        lhs = warp_sum(lhs, lane);
+        const float nrm = warp_max(cert_nrm, lane);
+        const float lhs = warp_sum(cert_lhs, lane);
         if (!(c * nrm > eps)) return false;
         if (!(lhs < -eps * nrm)) return false;
         sync_warp(lane);
@@ -1252,6 +1259,7 @@ struct QpWarp {
         gscal = ka.scal + (size_t)qp * NSCAL * plane;
         gdy = ka.dy + (size_t)qp * NDY * plane;
         zend[0] = zend[1] = endw[0] = endw[1] = 0.0f;
+        cert_nrm = cert_lhs = 0.0f;
         const bool warm = ka.mode == 1;
         rho = warm ? ka.rho_state[qp] : P.rho0;
         rho = fminf(fmaxf(rho, kRhoMin), kRhoMax);
@@ -1272,13 +1280,17 @@ struct QpWarp {
         bool checked = false;
         if (fok) {
             PQP_ROLL
+            int to_check = P.check_every > 0 ? P.check_every : -1;
+            int to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
             for (iter = 1; iter <= P.max_iter; ++iter) {
                 solve();
-                const bool can_check = P.check_every > 0 && (iter % P.check_every == 0);
-                const bool can_adapt = P.adaptive_rho && P.adaptive_interval > 0 &&
-                                       (iter % P.adaptive_interval == 0);
-                if (iter == 1) admm_update<true>(can_check, warm);
-                else admm_update<false>(can_check, warm);
+                // iter % interval == 0 without an integer division in the loop
+                const bool can_check = (--to_check == 0);
+                const bool can_adapt = (--to_adapt == 0);
+                if (can_check) to_check = P.check_every;
+                if (can_adapt) to_adapt = P.adaptive_interval;
+                if (can_check) admm_update<true>(iter == 1, warm);
+                else admm_update<false>(iter == 1, warm);
                 checked = false;
                 if (can_check || can_adapt) {
                     nr = residuals();
