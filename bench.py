@@ -163,7 +163,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from path_optimizer_2_b200 import solver
+    from path_optimizer_2_b200 import sharding, solver
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -190,15 +190,12 @@ def main():
     bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
                              None, None, None, None)
     # gathered per-instance results {cost f64, status i32, iters i32} = 16 B / instance
-    packed = torch.zeros((B, 2), dtype=torch.float64, device=dev)
     gathered = torch.zeros((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
 
     def step_device():
         sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
-        if world > 1:
-            packed[:, 0] = d_cost
-            packed[:, 1] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
-            dist.all_gather_into_tensor(gathered, packed)
+        if world > 1:  # the only exchange: all-gather of {cost, status, iters} over NCCL
+            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
 
     def barrier():
         torch.cuda.synchronize()
@@ -221,9 +218,7 @@ def main():
         sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
         kev[i][1].record()
         if world > 1:
-            packed[:, 0] = d_cost
-            packed[:, 1] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
-            dist.all_gather_into_tensor(gathered, packed)
+            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
         ev[i + 1].record()
     barrier()
     launches = sv.launch_count - launches0

@@ -160,7 +160,7 @@ typedef struct pqp_handle pqp_handle;
 int pqp_default_params(pqp_params *params);
 
 /* Create a solver bound to CUDA device `device` able to hold `batch_max` instances of up
- * to `n_max` knots (2 <= n_max <= 256). Owns device buffers for inputs, outputs and the
+ * to `n_max` knots (2 <= n_max <= 255). Owns device buffers for inputs, outputs and the
  * per-instance warm state (scaled x, z, y and rho; the OSQP workspace of
  * base_solver.hpp:62). */
 int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32_t device,
@@ -192,9 +192,9 @@ int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *
 int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n,
                             const double *ref_xyh, const double *sol, double *out_xyh);
 
-/* Device time (ms) of the last solve/resolve kernel launched through the host-pointer
- * API (CUDA events on the launching stream), and the number of kernel launches the
- * handle has issued so far. */
+/* Device time (ms) of the last host-pointer solve/resolve, first copy to last copy (CUDA
+ * events on the handle's streams; the call is a chunked H2D / kernel / D2H pipeline), and the
+ * number of kernel launches the handle has issued so far. */
 int pqp_last_kernel_ms(pqp_handle *h, float *ms);
 int pqp_launch_count(pqp_handle *h, int64_t *count);
 

@@ -126,7 +126,8 @@ struct pqp_handle {
     int n_max = 0, batch_max = 0, device = 0, chunk = 0;
     int sm_count = 0, warps_per_sm = 0;
     size_t smem_bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t evs[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device buffers owned by the handle
     double *d_knots = nullptr, *d_inst = nullptr, *d_sol = nullptr, *d_cost = nullptr, *d_info = nullptr;
@@ -189,12 +190,13 @@ int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *o
 
 // device pointers in `in`/`out`; asynchronous
 int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode,
-               cudaStream_t s, bool timed) {
+               cudaStream_t s, bool timed, int qp0 = 0) {
     pqp::KernelArgs ka;
     ka.prm = pqp::make_dev_params(h->prm);
     ka.batch = in->batch;
     ka.n_max = in->n_max;
     ka.mode = mode;
+    ka.qp0 = qp0;
     const size_t block_bytes = (size_t)PQP_NFIELDS * in->n_max * sizeof(double);
     ka.use_tma = ((block_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in->knots) % 16) == 0) ? 1 : 0;
     ka.knots = in->knots;
@@ -218,7 +220,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     if (timed) PQP_CUDA(h, cudaEventRecord(h->ev1, s));
     h->launches++;
     h->solved = true;
-    h->last_batch = in->batch;
+    if (qp0 == 0) h->last_batch = in->batch;
     return PQP_OK;
 }
 
@@ -242,10 +244,6 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
             if (in->p && (in->p[b] < 0 || in->p[b] > in->n[b])) return fail(h, PQP_E_INVALID, "p[b] must be in [0, n[b]]");
         }
         if (mode == 1 && (!h->solved || B != h->last_batch)) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
-        PQP_CUDA(h, cudaMemcpyAsync(h->d_knots, in->knots, (size_t)B * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, s));
-        PQP_CUDA(h, cudaMemcpyAsync(h->d_inst, in->inst, (size_t)B * PQP_NINST * sizeof(double), cudaMemcpyHostToDevice, s));
-        PQP_CUDA(h, cudaMemcpyAsync(h->d_n, in->n, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
-        if (in->p) PQP_CUDA(h, cudaMemcpyAsync(h->d_p, in->p, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
         h->host_inputs_resident = true;
         h->d_p_valid = in->p != nullptr;
     } else {
@@ -263,36 +261,70 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     if (out->x_full && !h->d_xf) PQP_CUDA(h, dmalloc(&h->d_xf, (size_t)h->batch_max * nvm));
     if (out->y_full && !h->d_yf) PQP_CUDA(h, dmalloc(&h->d_yf, (size_t)h->batch_max * mm));
     if (out->z_full && !h->d_zf) PQP_CUDA(h, dmalloc(&h->d_zf, (size_t)h->batch_max * mm));
-    if (out->x_full) PQP_CUDA(h, cudaMemsetAsync(h->d_xf, 0, (size_t)B * nvm * sizeof(double), s));
-    if (out->y_full) PQP_CUDA(h, cudaMemsetAsync(h->d_yf, 0, (size_t)B * mm * sizeof(double), s));
-    if (out->z_full) PQP_CUDA(h, cudaMemsetAsync(h->d_zf, 0, (size_t)B * mm * sizeof(double), s));
-    pqp_batch_in din;
-    din.batch = B;
-    din.n_max = nmax;
-    din.knots = h->d_knots;
-    din.inst = h->d_inst;
-    din.n = h->d_n;
-    din.p = h->d_p_valid ? h->d_p : nullptr;
-    pqp_batch_out dout;
-    dout.sol = h->d_sol;
-    dout.cost = h->d_cost;
-    dout.status = h->d_status;
-    dout.iters = h->d_iters;
-    dout.x_full = out->x_full ? h->d_xf : nullptr;
-    dout.y_full = out->y_full ? h->d_yf : nullptr;
-    dout.z_full = out->z_full ? h->d_zf : nullptr;
-    dout.info = h->d_info;
-    rc = run_device(h, &din, &dout, mode, s, true);
-    if (rc) return rc;
-    PQP_CUDA(h, cudaMemcpyAsync(out->sol, h->d_sol, (size_t)B * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost, h->d_cost, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status, h->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out->iters) PQP_CUDA(h, cudaMemcpyAsync(out->iters, h->d_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out->info) PQP_CUDA(h, cudaMemcpyAsync(out->info, h->d_info, (size_t)B * PQP_NINFO * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->x_full) PQP_CUDA(h, cudaMemcpyAsync(out->x_full, h->d_xf, (size_t)B * nvm * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->y_full) PQP_CUDA(h, cudaMemcpyAsync(out->y_full, h->d_yf, (size_t)B * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full, h->d_zf, (size_t)B * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
-    PQP_CUDA(h, cudaStreamSynchronize(s));
+    // Chunked two-stream pipeline: chunk c+1's H2D copy and chunk c-1's D2H copy overlap chunk
+    // c's kernel (fully asynchronous when the caller's buffers are pinned). Scratch slots are
+    // addressed by the instance's index in the whole batch (qp0), so chunking is invisible to
+    // the warm state.
+    const int kMinChunk = 1024;
+    int nchunks = (B + kMinChunk - 1) / kMinChunk;
+    if (nchunks > 8) nchunks = 8;
+    if (nchunks < 1) nchunks = 1;
+    const int per = (B + nchunks - 1) / nchunks;
+    cudaStream_t streams[2] = {h->stream, h->stream2};
+    if (!in) {  // relinearise ran on streams[0]: make stream2 wait for it
+        PQP_CUDA(h, cudaEventRecord(h->evs[0], streams[0]));
+        PQP_CUDA(h, cudaStreamWaitEvent(streams[1], h->evs[0], 0));
+    }
+    PQP_CUDA(h, cudaEventRecord(h->ev0, streams[0]));
+    for (int c = 0; c < nchunks; ++c) {
+        const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
+        if (lo >= hi) break;
+        const size_t nb = (size_t)(hi - lo);
+        cudaStream_t s = streams[c & 1];
+        if (in) {
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_knots + (size_t)lo * PQP_NFIELDS * nmax, in->knots + (size_t)lo * PQP_NFIELDS * nmax,
+                                        nb * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_inst + (size_t)lo * PQP_NINST, in->inst + (size_t)lo * PQP_NINST,
+                                        nb * PQP_NINST * sizeof(double), cudaMemcpyHostToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_n + lo, in->n + lo, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+            if (in->p) PQP_CUDA(h, cudaMemcpyAsync(h->d_p + lo, in->p + lo, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        }
+        if (out->x_full) PQP_CUDA(h, cudaMemsetAsync(h->d_xf + lo * nvm, 0, nb * nvm * sizeof(double), s));
+        if (out->y_full) PQP_CUDA(h, cudaMemsetAsync(h->d_yf + lo * mm, 0, nb * mm * sizeof(double), s));
+        if (out->z_full) PQP_CUDA(h, cudaMemsetAsync(h->d_zf + lo * mm, 0, nb * mm * sizeof(double), s));
+        pqp_batch_in din;
+        din.batch = (int32_t)nb;
+        din.n_max = nmax;
+        din.knots = h->d_knots + (size_t)lo * PQP_NFIELDS * nmax;
+        din.inst = h->d_inst + (size_t)lo * PQP_NINST;
+        din.n = h->d_n + lo;
+        din.p = h->d_p_valid ? h->d_p + lo : nullptr;
+        pqp_batch_out dout;
+        dout.sol = h->d_sol + (size_t)lo * 4 * nmax;
+        dout.cost = h->d_cost + lo;
+        dout.status = h->d_status + lo;
+        dout.iters = h->d_iters + lo;
+        dout.x_full = out->x_full ? h->d_xf + lo * nvm : nullptr;
+        dout.y_full = out->y_full ? h->d_yf + lo * mm : nullptr;
+        dout.z_full = out->z_full ? h->d_zf + lo * mm : nullptr;
+        dout.info = h->d_info + (size_t)lo * PQP_NINFO;
+        rc = run_device(h, &din, &dout, mode, s, false, lo);
+        if (rc) return rc;
+        PQP_CUDA(h, cudaMemcpyAsync(out->sol + (size_t)lo * 4 * nmax, dout.sol, nb * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost + lo, dout.cost, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status + lo, dout.status, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (out->iters) PQP_CUDA(h, cudaMemcpyAsync(out->iters + lo, dout.iters, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (out->info) PQP_CUDA(h, cudaMemcpyAsync(out->info + (size_t)lo * PQP_NINFO, dout.info, nb * PQP_NINFO * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->x_full) PQP_CUDA(h, cudaMemcpyAsync(out->x_full + lo * nvm, dout.x_full, nb * nvm * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->y_full) PQP_CUDA(h, cudaMemcpyAsync(out->y_full + lo * mm, dout.y_full, nb * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full + lo * mm, dout.z_full, nb * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    h->last_batch = B;
+    // join: stream[0] waits for stream[1]; ev1 marks the end of the whole pipeline
+    PQP_CUDA(h, cudaEventRecord(h->evs[1], streams[1]));
+    PQP_CUDA(h, cudaStreamWaitEvent(streams[0], h->evs[1], 0));
+    PQP_CUDA(h, cudaEventRecord(h->ev1, streams[0]));
+    PQP_CUDA(h, cudaStreamSynchronize(streams[0]));
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return PQP_OK;
 }
@@ -357,6 +389,9 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     }
     h->warps_per_sm = bps;
     PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[0], cudaEventDisableTiming));
+    PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[1], cudaEventDisableTiming));
     PQP_CREATE_CUDA(cudaEventCreate(&h->ev0));
     PQP_CREATE_CUDA(cudaEventCreate(&h->ev1));
     const size_t B = batch_max, c = h->chunk;
@@ -392,6 +427,9 @@ int pqp_destroy(pqp_handle *h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->evs[0]) cudaEventDestroy(h->evs[0]);
+    if (h->evs[1]) cudaEventDestroy(h->evs[1]);
     delete h;
     return PQP_OK;
 }

@@ -108,6 +108,7 @@ struct DevParams {
 struct KernelArgs {
     DevParams prm;
     int batch, n_max, mode, use_tma;  // mode 0 cold, 1 warm
+    int qp0;                          // index of this launch's first instance in the handle's scratch
     const double *knots, *inst;
     const int *n, *p;
     double *sol, *cost;
@@ -1255,13 +1256,14 @@ struct QpWarp {
         lr = (float)P.rear_length;
         kmax = (float)P.kappa_limit;
         const size_t plane = (size_t)C * 32;
-        gwarm = ka.warm + (size_t)qp * NWARM * plane;
-        gscal = ka.scal + (size_t)qp * NSCAL * plane;
-        gdy = ka.dy + (size_t)qp * NDY * plane;
+        const size_t slot = (size_t)(qp + ka.qp0);  // per-instance scratch slot in the handle
+        gwarm = ka.warm + slot * NWARM * plane;
+        gscal = ka.scal + slot * NSCAL * plane;
+        gdy = ka.dy + slot * NDY * plane;
         zend[0] = zend[1] = endw[0] = endw[1] = 0.0f;
         cert_nrm = cert_lhs = 0.0f;
         const bool warm = ka.mode == 1;
-        rho = warm ? ka.rho_state[qp] : P.rho0;
+        rho = warm ? ka.rho_state[qp + ka.qp0] : P.rho0;
         rho = fminf(fmaxf(rho, kRhoMin), kRhoMax);
 
         assemble(src, stride);
@@ -1414,7 +1416,7 @@ struct QpWarp {
                 double *inf = ka.info + (size_t)qp * 4;
                 inf[0] = nr.pri; inf[1] = nr.dua; inf[2] = rho; inf[3] = rho_updates;
             }
-            ka.rho_state[qp] = rho;
+            ka.rho_state[qp + ka.qp0] = rho;
         }
     }
 };

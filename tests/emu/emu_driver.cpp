@@ -43,6 +43,7 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     ka.n_max = in->n_max;
     ka.mode = mode;
     ka.use_tma = 0;
+    ka.qp0 = 0;
     ka.knots = in->knots;
     ka.inst = in->inst;
     ka.n = in->n;
