@@ -972,6 +972,10 @@ double pqo_solve_batch(const pqp_params *prm, const pqp_batch_in *in, const pqp_
         const int n = in->n[b];
         const int p = in->p ? in->p[b] : n;
         const double *kn = in->knots + (size_t)b * PQP_NFIELDS * nmax;
+#ifdef _OPENMP
+        const int dbg = getenv("PQO_DEBUG") != NULL;
+        const double tb0 = now_s();
+#endif
         pqo_ws *w = pqo_setup(prm, n, p, kn, nmax, in->inst + (size_t)b * PQP_NINST);
         if (!w) {
 #ifdef _OPENMP
@@ -980,9 +984,12 @@ double pqo_solve_batch(const pqp_params *prm, const pqp_batch_in *in, const pqp_
             err = 1;
             continue;
         }
+        const double tb1 = now_s();
         if (dense_assembly) sink += assemble_dense_style(w);
         int st = pqo_solve(w);
         int iters = w->iter;
+        const double tb2 = now_s();
+        if (dbg) fprintf(stderr, "inst %d setup %.2f ms solve %.2f ms iters %d\n", b, 1e3 * (tb1 - tb0), 1e3 * (tb2 - tb1), iters);
         if (mode == 1 && (st == PQP_SOLVED)) {
             double *sol = (double *)malloc(sizeof(double) * 4 * n);
             pqo_get_sol(w, sol, n);
@@ -1008,8 +1015,26 @@ double pqo_solve_batch(const pqp_params *prm, const pqp_batch_in *in, const pqp_
             inf[PQP_INFO_RHO_UPDATES] = w->rho_updates;
         }
         pqo_free(w);
+#ifdef _OPENMP
+        if (dbg) fprintf(stderr, "inst %d thread %d start %.4f end %.4f\n", b, omp_get_thread_num(), tb0 - t0, now_s() - t0);
+#endif
     }
     const double t1 = now_s();
     (void)sink;
     return err ? -1.0 : (t1 - t0);
+}
+
+/* number of threads an OpenMP region with `nthreads` requested actually gets (diagnostic) */
+int pqo_omp_probe(int nthreads) {
+    int cnt = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+    {
+#pragma omp atomic
+        cnt++;
+    }
+#else
+    cnt = 1;
+#endif
+    return cnt;
 }
