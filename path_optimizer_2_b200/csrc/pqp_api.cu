@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "pqp_host_common.h"
 
@@ -57,9 +59,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // ------------------------------------------------------------------ device: kernel entry
 // One CTA = one warp = one QP instance. Dynamic shared memory: NFIELD*C*32 floats of
 // solver state (the factor region doubles as the FP64 input staging buffer) + 1 mbarrier.
-template <int C>
+template <int C, typename real>
 __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pqp::KernelArgs ka) {
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    real *smem = reinterpret_cast<real *>(smem_raw);
     const int lane = threadIdx.x;
     const int qp = blockIdx.x;
     if (qp >= ka.batch) return;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pq
         mbar_wait(bar, 0);
         src = stage;
     }
-    pqp::QpWarp<C> w(ka, smem, lane, qp);
+    pqp::QpWarp<C, real> w(ka, smem, lane, qp);
     w.run(src, ka.n_max);
 }
 
@@ -133,7 +136,20 @@ struct pqp_handle {
     double *d_knots = nullptr, *d_inst = nullptr, *d_sol = nullptr, *d_cost = nullptr, *d_info = nullptr;
     double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
     int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
-    float *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    void *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    bool fp64 = false;             // params.reserved bit 1: iterate in FP64
+    bool escalate = true;          // params.reserved bit 2 clears it
+    size_t smem_bytes64 = 0;
+    bool prepared64 = false;
+    int *d_flags = nullptr;
+    int *h_status = nullptr, *h_flags = nullptr;  // pinned host mirrors
+    // FP64 escalation of suspected-infeasible instances (small side batch)
+    int esc_cap = 0;
+    double *e_knots = nullptr, *e_inst = nullptr, *e_sol = nullptr, *e_cost = nullptr, *e_info = nullptr;
+    double *e_xf = nullptr, *e_yf = nullptr, *e_zf = nullptr;
+    int *e_n = nullptr, *e_p = nullptr, *e_status = nullptr, *e_iters = nullptr;
+    void *e_warm = nullptr, *e_scal = nullptr, *e_dy = nullptr, *e_rho = nullptr;
+    long long escalated = 0;
     double *d_sol2 = nullptr;
     int *d_n2 = nullptr;
     bool solved = false, host_inputs_resident = false, d_p_valid = false;
@@ -159,24 +175,34 @@ int cuda_fail(pqp_handle *h, cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call);  \
     } while (0)
 
-template <int C>
+template <int C, typename real>
 cudaError_t launch(const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
-    pqp_admm_kernel<C><<<ka.batch, 32, smem, s>>>(ka);
+    pqp_admm_kernel<C, real><<<ka.batch, 32, smem, s>>>(ka);
     return cudaGetLastError();
 }
+template <typename real>
 cudaError_t launch_chunk(int chunk, const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
     switch (chunk) {
-        case 1: return launch<1>(ka, smem, s);
-        case 2: return launch<2>(ka, smem, s);
-        case 4: return launch<4>(ka, smem, s);
-        default: return launch<8>(ka, smem, s);
+        case 1: return launch<1, real>(ka, smem, s);
+        case 2: return launch<2, real>(ka, smem, s);
+        case 4: return launch<4, real>(ka, smem, s);
+        default: return launch<8, real>(ka, smem, s);
     }
 }
-template <int C>
+template <int C, typename real>
 cudaError_t prepare(size_t smem, int *blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel<C, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, pqp_admm_kernel<C>, 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, pqp_admm_kernel<C, real>, 32, smem);
+}
+template <typename real>
+cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
+    switch (chunk) {
+        case 1: return prepare<1, real>(smem, bps);
+        case 2: return prepare<2, real>(smem, bps);
+        case 4: return prepare<4, real>(smem, bps);
+        default: return prepare<8, real>(smem, bps);
+    }
 }
 
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
@@ -190,7 +216,7 @@ int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *o
 
 // device pointers in `in`/`out`; asynchronous
 int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode,
-               cudaStream_t s, bool timed, int qp0 = 0) {
+               cudaStream_t s, bool timed, int qp0 = 0, bool esc = false, int *flags = nullptr) {
     pqp::KernelArgs ka;
     ka.prm = pqp::make_dev_params(h->prm);
     ka.batch = in->batch;
@@ -211,16 +237,28 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     ka.y_full = out->y_full;
     ka.z_full = out->z_full;
     ka.info = out->info;
-    ka.warm = h->d_warm;
-    ka.scal = h->d_scal;
-    ka.dy = h->d_dy;
-    ka.rho_state = h->d_rho;
+    ka.flags = flags;
+    ka.warm = esc ? h->e_warm : h->d_warm;
+    ka.scal = esc ? h->e_scal : h->d_scal;
+    ka.dy = esc ? h->e_dy : h->d_dy;
+    ka.rho_state = esc ? h->e_rho : h->d_rho;
     if (timed) PQP_CUDA(h, cudaEventRecord(h->ev0, s));
-    PQP_CUDA(h, launch_chunk(h->chunk, ka, h->smem_bytes, s));
+    if (esc || h->fp64) {
+        if (!h->prepared64) {
+            int bps = 0;
+            PQP_CUDA(h, prepare_chunk<double>(h->chunk, h->smem_bytes64, &bps));
+            h->prepared64 = true;
+        }
+        PQP_CUDA(h, launch_chunk<double>(h->chunk, ka, h->smem_bytes64, s));
+    } else {
+        PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
+    }
     if (timed) PQP_CUDA(h, cudaEventRecord(h->ev1, s));
     h->launches++;
-    h->solved = true;
-    if (qp0 == 0) h->last_batch = in->batch;
+    if (!esc) {
+        h->solved = true;
+        if (qp0 == 0) h->last_batch = in->batch;
+    }
     return PQP_OK;
 }
 
@@ -228,6 +266,79 @@ template <typename T>
 cudaError_t dmalloc(T **p, size_t count) {
     return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
 }
+
+// Instances the FP32 kernel could neither solve nor certify (iteration cap reached while the
+// first two conditions of OSQP's primal-infeasibility certificate held) are re-solved cold by
+// the FP64 instantiation of the same kernel: FP32 iterates resolve |A'dy| < 1e-4 |dy| only to
+// ~5e-4, FP64 ones reproduce the reference's PRIMAL_INFEASIBLE status. Rare path,
+// plain synchronous copies.
+int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int B) {
+    std::vector<int> idx;
+    for (int b = 0; b < B; ++b)
+        if (h->h_status[b] == PQP_MAX_ITER_REACHED && (h->h_flags[b] & 1)) idx.push_back(b);
+    if (idx.empty()) return PQP_OK;
+    const int nmax = h->n_max;
+    const size_t c = h->chunk;
+    const size_t nvm = 6 * (size_t)nmax - 1, mm = 6 * (size_t)nmax + 2;
+    if (!h->e_knots) {
+        h->esc_cap = h->batch_max < 256 ? h->batch_max : 256;
+        const size_t E = h->esc_cap;
+        PQP_CUDA(h, dmalloc(&h->e_knots, E * PQP_NFIELDS * nmax));
+        PQP_CUDA(h, dmalloc(&h->e_inst, E * PQP_NINST));
+        PQP_CUDA(h, dmalloc(&h->e_n, E));
+        PQP_CUDA(h, dmalloc(&h->e_p, E));
+        PQP_CUDA(h, dmalloc(&h->e_sol, E * 4 * nmax));
+        PQP_CUDA(h, dmalloc(&h->e_cost, E));
+        PQP_CUDA(h, dmalloc(&h->e_status, E));
+        PQP_CUDA(h, dmalloc(&h->e_iters, E));
+        PQP_CUDA(h, dmalloc(&h->e_info, E * PQP_NINFO));
+        PQP_CUDA(h, dmalloc(&h->e_xf, E * nvm));
+        PQP_CUDA(h, dmalloc(&h->e_yf, E * mm));
+        PQP_CUDA(h, dmalloc(&h->e_zf, E * mm));
+        PQP_CUDA(h, cudaMalloc(&h->e_warm, E * pqp::warm_floats(c) * sizeof(double)));
+        PQP_CUDA(h, cudaMalloc(&h->e_scal, E * pqp::scal_floats(c) * sizeof(double)));
+        PQP_CUDA(h, cudaMalloc(&h->e_dy, E * pqp::dy_floats(c) * sizeof(double)));
+        PQP_CUDA(h, cudaMalloc(&h->e_rho, E * sizeof(double)));
+    }
+    cudaStream_t s = h->stream;
+    const size_t kb = (size_t)PQP_NFIELDS * nmax;
+    for (size_t start = 0; start < idx.size(); start += h->esc_cap) {
+        const int E = (int)std::min(idx.size() - start, (size_t)h->esc_cap);
+        for (int j = 0; j < E; ++j) {
+            const int b = idx[start + j];
+            // inputs come from the handle's device copy (valid for both host-batch and NULL-batch calls)
+            PQP_CUDA(h, cudaMemcpyAsync(h->e_knots + j * kb, h->d_knots + b * kb, kb * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->e_inst + (size_t)j * PQP_NINST, h->d_inst + (size_t)b * PQP_NINST, PQP_NINST * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->e_n + j, h->d_n + b, sizeof(int), cudaMemcpyDeviceToDevice, s));
+            if (h->d_p_valid) PQP_CUDA(h, cudaMemcpyAsync(h->e_p + j, h->d_p + b, sizeof(int), cudaMemcpyDeviceToDevice, s));
+        }
+        PQP_CUDA(h, cudaMemsetAsync(h->e_xf, 0, (size_t)E * nvm * sizeof(double), s));
+        PQP_CUDA(h, cudaMemsetAsync(h->e_yf, 0, (size_t)E * mm * sizeof(double), s));
+        PQP_CUDA(h, cudaMemsetAsync(h->e_zf, 0, (size_t)E * mm * sizeof(double), s));
+        pqp_batch_in din = {E, nmax, h->e_knots, h->e_inst, h->e_n, h->d_p_valid ? h->e_p : nullptr};
+        pqp_batch_out dout = {h->e_sol, h->e_cost, h->e_status, h->e_iters, h->e_xf, h->e_yf, h->e_zf, h->e_info};
+        int rc = run_device(h, &din, &dout, 0, s, false, 0, true, nullptr);
+        if (rc) return rc;
+        for (int j = 0; j < E; ++j) {
+            const int b = idx[start + j];
+            PQP_CUDA(h, cudaMemcpyAsync(out->sol + (size_t)b * 4 * nmax, h->e_sol + (size_t)j * 4 * nmax, 4 * (size_t)nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost + b, h->e_cost + j, sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status + b, h->e_status + j, sizeof(int), cudaMemcpyDeviceToHost, s));
+            if (out->iters) PQP_CUDA(h, cudaMemcpyAsync(out->iters + b, h->e_iters + j, sizeof(int), cudaMemcpyDeviceToHost, s));
+            if (out->info) PQP_CUDA(h, cudaMemcpyAsync(out->info + (size_t)b * PQP_NINFO, h->e_info + (size_t)j * PQP_NINFO, PQP_NINFO * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->x_full) PQP_CUDA(h, cudaMemcpyAsync(out->x_full + b * nvm, h->e_xf + j * nvm, nvm * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->y_full) PQP_CUDA(h, cudaMemcpyAsync(out->y_full + b * mm, h->e_yf + j * mm, mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full + b * mm, h->e_zf + j * mm, mm * sizeof(double), cudaMemcpyDeviceToHost, s));
+            // keep the device-resident results coherent too (resolve(NULL) linearises about d_sol)
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_sol + (size_t)b * 4 * nmax, h->e_sol + (size_t)j * 4 * nmax, 4 * (size_t)nmax * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_status + b, h->e_status + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
+        }
+        PQP_CUDA(h, cudaStreamSynchronize(s));
+        h->escalated += E;
+    }
+    return PQP_OK;
+}
+
 
 int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode) {
     int rc;
@@ -308,8 +419,10 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         dout.y_full = out->y_full ? h->d_yf + lo * mm : nullptr;
         dout.z_full = out->z_full ? h->d_zf + lo * mm : nullptr;
         dout.info = h->d_info + (size_t)lo * PQP_NINFO;
-        rc = run_device(h, &din, &dout, mode, s, false, lo);
+        rc = run_device(h, &din, &dout, mode, s, false, lo, false, h->d_flags + lo);
         if (rc) return rc;
+        PQP_CUDA(h, cudaMemcpyAsync(h->h_status + lo, dout.status, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
+        PQP_CUDA(h, cudaMemcpyAsync(h->h_flags + lo, h->d_flags + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         PQP_CUDA(h, cudaMemcpyAsync(out->sol + (size_t)lo * 4 * nmax, dout.sol, nb * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost + lo, dout.cost, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status + lo, dout.status, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -326,6 +439,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     PQP_CUDA(h, cudaEventRecord(h->ev1, streams[0]));
     PQP_CUDA(h, cudaStreamSynchronize(streams[0]));
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (!h->fp64 && h->escalate) return escalate_fp64(h, in, out, B);
     return PQP_OK;
 }
 
@@ -380,12 +494,15 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
         }                                                                         \
     } while (0)
     PQP_CREATE_CUDA(cudaSetDevice(device));
+    h->fp64 = (params->reserved & 2) != 0;
+    h->escalate = (params->reserved & 4) == 0;
+    h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
-    switch (h->chunk) {
-        case 1: PQP_CREATE_CUDA(prepare<1>(h->smem_bytes, &bps)); break;
-        case 2: PQP_CREATE_CUDA(prepare<2>(h->smem_bytes, &bps)); break;
-        case 4: PQP_CREATE_CUDA(prepare<4>(h->smem_bytes, &bps)); break;
-        default: PQP_CREATE_CUDA(prepare<8>(h->smem_bytes, &bps)); break;
+    if (h->fp64) {
+        PQP_CREATE_CUDA(prepare_chunk<double>(h->chunk, h->smem_bytes64, &bps));
+        h->prepared64 = true;
+    } else {
+        PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps));
     }
     h->warps_per_sm = bps;
     PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -404,11 +521,16 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(dmalloc(&h->d_status, B));
     PQP_CREATE_CUDA(dmalloc(&h->d_iters, B));
     PQP_CREATE_CUDA(dmalloc(&h->d_info, B * PQP_NINFO));
-    PQP_CREATE_CUDA(dmalloc(&h->d_warm, B * pqp::warm_floats(c)));
-    PQP_CREATE_CUDA(dmalloc(&h->d_scal, B * pqp::scal_floats(c)));
-    PQP_CREATE_CUDA(dmalloc(&h->d_dy, B * pqp::dy_floats(c)));
-    PQP_CREATE_CUDA(dmalloc(&h->d_rho, B));
-    PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * sizeof(float)));
+    const size_t esz = h->fp64 ? sizeof(double) : sizeof(float);
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_warm, B * pqp::warm_floats(c) * esz));
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_scal, B * pqp::scal_floats(c) * esz));
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, B * pqp::dy_floats(c) * esz));
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
+    PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
+    PQP_CREATE_CUDA(dmalloc(&h->d_flags, B));
+    PQP_CREATE_CUDA(cudaMemset(h->d_flags, 0, B * sizeof(int)));
+    PQP_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_status), B * sizeof(int)));
+    PQP_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_flags), B * sizeof(int)));
     PQP_CREATE_CUDA(cudaMemset(h->d_sol, 0, B * 4 * n_max * sizeof(double)));
 #undef PQP_CREATE_CUDA
     *out = h;
@@ -424,6 +546,12 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_info); cudaFree(h->d_xf); cudaFree(h->d_yf); cudaFree(h->d_zf);
     cudaFree(h->d_ref); cudaFree(h->d_xy); cudaFree(h->d_sol2); cudaFree(h->d_n2);
     cudaFree(h->d_warm); cudaFree(h->d_scal); cudaFree(h->d_dy); cudaFree(h->d_rho);
+    cudaFree(h->d_flags);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    cudaFree(h->e_knots); cudaFree(h->e_inst); cudaFree(h->e_sol); cudaFree(h->e_cost); cudaFree(h->e_info);
+    cudaFree(h->e_xf); cudaFree(h->e_yf); cudaFree(h->e_zf); cudaFree(h->e_n); cudaFree(h->e_p);
+    cudaFree(h->e_status); cudaFree(h->e_iters); cudaFree(h->e_warm); cudaFree(h->e_scal); cudaFree(h->e_dy); cudaFree(h->e_rho);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);

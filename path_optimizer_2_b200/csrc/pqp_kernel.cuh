@@ -45,13 +45,13 @@ struct alignas(16) float4 { float x, y, z, w; };
 namespace pqp {
 
 // ------------------------------------------------------------------ constants (OSQP 0.6.x)
-constexpr float kOsqpInfty = 1e30f;
-constexpr float kMinScaling = 1e-4f;
-constexpr float kMaxScaling = 1e4f;
-constexpr float kRhoMin = 1e-6f;
-constexpr float kRhoMax = 1e6f;
-constexpr float kRhoEqOverIneq = 1e3f;
-constexpr float kRhoTol = 1e-4f;
+constexpr double kOsqpInfty = 1e30;
+constexpr double kMinScaling = 1e-4;
+constexpr double kMaxScaling = 1e4;
+constexpr double kRhoMin = 1e-6;
+constexpr double kRhoMax = 1e6;
+constexpr double kRhoEqOverIneq = 1e3;
+constexpr double kRhoTol = 1e-4;
 
 // status codes: keep in sync with include/pqp.h
 constexpr int kSolved = 0, kMaxIter = 1, kPrimInf = 2, kDualInf = 3, kSolvedInacc = 4,
@@ -99,8 +99,8 @@ enum : int {
 
 struct DevParams {
     double front_length, rear_length, kappa_limit, safety_margin, end_l_lb, end_l_ub;
-    float w_l, w_kappa, w_dkappa, w_slack;
-    float rho0, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, rho_tol;
+    double w_l, w_kappa, w_dkappa, w_slack;
+    double rho0, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, rho_tol;
     int max_iter, check_every, scaling, adaptive_rho, adaptive_interval;
     int factor_fp64;
 };
@@ -113,8 +113,9 @@ struct KernelArgs {
     const int *n, *p;
     double *sol, *cost;
     int *status, *iters;
+    int *flags;  // optional: bit 0 = infeasibility suspected (certificate conditions 1-2 held)
     double *x_full, *y_full, *z_full, *info;
-    float *warm, *scal, *dy, *rho_state;
+    void *warm, *scal, *dy, *rho_state;  // per-instance scratch in the kernel's scalar type
 };
 
 // ------------------------------------------------------------------ warp primitives
@@ -129,8 +130,6 @@ template <typename T> PQP_DEV T shfl_xor(T v, int m, int lane) {
     return warp_emu::exchange(v, lane, lane ^ m);
 }
 PQP_DEV void sync_warp(int lane) { warp_emu::current()->barrier(lane); }
-PQP_DEV float frsqrt(float x) { return 1.0f / std::sqrt(x); }
-PQP_DEV float fdivf(float a, float b) { return a / b; }
 using std::fabs;
 using std::fmax;
 using std::fmin;
@@ -140,26 +139,41 @@ template <typename T> PQP_DEV T shfl_up(T v, int d, int) { return __shfl_up_sync
 template <typename T> PQP_DEV T shfl_down(T v, int d, int) { return __shfl_down_sync(0xffffffffu, v, d); }
 template <typename T> PQP_DEV T shfl_xor(T v, int m, int) { return __shfl_xor_sync(0xffffffffu, v, m); }
 PQP_DEV void sync_warp(int) { __syncwarp(); }
-PQP_DEV float frsqrt(float x) { return 1.0f / sqrtf(x); }
-PQP_DEV float fdivf(float a, float b) { return a / b; }
 #endif
 
-PQP_DEV float warp_max(float v, int lane) {
+// scalar-type generic math (the kernel is instantiated for float and for double)
+PQP_DEV float xmax(float a, float b) { return fmaxf(a, b); }
+PQP_DEV double xmax(double a, double b) { return fmax(a, b); }
+PQP_DEV float xmin(float a, float b) { return fminf(a, b); }
+PQP_DEV double xmin(double a, double b) { return fmin(a, b); }
+PQP_DEV float xabs(float a) { return fabsf(a); }
+PQP_DEV double xabs(double a) { return fabs(a); }
+PQP_DEV float xsqrt(float a) { return sqrtf(a); }
+PQP_DEV double xsqrt(double a) { return sqrt(a); }
+template <typename T> PQP_DEV T frsqrt(T x) { return T(1) / xsqrt(x); }
+
+template <typename T> PQP_DEV T warp_max(T v, int lane) {
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, shfl_xor(v, m, lane));
+    for (int m = 16; m >= 1; m >>= 1) v = xmax(v, shfl_xor(v, m, lane));
     return v;
 }
-PQP_DEV float warp_sum(float v, int lane) {
+template <typename T> PQP_DEV T warp_sum(T v, int lane) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) v += shfl_xor(v, m, lane);
     return v;
 }
 
-PQP_DEV float limit_scaling(float v) {
-    v = v < kMinScaling ? 1.0f : v;
-    return v > kMaxScaling ? kMaxScaling : v;
+template <typename T> PQP_DEV T limit_scaling(T v) {
+    v = v < T(kMinScaling) ? T(1) : v;
+    return v > T(kMaxScaling) ? T(kMaxScaling) : v;
 }
-PQP_DEV float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+template <typename T> PQP_DEV T clampf(T v, T lo, T hi) { return xmin(xmax(v, lo), hi); }
+
+// 4-wide vector of the kernel's scalar type (one shared-memory "group")
+template <typename T> struct Vec4T;
+template <> struct Vec4T<float> { typedef float4 type; };
+struct alignas(32) pqp_double4 { double x, y, z, w; };
+template <> struct Vec4T<double> { typedef pqp_double4 type; };
 
 // ------------------------------------------------------------------ 3x3 helpers
 // symmetric 3x3 as [6] = (00,01,02,11,12,22); general 3x3 row-major [9]
@@ -172,15 +186,15 @@ template <typename T> PQP_DEV bool inv_sym3(const T (&a)[6], T (&o)[6]) {
     bool ok = true;
     T p0 = a[0];
     ok = ok && (p0 > T(0));
-    T i00 = T(1) / sqrt(p0);
+    T i00 = T(1) / xsqrt(p0);
     T l10 = a[1] * i00, l20 = a[2] * i00;
     T p1 = a[3] - l10 * l10;
     ok = ok && (p1 > T(0));
-    T i11 = T(1) / sqrt(p1);
+    T i11 = T(1) / xsqrt(p1);
     T l21 = (a[4] - l20 * l10) * i11;
     T p2 = a[5] - l20 * l20 - l21 * l21;
     ok = ok && (p2 > T(0));
-    T i22 = T(1) / sqrt(p2);
+    T i22 = T(1) / xsqrt(p2);
     T i10 = -l10 * i00 * i11;
     T i21 = -l21 * i11 * i22;
     T i20 = -(l20 * i00 + l21 * i10) * i22;
@@ -252,34 +266,38 @@ PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, doubl
 // cache (40 % no_inst stalls in profiles/r1/ncu_v1_unrolled_summary.txt).
 #define PQP_ROLL _Pragma("unroll 1")
 
-template <int C>
+template <int C, typename real>
 struct QpWarp {
+    typedef typename Vec4T<real>::type Vec4;
     const KernelArgs &ka;
-    float *sm;
+    real *sm;
     const int lane, qp;
     int n, p;
-    float lf, lr, kmax;
+    real lf, lr, kmax;
     // end rows (valid on the lane/stage that owns knot n-1)
-    float zend[2], endw[2];
+    real zend[2], endw[2];
     // separator (cyclic reduction) factors of this lane
-    float crAinv[6], crGm[9], crGp[9];
+    real crAinv[6], crGm[9], crGp[9];
     // Ruiz cost scaling and current rho
-    float cscale, rho;
+    real cscale, rho;
     // per-lane partial sums of the primal-infeasibility certificate (last check iteration)
-    float cert_nrm, cert_lhs;
+    real cert_nrm, cert_lhs;
+    int suspect;  // certificate conditions 1-2 held at the last check (warp-uniform)
     // per-QP global scratch
-    float *gwarm, *gscal, *gdy;
+    real *gwarm, *gscal, *gdy;
+    // solver parameters in the kernel's scalar type
+    real w_l, w_kappa, w_dkappa, w_slack, sigma, alpha, eps_abs, eps_rel, eps_pinf, rho_tol;
 
-    PQP_DEV QpWarp(const KernelArgs &k, float *s, int l, int q) : ka(k), sm(s), lane(l), qp(q) {}
+    PQP_DEV QpWarp(const KernelArgs &k, real *s, int l, int q) : ka(k), sm(s), lane(l), qp(q) {}
 
     // scalar view of logical field f (group f>>2, component f&3)
-    PQP_DEV float &S(int f, int k) { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
-    PQP_DEV float &SL(int f, int k, int ln) { return sm[(((f >> 2) * C + k) * 32 + ln) * 4 + (f & 3)]; }
+    PQP_DEV real &S(int f, int k) { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
+    PQP_DEV real &SL(int f, int k, int ln) { return sm[(((f >> 2) * C + k) * 32 + ln) * 4 + (f & 3)]; }
     // vector view of group g
-    PQP_DEV float4 &V(int g, int k) { return reinterpret_cast<float4 *>(sm)[(g * C + k) * 32 + lane]; }
-    PQP_DEV float &G(float *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
-    PQP_DEV float &GL(float *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
-    PQP_DEV int &GCLSI(int k) { return reinterpret_cast<int *>(gscal)[(GCLS * C + k) * 32 + lane]; }
+    PQP_DEV Vec4 &V(int g, int k) { return reinterpret_cast<Vec4 *>(sm)[(g * C + k) * 32 + lane]; }
+    PQP_DEV real &G(real *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
+    PQP_DEV real &GL(real *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
+    PQP_DEV int &GCLSI(int k) { return *reinterpret_cast<int *>(&gscal[(GCLS * C + k) * 32 + lane]); }
     PQP_DEV StagePred pred(int k) const { return stage_pred(lane * C + k, n, p, lf, lr); }
 
     // -------------------------------------------------------------- assembly
@@ -290,13 +308,13 @@ struct QpWarp {
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const int g = lane * C + k;
-            float a[6] = {0, 0, 0, 0, 0, 0};
-            float ob[3] = {0, 0, 0};
-            float clo[2] = {0, 0}, chi[2] = {0, 0};
+            real a[6] = {0, 0, 0, 0, 0, 0};
+            real ob[3] = {0, 0, 0};
+            real clo[2] = {0, 0}, chi[2] = {0, 0};
             if (g == 0) {
-                ob[0] = (float)(-in[0]);
-                ob[1] = (float)(-in[1]);
-                ob[2] = (float)(-in[2]);
+                ob[0] = (real)(-in[0]);
+                ob[1] = (real)(-in[1]);
+                ob[2] = (real)(-in[2]);
             } else if (g <= n - 1) {
                 const int i = g - 1;
                 const double xl = src[2 * stride + i], xp = src[3 * stride + i], xk = src[4 * stride + i];
@@ -307,39 +325,39 @@ struct QpWarp {
                 const double f00 = -xk * tp, f01 = (1 - xk * xl) / (cp * cp);
                 const double f10 = -xk * xk / cp, f11 = (1 - xk * xl) * xk * tp / cp,
                              f12 = (1 - xk * xl) / cp;
-                a[0] = (float)(ds * f00 + 1.0);
-                a[1] = (float)(ds * f01);
-                a[2] = (float)(ds * f10);
-                a[3] = (float)(ds * f11 + 1.0);
-                a[4] = (float)(ds * f12);
-                a[5] = (float)ds;
+                a[0] = (real)(ds * f00 + 1.0);
+                a[1] = (real)(ds * f01);
+                a[2] = (real)(ds * f10);
+                a[3] = (real)(ds * f11 + 1.0);
+                a[4] = (real)(ds * f12);
+                a[5] = (real)ds;
                 const double u_in = (xkn - xk) / ds;
                 const double g0 = (1 - xk * xl) * tp;
                 const double g1 = (1 - xk * xl) * xk / cp - kref;
                 const double c0 = ds * (g0 - (f00 * xl + f01 * xp));
                 const double c1 = ds * (g1 - (f10 * xl + f11 * xp + f12 * xk));
                 const double c2 = ds * (u_in - u_in);
-                ob[0] = (float)(-c0);
-                ob[1] = (float)(-c1);
-                ob[2] = (float)(-c2);
+                ob[0] = (real)(-c0);
+                ob[1] = (real)(-c1);
+                ob[2] = (real)(-c2);
             } else if (g == n) {
-                a[0] = 1.0f;  // end-l row:   1 * l_{n-1}
-                a[3] = 1.0f;  // end-psi row: 1 * psi_{n-1}
-                ob[0] = (float)P.end_l_lb;
-                endw[0] = (float)(P.end_l_ub - P.end_l_lb);
-                ob[1] = (float)in[3];
-                endw[1] = (float)(in[4] - in[3]);
+                a[0] = real(1.0);  // end-l row:   1 * l_{n-1}
+                a[3] = real(1.0);  // end-psi row: 1 * psi_{n-1}
+                ob[0] = (real)P.end_l_lb;
+                endw[0] = (real)(P.end_l_ub - P.end_l_lb);
+                ob[1] = (real)in[3];
+                endw[1] = (real)(in[4] - in[3]);
             }
             if (g >= 1 && g <= n) {
                 const int i = g - 1;
                 double lo, hi;
                 soft_bounds(src[5 * stride + i], src[6 * stride + i], P.safety_margin, lo, hi);
-                clo[0] = (float)lo;
-                chi[0] = (float)hi;
+                clo[0] = (real)lo;
+                chi[0] = (real)hi;
                 if (g <= p) {
                     soft_bounds(src[7 * stride + i], src[8 * stride + i], P.safety_margin, lo, hi);
-                    clo[1] = (float)lo;
-                    chi[1] = (float)hi;
+                    clo[1] = (real)lo;
+                    chi[1] = (real)hi;
                 }
             }
 #pragma unroll
@@ -363,63 +381,63 @@ struct QpWarp {
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
 #pragma unroll
-            for (int j = 0; j < 12; ++j) S(FT + j, k) = 1.0f;
+            for (int j = 0; j < 12; ++j) S(FT + j, k) = real(1.0);
         }
-        float c = 1.0f;
-        const float nv_inv = 1.0f / (float)(3 * n + (n - 1) + (p + n));
+        real c = real(1.0);
+        const real nv_inv = real(1.0) / (real)(3 * n + (n - 1) + (p + n));
         int cur = 0;
         for (int pass = 0; pass < P.scaling; ++pass) {
             sync_warp(lane);
             const int FD0 = FT + 12 * cur, FE0 = FD0 + 6, FD1 = FT + 12 * (1 - cur), FE1 = FD1 + 6;
-            float psum = 0.0f;
+            real psum = real(0.0);
             PQP_ROLL
             for (int k = 0; k < C; ++k) {
                 const StagePred sp = pred(k);
-                const float a00 = fabsf(S(FA + 0, k)), a01 = fabsf(S(FA + 1, k)), a10 = fabsf(S(FA + 2, k)),
-                            a11 = fabsf(S(FA + 3, k)), a12 = fabsf(S(FA + 4, k)), ds = fabsf(S(FA + 5, k));
-                const float gn = fabsf(sp.gn), h0 = fabsf(sp.h0), h1 = fabsf(sp.h1);
-                float dk[6], ek[6], eL[3], dR[3];
+                const real a00 = xabs(S(FA + 0, k)), a01 = xabs(S(FA + 1, k)), a10 = xabs(S(FA + 2, k)),
+                            a11 = xabs(S(FA + 3, k)), a12 = xabs(S(FA + 4, k)), ds = xabs(S(FA + 5, k));
+                const real gn = xabs(sp.gn), h0 = xabs(sp.h0), h1 = xabs(sp.h1);
+                real dk[6], ek[6], eL[3], dR[3];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) { dk[j] = S(FD0 + j, k); ek[j] = S(FE0 + j, k); }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    eL[r] = (k > 0) ? S(FE0 + r, k > 0 ? k - 1 : 0) : (lane > 0 ? SL(FE0 + r, C - 1, lane > 0 ? lane - 1 : 0) : 0.0f);
-                    dR[r] = (k < C - 1) ? S(FD0 + r, k < C - 1 ? k + 1 : k) : (lane < 31 ? SL(FD0 + r, 0, lane < 31 ? lane + 1 : lane) : 0.0f);
+                    eL[r] = (k > 0) ? S(FE0 + r, k > 0 ? k - 1 : 0) : (lane > 0 ? SL(FE0 + r, C - 1, lane > 0 ? lane - 1 : 0) : real(0.0));
+                    dR[r] = (k < C - 1) ? S(FD0 + r, k < C - 1 ? k + 1 : k) : (lane < 31 ? SL(FD0 + r, 0, lane < 31 ? lane + 1 : lane) : real(0.0));
                 }
                 // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
-                const float hasL = sp.real ? 1.0f : 0.0f;
-                const float ec0 = sp.act0 ? ek[4] : 0.0f, ec1 = sp.act1 ? ek[5] : 0.0f;
-                const float ekap = sp.real ? ek[3] : 0.0f;
-                float cn[6];
-                cn[0] = dk[0] * fmaxf(fmaxf(a00 * ek[0], a10 * ek[1]), fmaxf(hasL * eL[0], fmaxf(ec0, ec1)));
-                cn[1] = dk[1] * fmaxf(fmaxf(a01 * ek[0], a11 * ek[1]), fmaxf(hasL * eL[1], fmaxf(h0 * ec0, h1 * ec1)));
-                cn[2] = dk[2] * fmaxf(fmaxf(a12 * ek[1], sp.a22 * ek[2]), fmaxf(hasL * eL[2], ekap));
+                const real hasL = sp.real ? real(1.0) : real(0.0);
+                const real ec0 = sp.act0 ? ek[4] : real(0.0), ec1 = sp.act1 ? ek[5] : real(0.0);
+                const real ekap = sp.real ? ek[3] : real(0.0);
+                real cn[6];
+                cn[0] = dk[0] * xmax(xmax(a00 * ek[0], a10 * ek[1]), xmax(hasL * eL[0], xmax(ec0, ec1)));
+                cn[1] = dk[1] * xmax(xmax(a01 * ek[0], a11 * ek[1]), xmax(hasL * eL[1], xmax(h0 * ec0, h1 * ec1)));
+                cn[2] = dk[2] * xmax(xmax(a12 * ek[1], sp.a22 * ek[2]), xmax(hasL * eL[2], ekap));
                 cn[3] = dk[3] * ds * ek[2];
                 cn[4] = dk[4] * ec0;
                 cn[5] = dk[5] * ec1;
-                const float pw[6] = {sp.real ? P.w_l : 0.0f, 0.0f, sp.real ? P.w_kappa : 0.0f,
-                                     sp.mid ? P.w_dkappa : 0.0f, sp.act0 ? P.w_slack : 0.0f,
-                                     sp.act1 ? P.w_slack : 0.0f};
+                const real pw[6] = {sp.real ? w_l : real(0.0), real(0.0), sp.real ? w_kappa : real(0.0),
+                                     sp.mid ? w_dkappa : real(0.0), sp.act0 ? w_slack : real(0.0),
+                                     sp.act1 ? w_slack : real(0.0)};
 #pragma unroll
-                for (int j = 0; j < 6; ++j) cn[j] = fmaxf(cn[j], c * dk[j] * dk[j] * pw[j]);
-                float rn[6];
-                rn[0] = ek[0] * fmaxf(fmaxf(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
-                rn[1] = ek[1] * fmaxf(fmaxf(a10 * dk[0], a11 * dk[1]), fmaxf(a12 * dk[2], gn * dR[1]));
-                rn[2] = ek[2] * fmaxf(fmaxf(sp.a22 * dk[2], ds * dk[3]), gn * dR[2]);
+                for (int j = 0; j < 6; ++j) cn[j] = xmax(cn[j], c * dk[j] * dk[j] * pw[j]);
+                real rn[6];
+                rn[0] = ek[0] * xmax(xmax(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
+                rn[1] = ek[1] * xmax(xmax(a10 * dk[0], a11 * dk[1]), xmax(a12 * dk[2], gn * dR[1]));
+                rn[2] = ek[2] * xmax(xmax(sp.a22 * dk[2], ds * dk[3]), gn * dR[2]);
                 rn[3] = ekap * dk[2];
-                rn[4] = ec0 * fmaxf(fmaxf(dk[0], h0 * dk[1]), dk[4]);
-                rn[5] = ec1 * fmaxf(fmaxf(dk[0], h1 * dk[1]), dk[5]);
+                rn[4] = ec0 * xmax(xmax(dk[0], h0 * dk[1]), dk[4]);
+                rn[5] = ec1 * xmax(xmax(dk[0], h1 * dk[1]), dk[5]);
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    const float dnw = dk[j] * frsqrt(limit_scaling(cn[j]));
+                    const real dnw = dk[j] * frsqrt(limit_scaling(cn[j]));
                     S(FD1 + j, k) = dnw;
                     S(FE1 + j, k) = ek[j] * frsqrt(limit_scaling(rn[j]));
                     psum += dnw * dnw * pw[j];
                 }
             }
             // cost normalisation: c_temp = 1 / limit(max(mean_j |Pbar_jj|, 1))   (q = 0 -> 1)
-            const float mean = c * warp_sum(psum, lane) * nv_inv;
-            float ct = fmaxf(mean, 1.0f);
+            const real mean = c * warp_sum(psum, lane) * nv_inv;
+            real ct = xmax(mean, real(1.0));
             ct = limit_scaling(ct);
             c = c / ct;
             cur = 1 - cur;
@@ -427,31 +445,31 @@ struct QpWarp {
         sync_warp(lane);
         cscale = c;
         const int FDc = FT + 12 * cur, FEc = FDc + 6;
-        const float cinv = 1.0f / c;
+        const real cinv = real(1.0) / c;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             int cls = 0;
-            float e[6];
+            real e[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const float d = S(FDc + j, k);
+                const real d = S(FDc + j, k);
                 e[j] = S(FEc + j, k);
                 G(gscal, GD + j, k) = d;
                 G(gscal, GE + j, k) = e[j];
-                S(FS + j, k) = ka.prm.sigma * cinv / (d * d);
+                S(FS + j, k) = sigma * cinv / (d * d);
             }
             // dummy variables get an identity pivot
-            if (!sp.real) { S(FS + 0, k) = 1.0f; S(FS + 1, k) = 1.0f; S(FS + 2, k) = 1.0f; S(FS + 4, k) = 1.0f; }
-            if (!sp.mid) S(FS + 3, k) = 1.0f;
-            if (!sp.act1) S(FS + 5, k) = 1.0f;
+            if (!sp.real) { S(FS + 0, k) = real(1.0); S(FS + 1, k) = real(1.0); S(FS + 2, k) = real(1.0); S(FS + 4, k) = real(1.0); }
+            if (!sp.mid) S(FS + 3, k) = real(1.0);
+            if (!sp.act1) S(FS + 5, k) = real(1.0);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                float lo, hi;
+                real lo, hi;
                 bool act;
                 if (r < 3) {
                     lo = S(FOB + r, k);
-                    hi = lo + ((sp.last && r < 2) ? endw[r] : 0.0f);
+                    hi = lo + ((sp.last && r < 2) ? endw[r] : real(0.0));
                     act = (lane * C + k <= n - 1) || (sp.last && r < 2);
                 } else if (r == 3) {
                     lo = -kmax; hi = kmax; act = sp.real;
@@ -459,15 +477,15 @@ struct QpWarp {
                     lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k);
                     act = (r == 4) ? sp.act0 : sp.act1;
                 }
-                const float ls = lo * e[r], hs = hi * e[r];
+                const real ls = lo * e[r], hs = hi * e[r];
                 int cl;
                 if (!act) cl = 3;
-                else if (ls < -kOsqpInfty * kMinScaling && hs > kOsqpInfty * kMinScaling) cl = 2;
-                else if (hs - ls < kRhoTol) cl = 1;
+                else if (ls < real(-kOsqpInfty * kMinScaling) && hs > real(kOsqpInfty * kMinScaling)) cl = 2;
+                else if (hs - ls < real(kRhoTol)) cl = 1;
                 else cl = 0;
                 cls |= cl << (2 * r);
-                const float base = (cl == 3) ? 0.0f : (cl == 2 ? kRhoMin : (cl == 1 ? kRhoEqOverIneq * rho : rho));
-                const float Rw = base * e[r] * e[r] * cinv;
+                const real base = (cl == 3) ? real(0.0) : (cl == 2 ? real(kRhoMin) : (cl == 1 ? real(kRhoEqOverIneq) * rho : rho));
+                const real Rw = base * e[r] * e[r] * cinv;
                 if (r < 3) S(FOR_ + r, k) = Rw;
                 else if (r == 3) S(FKR, k) = Rw;
                 else S(FCR + r - 4, k) = Rw;
@@ -478,19 +496,19 @@ struct QpWarp {
 
     // -------------------------------------------------------------- iterates: cold / warm
     PQP_DEV void init_iterates(bool warm) {
-        const float c = cscale;
+        const real c = cscale;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             if (!warm) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) S(FX + j, k) = 0.0f;
+                for (int j = 0; j < 6; ++j) S(FX + j, k) = real(0.0);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) S(FOY + r, k) = 0.0f;
-                S(FKZ, k) = 0.0f; S(FKY, k) = 0.0f;
+                for (int r = 0; r < 3; ++r) S(FOY + r, k) = real(0.0);
+                S(FKZ, k) = real(0.0); S(FKY, k) = real(0.0);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) { S(FCZ + j, k) = 0.0f; S(FCY + j, k) = 0.0f; }
-                if (sp.last) { zend[0] = 0.0f; zend[1] = 0.0f; }
+                for (int j = 0; j < 2; ++j) { S(FCZ + j, k) = real(0.0); S(FCY + j, k) = real(0.0); }
+                if (sp.last) { zend[0] = real(0.0); zend[1] = real(0.0); }
             } else {
                 // scaled iterates of the previous solve are re-interpreted in the NEW scaling
                 // (OSQP keeps work->x/z/y untouched across osqp_update_A's re-scaling)
@@ -498,20 +516,20 @@ struct QpWarp {
                 for (int j = 0; j < 6; ++j) S(FX + j, k) = G(gwarm, WX + j, k) * G(gscal, GD + j, k);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float e = G(gscal, GE + r, k), R = S(FOR_ + r, k);
-                    const float y = G(gwarm, WOY + r, k) * e / c;
-                    S(FOY + r, k) = R > 0.0f ? y / R : 0.0f;
+                    const real e = G(gscal, GE + r, k), R = S(FOR_ + r, k);
+                    const real y = G(gwarm, WOY + r, k) * e / c;
+                    S(FOY + r, k) = R > real(0.0) ? y / R : real(0.0);
                 }
                 {
-                    const float e = G(gscal, GE + 3, k), R = S(FKR, k);
+                    const real e = G(gscal, GE + 3, k), R = S(FKR, k);
                     S(FKZ, k) = G(gwarm, WKZ, k) / e;
-                    S(FKY, k) = R > 0.0f ? (G(gwarm, WKY, k) * e / c) / R : 0.0f;
+                    S(FKY, k) = R > real(0.0) ? (G(gwarm, WKY, k) * e / c) / R : real(0.0);
                 }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const float e = G(gscal, GE + 4 + j, k), R = S(FCR + j, k);
+                    const real e = G(gscal, GE + 4 + j, k), R = S(FCR + j, k);
                     S(FCZ + j, k) = G(gwarm, WCZ + j, k) / e;
-                    S(FCY + j, k) = R > 0.0f ? (G(gwarm, WCY + j, k) * e / c) / R : 0.0f;
+                    S(FCY + j, k) = R > real(0.0) ? (G(gwarm, WCY + j, k) * e / c) / R : real(0.0);
                 }
                 if (sp.last) {
                     zend[0] = G(gwarm, WOZ + 0, k) / G(gscal, GE + 0, k);
@@ -522,8 +540,8 @@ struct QpWarp {
     }
 
     // z of outgoing row r at the start of a (warm) solve, before the first iteration
-    PQP_DEV float z0_out(bool warm, int r, int k) {
-        return warm ? G(gwarm, WOZ + r, k) / G(gscal, GE + r, k) : 0.0f;
+    PQP_DEV real z0_out(bool warm, int r, int k) {
+        return warm ? G(gwarm, WOZ + r, k) / G(gscal, GE + r, k) : real(0.0);
     }
 
     // -------------------------------------------------------------- factorisation
@@ -534,10 +552,10 @@ struct QpWarp {
         const DevParams &P = ka.prm;
         const T ds = S(FA + 5, k);
         const T R2 = S(FOR_ + 2, k);
-        const T pu = sp.mid ? T(P.w_dkappa) : T(0);
+        const T pu = sp.mid ? T(w_dkappa) : T(0);
         const T mu = pu + T(S(FS + 3, k)) + R2 * ds * ds;
         const T miu = T(1) / mu;
-        if (store) S(FE + 0, k) = (float)miu;
+        if (store) S(FE + 0, k) = (real)miu;
         Rt[0] = S(FOR_ + 0, k);
         Rt[1] = S(FOR_ + 1, k);
         Rt[2] = R2 - (R2 * ds * miu) * R2 * ds;
@@ -552,15 +570,15 @@ struct QpWarp {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const bool act = j == 0 ? sp.act0 : sp.act1;
-            const T ps = act ? T(P.w_slack) : T(0);
+            const T ps = act ? T(w_slack) : T(0);
             const T Rcj = S(FCR + j, k);
             const T ms = ps + T(S(FS + 4 + j, k)) + Rcj;
             const T mis = T(1) / ms;
-            S(FE + 1 + j, k) = (float)mis;
+            S(FE + 1 + j, k) = (real)mis;
             Rc[j] = Rcj - (Rcj * mis) * Rcj;
         }
         const T h0 = sp.h0, h1 = sp.h1;
-        const T pk = sp.real ? T(P.w_kappa) : T(0), pl = sp.real ? T(P.w_l) : T(0);
+        const T pk = sp.real ? T(w_kappa) : T(0), pl = sp.real ? T(w_l) : T(0);
         const T hasL = sp.real ? T(1) : T(0);
         D[0] = T(S(FS + 0, k)) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
         D[1] = Rt[0] * a00 * a01 + Rt[1] * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
@@ -628,9 +646,9 @@ struct QpWarp {
             mul_ms(O, Dinv, Gh);
             mul_ms(Phi, Dinv, Fh);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) S(FDI + j, k) = (float)Dinv[j];
+            for (int j = 0; j < 6; ++j) S(FDI + j, k) = (real)Dinv[j];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { S(FG + j, k) = (float)Gh[j]; S(FF + j, k) = (float)Fh[j]; }
+            for (int j = 0; j < 9; ++j) { S(FG + j, k) = (real)Gh[j]; S(FF + j, k) = (real)Fh[j]; }
             T t6[6], t9[9];
             mul_abt_sym(Fh, Phi, t6);
 #pragma unroll
@@ -717,37 +735,37 @@ struct QpWarp {
             for (int j = 0; j < 6; ++j) myAinv[j] = Ainv[j];
         }
 #pragma unroll
-        for (int j = 0; j < 6; ++j) crAinv[j] = (float)myAinv[j];
+        for (int j = 0; j < 6; ++j) crAinv[j] = (real)myAinv[j];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) { crGm[j] = (float)myGm[j]; crGp[j] = (float)myGp[j]; }
-        float bad = ok ? 0.0f : 1.0f;
+        for (int j = 0; j < 9; ++j) { crGm[j] = (real)myGm[j]; crGp[j] = (real)myGp[j]; }
+        real bad = ok ? real(0.0) : real(1.0);
         bad = warp_max(bad, lane);
-        return bad == 0.0f;
+        return bad == real(0.0);
     }
 
     // -------------------------------------------------------------- solve  M_red x = b
     // b lives in shared memory (group GBV); overwritten by the solution. The factor of one
-    // stage is 6 float4 (Dinv[6] G[9] F[9] packed contiguously).
-    PQP_DEV void load_factor(int k, float (&f)[24], bool with_dinv) {
+    // stage is 6 Vec4 (Dinv[6] G[9] F[9] packed contiguously).
+    PQP_DEV void load_factor(int k, real (&f)[24], bool with_dinv) {
 #pragma unroll
         for (int g = with_dinv ? 0 : 1; g < 6; ++g) {
-            const float4 v = V(GF0 + g, k);
+            const Vec4 v = V(GF0 + g, k);
             f[4 * g] = v.x; f[4 * g + 1] = v.y; f[4 * g + 2] = v.z; f[4 * g + 3] = v.w;
         }
     }
     PQP_DEV void solve() {
-        float acc[3] = {0.0f, 0.0f, 0.0f};
-        float4 bv = V(GBV, 0);
-        float bk[3] = {bv.x, bv.y, bv.z};
+        real acc[3] = {real(0.0), real(0.0), real(0.0)};
+        Vec4 bv = V(GBV, 0);
+        real bk[3] = {bv.x, bv.y, bv.z};
         // forward sweep; the factor of stage k+1 is prefetched while stage k is processed
-        float f[24], fnx[24];
+        real f[24], fnx[24];
         if (C > 1) load_factor(0, f, false);
         PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
             if (k + 1 < C - 1) load_factor(k + 1, fnx, false);
-            const float *Gm = f + 6, *Fm = f + 15;
-            float4 nv = V(GBV, k + 1);
-            float bn[3] = {nv.x, nv.y, nv.z};
+            const real *Gm = f + 6, *Fm = f + 15;
+            Vec4 nv = V(GBV, k + 1);
+            real bn[3] = {nv.x, nv.y, nv.z};
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 bn[r] -= Gm[3 * r] * bk[0] + Gm[3 * r + 1] * bk[1] + Gm[3 * r + 2] * bk[2];
@@ -760,11 +778,11 @@ struct QpWarp {
 #pragma unroll
             for (int j = 4; j < 24; ++j) f[j] = fnx[j];
         }
-        float bs[3];
+        real bs[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            float fr = shfl_down(acc[r], 1, lane);
-            if (lane == 31) fr = 0.0f;
+            real fr = shfl_down(acc[r], 1, lane);
+            if (lane == 31) fr = real(0.0);
             bs[r] = bk[r] - fr;
         }
         // cyclic reduction, forward (unrolled: lane masks become constants)
@@ -773,23 +791,23 @@ struct QpWarp {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
             const bool surv = (lane & (2 * h - 1)) == 0;
-            float upd[3];
+            real upd[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                float vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
-                float vp = crGp[3 * r] * bs[0] + crGp[3 * r + 1] * bs[1] + crGp[3 * r + 2] * bs[2];
-                vm = elim ? vm : 0.0f;
-                vp = elim ? vp : 0.0f;
-                float fr = shfl_down(vm, h, lane);
-                float fl = shfl_up(vp, h, lane);
-                if (lane + h > 31) fr = 0.0f;
-                if (lane < h) fl = 0.0f;
-                upd[r] = surv ? (fr + fl) : 0.0f;
+                real vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
+                real vp = crGp[3 * r] * bs[0] + crGp[3 * r + 1] * bs[1] + crGp[3 * r + 2] * bs[2];
+                vm = elim ? vm : real(0.0);
+                vp = elim ? vp : real(0.0);
+                real fr = shfl_down(vm, h, lane);
+                real fl = shfl_up(vp, h, lane);
+                if (lane + h > 31) fr = real(0.0);
+                if (lane < h) fl = real(0.0);
+                upd[r] = surv ? (fr + fl) : real(0.0);
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r) bs[r] -= upd[r];
         }
-        float ts[3], xs[3];
+        real ts[3], xs[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             ts[r] = crAinv[SI(r, 0)] * bs[0] + crAinv[SI(r, 1)] * bs[1] + crAinv[SI(r, 2)] * bs[2];
@@ -800,12 +818,12 @@ struct QpWarp {
         for (int t = 4; t >= 0; --t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
-            float xl[3], xr[3];
+            real xl[3], xr[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 xl[r] = shfl_up(xs[r], h, lane);
                 xr[r] = shfl_down(xs[r], h, lane);
-                if (lane + h > 31) xr[r] = 0.0f;
+                if (lane + h > 31) xr[r] = real(0.0);
             }
             if (elim) {
 #pragma unroll
@@ -815,31 +833,31 @@ struct QpWarp {
             }
         }
         // local backward substitution
-        float xSL[3], xn[3];
+        real xSL[3], xn[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             xSL[r] = shfl_up(xs[r], 1, lane);
-            if (lane == 0) xSL[r] = 0.0f;
+            if (lane == 0) xSL[r] = real(0.0);
             xn[r] = xs[r];
         }
         {
-            float4 v = V(GBV, C - 1);
+            Vec4 v = V(GBV, C - 1);
             v.x = xs[0]; v.y = xs[1]; v.z = xs[2];
             V(GBV, C - 1) = v;
         }
         // backward sweep, same prefetch scheme (the rhs of the next stage rides along)
-        float4 vcur;
+        Vec4 vcur;
         if (C > 1) { load_factor(C - 2, f, true); vcur = V(GBV, C - 2); }
         PQP_ROLL
         for (int k = C - 2; k >= 0; --k) {
-            float4 vnx;
+            Vec4 vnx;
             if (k > 0) { load_factor(k - 1, fnx, true); vnx = V(GBV, k - 1); }
-            const float *Di = f, *Gm = f + 6, *Fm = f + 15;
-            const float b0 = vcur.x, b1 = vcur.y, b2 = vcur.z;
-            float xk[3];
+            const real *Di = f, *Gm = f + 6, *Fm = f + 15;
+            const real b0 = vcur.x, b1 = vcur.y, b2 = vcur.z;
+            real xk[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float t = Di[SI(c, 0)] * b0 + Di[SI(c, 1)] * b1 + Di[SI(c, 2)] * b2;
+                const real t = Di[SI(c, 0)] * b0 + Di[SI(c, 1)] * b1 + Di[SI(c, 2)] * b2;
                 xk[c] = t - (Gm[c] * xn[0] + Gm[3 + c] * xn[1] + Gm[6 + c] * xn[2]) -
                         (Fm[c] * xSL[0] + Fm[3 + c] * xSL[1] + Fm[6 + c] * xSL[2]);
             }
@@ -854,11 +872,11 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- per-stage data in registers
-    struct StageRO {  // read-only inside the ADMM loop (7 float4)
-        float a00, a01, a10, a11, a12, ds, miu, mis0, mis1, ob[3], Ro[3], Rk, clo[2], chi[2], Rc[2], Sw[6];
+    struct StageRO {  // read-only inside the ADMM loop (7 Vec4)
+        real a00, a01, a10, a11, a12, ds, miu, mis0, mis1, ob[3], Ro[3], Rk, clo[2], chi[2], Rc[2], Sw[6];
     };
     PQP_DEV void load_ro(int k, StageRO &q) {
-        const float4 g0 = V(GA0, k), g1 = V(GA1, k), g2 = V(GB2, k), g3 = V(GR3, k), g4 = V(GC4, k),
+        const Vec4 g0 = V(GA0, k), g1 = V(GA1, k), g2 = V(GB2, k), g3 = V(GR3, k), g4 = V(GC4, k),
                      g5 = V(GR5, k), g6 = V(GS6, k);
         q.a00 = g0.x; q.a01 = g0.y; q.a10 = g0.z; q.a11 = g0.w;
         q.a12 = g1.x; q.ds = g1.y; q.miu = g1.z; q.mis0 = g1.w;
@@ -873,27 +891,27 @@ struct QpWarp {
     // stage-local part of the rhs from the row vectors w (wo: outgoing, wk: kappa, wc:
     // clearance) and the iterate x; on return wo[2] includes the u-condensation (what the
     // right neighbour sees)
-    PQP_DEV void local_rhs(const StageRO &q, const StagePred &sp, const float (&x)[6], float (&wo)[3],
-                           float wk, float (&wc)[2], float (&bk)[3]) {
-        const float rhs_u = q.Sw[3] * x[3] + q.ds * wo[2];
+    PQP_DEV void local_rhs(const StageRO &q, const StagePred &sp, const real (&x)[6], real (&wo)[3],
+                           real wk, real (&wc)[2], real (&bk)[3]) {
+        const real rhs_u = q.Sw[3] * x[3] + q.ds * wo[2];
         wo[2] -= (q.Ro[2] * q.ds * q.miu) * rhs_u;
-        const float rhs_s0 = q.Sw[4] * x[4] + wc[0];
+        const real rhs_s0 = q.Sw[4] * x[4] + wc[0];
         wc[0] -= (q.Rc[0] * q.mis0) * rhs_s0;
-        const float rhs_s1 = q.Sw[5] * x[5] + wc[1];
+        const real rhs_s1 = q.Sw[5] * x[5] + wc[1];
         wc[1] -= (q.Rc[1] * q.mis1) * rhs_s1;
         bk[0] = q.Sw[0] * x[0] + q.a00 * wo[0] + q.a10 * wo[1] + wc[0] + wc[1];
         bk[1] = q.Sw[1] * x[1] + q.a01 * wo[0] + q.a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
         bk[2] = q.Sw[2] * x[2] + q.a12 * wo[1] + sp.a22 * wo[2] + wk;
     }
     // subtract the left neighbour lane's last-stage rows from this lane's first stage
-    PQP_DEV void fix_first_stage(const float (&wlast)[3]) {
+    PQP_DEV void fix_first_stage(const real (&wlast)[3]) {
         const StagePred sp0 = pred(0);
-        float4 v = V(GBV, 0);
-        float wL[3];
+        Vec4 v = V(GBV, 0);
+        real wL[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             wL[r] = shfl_up(wlast[r], 1, lane);
-            if (lane == 0 || !sp0.real) wL[r] = 0.0f;
+            if (lane == 0 || !sp0.real) wL[r] = real(0.0);
         }
         v.x -= wL[0]; v.y -= wL[1]; v.z -= wL[2];
         V(GBV, 0) = v;
@@ -903,19 +921,19 @@ struct QpWarp {
     // rho update). `initial`: the outgoing rows' z is z0 (cold: 0, warm: previous z), not yet
     // the bound.
     PQP_DEV void build_rhs(bool initial, bool warm) {
-        float wprev[3] = {0.0f, 0.0f, 0.0f};
+        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             StageRO q;
             load_ro(k, q);
-            const float4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
-            const float x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-            const float oyv[3] = {oy.x, oy.y, oy.z};
-            float wo[3], wk, wc[2], bk[3];
+            const Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+            const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+            const real oyv[3] = {oy.x, oy.y, oy.z};
+            real wo[3], wk, wc[2], bk[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                float z;
+                real z;
                 if (sp.last && r < 2) z = zend[r];
                 else z = initial ? z0_out(warm, r, k) : q.ob[r];
                 wo[r] = q.Ro[r] * (z - oyv[r]);
@@ -924,11 +942,11 @@ struct QpWarp {
             wc[0] = q.Rc[0] * (cz.x - cz.z);
             wc[1] = q.Rc[1] * (cz.y - cz.w);
             local_rhs(q, sp, x, wo, wk, wc, bk);
-            float4 bv;
-            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : 0.0f);
-            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : 0.0f);
-            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : 0.0f);
-            bv.w = 0.0f;
+            Vec4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
+            bv.w = real(0.0);
             V(GBV, k) = bv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
@@ -941,13 +959,13 @@ struct QpWarp {
     // of the recession cone of [lo, hi] (OSQP is_primal_infeasible); a bound counts as infinite
     // when |b| >= 1e29 (OSQP_INFTY = 1e30 is the caller's "no bound" value). Accumulates
     // |dy|_inf and u'max(dy,0) + l'min(dy,0); dy itself goes to global scratch for A'dy.
-    PQP_DEV void cert_row(int r, int k, float dy, float lo, float hi) {
-        const bool hinf = hi >= 1e29f, linf = lo <= -1e29f;
-        if (hinf) dy = linf ? 0.0f : fminf(dy, 0.0f);
-        else if (linf) dy = fmaxf(dy, 0.0f);
+    PQP_DEV void cert_row(int r, int k, real dy, real lo, real hi) {
+        const bool hinf = hi >= real(1e29), linf = lo <= -real(1e29);
+        if (hinf) dy = linf ? real(0.0) : xmin(dy, real(0.0));
+        else if (linf) dy = xmax(dy, real(0.0));
         G(gdy, r, k) = dy;
-        cert_nrm = fmaxf(cert_nrm, fabsf(dy));
-        cert_lhs += (dy > 0.0f ? hi * dy : 0.0f) + (dy < 0.0f ? lo * dy : 0.0f);
+        cert_nrm = xmax(cert_nrm, xabs(dy));
+        cert_lhs += (dy > real(0.0) ? hi * dy : real(0.0)) + (dy < real(0.0) ? lo * dy : real(0.0));
     }
 
     // -------------------------------------------------------------- one ADMM update
@@ -958,52 +976,52 @@ struct QpWarp {
     // z0 (cold: 0, warm: the previous solve's z) rather than their bound.
     template <bool kCheck>
     PQP_DEV void admm_update(bool first, bool warm) {
-        const float alpha = ka.prm.alpha, oma = 1.0f - alpha;
-        float xnb[3];
+        const real oma = real(1.0) - alpha;
+        real xnb[3];
         {
-            const float4 v = V(GBV, 0);
+            const Vec4 v = V(GBV, 0);
             xnb[0] = shfl_down(v.x, 1, lane);
             xnb[1] = shfl_down(v.y, 1, lane);
             xnb[2] = shfl_down(v.z, 1, lane);
-            if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = 0.0f; }
+            if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = real(0.0); }
         }
-        if (kCheck) { cert_nrm = 0.0f; cert_lhs = 0.0f; }
-        float wprev[3] = {0.0f, 0.0f, 0.0f};
-        float4 xt = V(GBV, 0);
+        if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
+        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
+        Vec4 xt = V(GBV, 0);
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             StageRO q;
             load_ro(k, q);
-            float4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
-            const float4 xtn = V(GBV, k < C - 1 ? k + 1 : k);
-            const float lt = xt.x, pt = xt.y, kt = xt.z;
-            const float ln = (k == C - 1) ? xnb[0] : xtn.x;
-            const float pn = (k == C - 1) ? xnb[1] : xtn.y;
-            const float kn = (k == C - 1) ? xnb[2] : xtn.z;
+            Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+            const Vec4 xtn = V(GBV, k < C - 1 ? k + 1 : k);
+            const real lt = xt.x, pt = xt.y, kt = xt.z;
+            const real ln = (k == C - 1) ? xnb[0] : xtn.x;
+            const real pn = (k == C - 1) ? xnb[1] : xtn.y;
+            const real kn = (k == C - 1) ? xnb[2] : xtn.z;
             // previous z of the outgoing rows
-            float zo_old[3];
+            real zo_old[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 if (sp.last && r < 2) zo_old[r] = zend[r];
                 else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
             }
-            const float oyv[3] = {oy.x, oy.y, oy.z};
+            const real oyv[3] = {oy.x, oy.y, oy.z};
             // recover the eliminated variables of x~ (rhs recomputed from the old iterates)
-            const float aux_u = q.Sw[3] * x0.w + q.ds * (q.Ro[2] * (zo_old[2] - oyv[2]));
-            const float aux_s0 = q.Sw[4] * x1.x + q.Rc[0] * (cz.x - cz.z);
-            const float aux_s1 = q.Sw[5] * x1.y + q.Rc[1] * (cz.y - cz.w);
-            const float ut = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * kt + sp.gn * kn));
-            const float s0t = q.mis0 * (aux_s0 - q.Rc[0] * (lt + sp.h0 * pt));
-            const float s1t = q.mis1 * (aux_s1 - q.Rc[1] * (lt + sp.h1 * pt));
+            const real aux_u = q.Sw[3] * x0.w + q.ds * (q.Ro[2] * (zo_old[2] - oyv[2]));
+            const real aux_s0 = q.Sw[4] * x1.x + q.Rc[0] * (cz.x - cz.z);
+            const real aux_s1 = q.Sw[5] * x1.y + q.Rc[1] * (cz.y - cz.w);
+            const real ut = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * kt + sp.gn * kn));
+            const real s0t = q.mis0 * (aux_s0 - q.Rc[0] * (lt + sp.h0 * pt));
+            const real s1t = q.mis1 * (aux_s1 - q.Rc[1] * (lt + sp.h1 * pt));
             // z~ = A x~
-            float zo[3];
+            real zo[3];
             zo[0] = q.a00 * lt + q.a01 * pt + sp.gn * ln;
             zo[1] = q.a10 * lt + q.a11 * pt + q.a12 * kt + sp.gn * pn;
             zo[2] = sp.a22 * kt + q.ds * ut + sp.gn * kn;
-            const float zk = sp.real ? kt : 0.0f;
-            const float zc0 = sp.act0 ? (lt + sp.h0 * pt + s0t) : 0.0f;
-            const float zc1 = sp.act1 ? (lt + sp.h1 * pt + s1t) : 0.0f;
+            const real zk = sp.real ? kt : real(0.0);
+            const real zc0 = sp.act0 ? (lt + sp.h0 * pt + s0t) : real(0.0);
+            const real zc1 = sp.act1 ? (lt + sp.h1 * pt + s1t) : real(0.0);
             // x+ = alpha x~ + (1 - alpha) x
             x0.x = alpha * lt + oma * x0.x;
             x0.y = alpha * pt + oma * x0.y;
@@ -1012,13 +1030,13 @@ struct QpWarp {
             x1.x = alpha * s0t + oma * x1.x;
             x1.y = alpha * s1t + oma * x1.y;
             // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
-            float wo[3], wk, wc[2], bk[3], oyn[3];
+            real wo[3], wk, wc[2], bk[3], oyn[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float bnd = q.ob[r];
-                const float zt = alpha * zo[r] + oma * zo_old[r];
-                const float zh = zt + oyv[r];
-                float zn;
+                const real bnd = q.ob[r];
+                const real zt = alpha * zo[r] + oma * zo_old[r];
+                const real zh = zt + oyv[r];
+                real zn;
                 if (sp.last && r < 2) {
                     zn = clampf(zh, bnd, bnd + endw[r]);
                     zend[r] = zn;
@@ -1031,27 +1049,27 @@ struct QpWarp {
             }
             oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
             {
-                const float zt = alpha * zk + oma * x1.z;
-                const float zh = zt + x1.w;
-                const float zn = clampf(zh, -kmax, kmax);
+                const real zt = alpha * zk + oma * x1.z;
+                const real zh = zt + x1.w;
+                const real zn = clampf(zh, -kmax, kmax);
                 x1.z = zn;
                 x1.w = zh - zn;
                 wk = q.Rk * (zn - x1.w);
                 if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
             }
             {
-                const float zt = alpha * zc0 + oma * cz.x;
-                const float zh = zt + cz.z;
-                const float zn = clampf(zh, q.clo[0], q.chi[0]);
+                const real zt = alpha * zc0 + oma * cz.x;
+                const real zh = zt + cz.z;
+                const real zn = clampf(zh, q.clo[0], q.chi[0]);
                 cz.x = zn;
                 cz.z = zh - zn;
                 wc[0] = q.Rc[0] * (zn - cz.z);
                 if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
             }
             {
-                const float zt = alpha * zc1 + oma * cz.y;
-                const float zh = zt + cz.w;
-                const float zn = clampf(zh, q.clo[1], q.chi[1]);
+                const real zt = alpha * zc1 + oma * cz.y;
+                const real zh = zt + cz.w;
+                const real zn = clampf(zh, q.clo[1], q.chi[1]);
                 cz.y = zn;
                 cz.w = zh - zn;
                 wc[1] = q.Rc[1] * (zn - cz.w);
@@ -1061,13 +1079,13 @@ struct QpWarp {
             V(GX1, k) = x1;
             V(GOY, k) = oy;
             V(GCZ, k) = cz;
-            const float x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+            const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
             local_rhs(q, sp, x, wo, wk, wc, bk);
-            float4 bv;
-            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : 0.0f);
-            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : 0.0f);
-            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : 0.0f);
-            bv.w = 0.0f;
+            Vec4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
+            bv.w = real(0.0);
             V(GBV, k) = bv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
@@ -1078,46 +1096,46 @@ struct QpWarp {
 
     // -------------------------------------------------------------- residuals (OSQP update_info)
     struct Norms {
-        float pri, ax, z, dua, px, aty;          // unscaled inf-norms
-        float spri, sax, sz, sdua, spx, saty;    // scaled (for the rho estimate)
+        real pri, ax, z, dua, px, aty;          // unscaled inf-norms
+        real spri, sax, sz, sdua, spx, saty;    // scaled (for the rho estimate)
     };
     // y of the left stage's outgoing row r as seen from local stage k
-    PQP_DEV float left_out_y(int r, int k) {
+    PQP_DEV real left_out_y(int r, int k) {
         if (k > 0) return S(FOR_ + r, k - 1) * S(FOY + r, k - 1);
-        if (lane == 0) return 0.0f;
+        if (lane == 0) return real(0.0);
         return SL(FOR_ + r, C - 1, lane - 1) * SL(FOY + r, C - 1, lane - 1);
     }
-    PQP_DEV float next_x(int c, int k) {
+    PQP_DEV real next_x(int c, int k) {
         if (k < C - 1) return S(FX + c, k + 1);
-        if (lane == 31) return 0.0f;
+        if (lane == 31) return real(0.0);
         return SL(FX + c, 0, lane + 1);
     }
     PQP_DEV Norms residuals() {
         const DevParams &P = ka.prm;
         sync_warp(lane);
-        float m[12];
+        real m[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) m[j] = 0.0f;
-        const float c = cscale;
+        for (int j = 0; j < 12; ++j) m[j] = real(0.0);
+        const real c = cscale;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             // Ruiz scalings (global scratch): issued first so their latency overlaps the rest
-            float ev[6], dv[6];
+            real ev[6], dv[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) { ev[j] = G(gscal, GE + j, k); dv[j] = c * G(gscal, GD + j, k); }
-            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+            const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
-            const float l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
+            const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
                         s0 = S(FX + 4, k), s1 = S(FX + 5, k);
-            const float ln = next_x(0, k), pn = next_x(1, k), kn = next_x(2, k);
-            float ax[6], z[6], y[6];
+            const real ln = next_x(0, k), pn = next_x(1, k), kn = next_x(2, k);
+            real ax[6], z[6], y[6];
             ax[0] = a00 * l + a01 * ps + sp.gn * ln;
             ax[1] = a10 * l + a11 * ps + a12 * kp + sp.gn * pn;
             ax[2] = sp.a22 * kp + ds * u + sp.gn * kn;
-            ax[3] = sp.real ? kp : 0.0f;
-            ax[4] = sp.act0 ? (l + sp.h0 * ps + s0) : 0.0f;
-            ax[5] = sp.act1 ? (l + sp.h1 * ps + s1) : 0.0f;
+            ax[3] = sp.real ? kp : real(0.0);
+            ax[4] = sp.act0 ? (l + sp.h0 * ps + s0) : real(0.0);
+            ax[5] = sp.act1 ? (l + sp.h1 * ps + s1) : real(0.0);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 z[r] = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
@@ -1128,31 +1146,31 @@ struct QpWarp {
             z[5] = S(FCZ + 1, k); y[5] = S(FCR + 1, k) * S(FCY + 1, k);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                const float e = ev[r];
-                const float rp = fabsf(ax[r] - z[r]);
-                m[0] = fmaxf(m[0], rp); m[1] = fmaxf(m[1], fabsf(ax[r])); m[2] = fmaxf(m[2], fabsf(z[r]));
-                m[6] = fmaxf(m[6], e * rp); m[7] = fmaxf(m[7], e * fabsf(ax[r])); m[8] = fmaxf(m[8], e * fabsf(z[r]));
+                const real e = ev[r];
+                const real rp = xabs(ax[r] - z[r]);
+                m[0] = xmax(m[0], rp); m[1] = xmax(m[1], xabs(ax[r])); m[2] = xmax(m[2], xabs(z[r]));
+                m[6] = xmax(m[6], e * rp); m[7] = xmax(m[7], e * xabs(ax[r])); m[8] = xmax(m[8], e * xabs(z[r]));
             }
-            const float hasL = sp.real ? 1.0f : 0.0f;
-            float aty[6], px[6];
+            const real hasL = sp.real ? real(1.0) : real(0.0);
+            real aty[6], px[6];
             aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - hasL * left_out_y(0, k);
             aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - hasL * left_out_y(1, k);
             aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - hasL * left_out_y(2, k);
             aty[3] = ds * y[2];
-            aty[4] = sp.act0 ? y[4] : 0.0f;
-            aty[5] = sp.act1 ? y[5] : 0.0f;
-            px[0] = sp.real ? P.w_l * l : 0.0f;
-            px[1] = 0.0f;
-            px[2] = sp.real ? P.w_kappa * kp : 0.0f;
-            px[3] = sp.mid ? P.w_dkappa * u : 0.0f;
-            px[4] = sp.act0 ? P.w_slack * s0 : 0.0f;
-            px[5] = sp.act1 ? P.w_slack * s1 : 0.0f;
+            aty[4] = sp.act0 ? y[4] : real(0.0);
+            aty[5] = sp.act1 ? y[5] : real(0.0);
+            px[0] = sp.real ? w_l * l : real(0.0);
+            px[1] = real(0.0);
+            px[2] = sp.real ? w_kappa * kp : real(0.0);
+            px[3] = sp.mid ? w_dkappa * u : real(0.0);
+            px[4] = sp.act0 ? w_slack * s0 : real(0.0);
+            px[5] = sp.act1 ? w_slack * s1 : real(0.0);
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const float d = dv[j];
-                const float rd = fabsf(px[j] + aty[j]);
-                m[3] = fmaxf(m[3], rd); m[4] = fmaxf(m[4], fabsf(px[j])); m[5] = fmaxf(m[5], fabsf(aty[j]));
-                m[9] = fmaxf(m[9], d * rd); m[10] = fmaxf(m[10], d * fabsf(px[j])); m[11] = fmaxf(m[11], d * fabsf(aty[j]));
+                const real d = dv[j];
+                const real rd = xabs(px[j] + aty[j]);
+                m[3] = xmax(m[3], rd); m[4] = xmax(m[4], xabs(px[j])); m[5] = xmax(m[5], xabs(aty[j]));
+                m[9] = xmax(m[9], d * rd); m[10] = xmax(m[10], d * xabs(px[j])); m[11] = xmax(m[11], d * xabs(aty[j]));
             }
         }
 #pragma unroll
@@ -1164,29 +1182,31 @@ struct QpWarp {
     }
 
     // OSQP is_primal_infeasible; |dy| and the bound term were accumulated by admm_update<true>
-    PQP_DEV bool primal_infeasible(float eps) {
-        const float c = cscale;
-        const float nrm = warp_max(cert_nrm, lane);
-        const float lhs = warp_sum(cert_lhs, lane);
+    PQP_DEV bool primal_infeasible(real eps) {
+        const real c = cscale;
+        const real nrm = warp_max(cert_nrm, lane);
+        const real lhs = warp_sum(cert_lhs, lane);
+        suspect = 0;
         if (!(c * nrm > eps)) return false;
         if (!(lhs < -eps * nrm)) return false;
+        suspect = 1;
         sync_warp(lane);
-        float mx = 0.0f;
+        real mx = real(0.0);
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            const float a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
+            const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
-            float y[6], yl[3];
+            real y[6], yl[3];
 #pragma unroll
             for (int r = 0; r < 6; ++r) y[r] = G(gdy, r, k);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 if (k > 0) yl[r] = G(gdy, r, k - 1);
-                else yl[r] = lane == 0 ? 0.0f : GL(gdy, r, C - 1, lane - 1);
-                if (!sp.real) yl[r] = 0.0f;
+                else yl[r] = lane == 0 ? real(0.0) : GL(gdy, r, C - 1, lane - 1);
+                if (!sp.real) yl[r] = real(0.0);
             }
-            float aty[6];
+            real aty[6];
             aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - yl[0];
             aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - yl[1];
             aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - yl[2];
@@ -1194,7 +1214,7 @@ struct QpWarp {
             aty[4] = y[4];
             aty[5] = y[5];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) mx = fmaxf(mx, fabsf(aty[j]));
+            for (int j = 0; j < 6; ++j) mx = xmax(mx, xabs(aty[j]));
         }
         mx = warp_max(mx, lane);
         return mx < eps * nrm;
@@ -1203,11 +1223,11 @@ struct QpWarp {
     // OSQP check_termination; returns status or kUnsolved
     PQP_DEV int check_termination(const Norms &nr, bool approx) {
         const DevParams &P = ka.prm;
-        float ea = P.eps_abs, er = P.eps_rel, epi = P.eps_pinf;
-        if (!(nr.pri <= kOsqpInfty) || !(nr.dua <= kOsqpInfty)) return kNumerical;
-        if (approx) { ea *= 10.0f; er *= 10.0f; epi *= 10.0f; }
-        const float eps_prim = ea + er * fmaxf(nr.ax, nr.z);
-        const float eps_dual = ea + er * fmaxf(nr.px, nr.aty);
+        real ea = eps_abs, er = eps_rel, epi = eps_pinf;
+        if (!(nr.pri <= real(kOsqpInfty)) || !(nr.dua <= real(kOsqpInfty))) return kNumerical;
+        if (approx) { ea *= real(10.0); er *= real(10.0); epi *= real(10.0); }
+        const real eps_prim = ea + er * xmax(nr.ax, nr.z);
+        const real eps_dual = ea + er * xmax(nr.px, nr.aty);
         const bool pok = nr.pri < eps_prim, dok = nr.dua < eps_dual;
         bool pinf = false;
         if (!pok) pinf = primal_infeasible(epi);
@@ -1217,17 +1237,17 @@ struct QpWarp {
         return kUnsolved;
     }
 
-    PQP_DEV bool refactor() { return ka.prm.factor_fp64 ? factor<double>() : factor<float>(); }
+    PQP_DEV bool refactor() { return (sizeof(real) == 8 || ka.prm.factor_fp64) ? factor<double>() : factor<real>(); }
 
     // OSQP compute_rho_estimate + update; returns true if rho changed (and refactors)
     PQP_DEV bool adapt_rho(const Norms &nr, bool &factor_ok) {
         const DevParams &P = ka.prm;
-        const float pri = nr.spri / (fmaxf(nr.sz, nr.sax) + 1e-10f);
-        const float dua = nr.sdua / (fmaxf(nr.saty, nr.spx) + 1e-10f);
-        float est = rho * sqrtf(pri / (dua + 1e-10f));
-        est = fminf(fmaxf(est, kRhoMin), kRhoMax);
-        if (!(est > rho * P.rho_tol || est < rho / P.rho_tol)) return false;
-        const float ratio = est / rho, rinv = rho / est;
+        const real pri = nr.spri / (xmax(nr.sz, nr.sax) + real(1e-10));
+        const real dua = nr.sdua / (xmax(nr.saty, nr.spx) + real(1e-10));
+        real est = rho * xsqrt(pri / (dua + real(1e-10)));
+        est = xmin(xmax(est, real(kRhoMin)), real(kRhoMax));
+        if (!(est > rho * rho_tol || est < rho / rho_tol)) return false;
+        const real ratio = est / rho, rinv = rho / est;
         rho = est;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
@@ -1252,19 +1272,23 @@ struct QpWarp {
         n = ka.n[qp];
         p = ka.p ? ka.p[qp] : n;
         p = p < 0 ? 0 : (p > n ? n : p);
-        lf = (float)P.front_length;
-        lr = (float)P.rear_length;
-        kmax = (float)P.kappa_limit;
+        lf = (real)P.front_length;
+        lr = (real)P.rear_length;
+        kmax = (real)P.kappa_limit;
         const size_t plane = (size_t)C * 32;
         const size_t slot = (size_t)(qp + ka.qp0);  // per-instance scratch slot in the handle
-        gwarm = ka.warm + slot * NWARM * plane;
-        gscal = ka.scal + slot * NSCAL * plane;
-        gdy = ka.dy + slot * NDY * plane;
-        zend[0] = zend[1] = endw[0] = endw[1] = 0.0f;
-        cert_nrm = cert_lhs = 0.0f;
+        gwarm = static_cast<real *>(ka.warm) + slot * NWARM * plane;
+        gscal = static_cast<real *>(ka.scal) + slot * NSCAL * plane;
+        gdy = static_cast<real *>(ka.dy) + slot * NDY * plane;
+        w_l = (real)P.w_l; w_kappa = (real)P.w_kappa; w_dkappa = (real)P.w_dkappa; w_slack = (real)P.w_slack;
+        sigma = (real)P.sigma; alpha = (real)P.alpha; eps_abs = (real)P.eps_abs; eps_rel = (real)P.eps_rel;
+        eps_pinf = (real)P.eps_pinf; rho_tol = (real)P.rho_tol;
+        zend[0] = zend[1] = endw[0] = endw[1] = real(0.0);
+        cert_nrm = cert_lhs = real(0.0);
+        suspect = 0;
         const bool warm = ka.mode == 1;
-        rho = warm ? ka.rho_state[qp + ka.qp0] : P.rho0;
-        rho = fminf(fmaxf(rho, kRhoMin), kRhoMax);
+        rho = warm ? static_cast<real *>(ka.rho_state)[qp + ka.qp0] : (real)P.rho0;
+        rho = xmin(xmax(rho, real(kRhoMin)), real(kRhoMax));
 
         assemble(src, stride);
         sync_warp(lane);
@@ -1278,7 +1302,7 @@ struct QpWarp {
         int status = fok ? kUnsolved : kNumerical;
         int iter = 0, rho_updates = 0;
         Norms nr;
-        nr.pri = nr.dua = 0.0f;
+        nr.pri = nr.dua = real(0.0);
         bool checked = false;
         if (fok) {
             PQP_ROLL
@@ -1331,9 +1355,9 @@ struct QpWarp {
     PQP_DEV void epilogue(int status, int iter, int rho_updates, const Norms &nr) {
         const DevParams &P = ka.prm;
         const int nmax = ka.n_max;
-        const float c = cscale;
+        const real c = cscale;
         double *sol = ka.sol + (size_t)qp * 4 * nmax;
-        float cost = 0.0f;
+        real cost = real(0.0);
         const int nvm = 6 * nmax - 1, mm = 6 * nmax + 2;
         double *xf = ka.x_full ? ka.x_full + (size_t)qp * nvm : nullptr;
         double *yf = ka.y_full ? ka.y_full + (size_t)qp * mm : nullptr;
@@ -1342,7 +1366,7 @@ struct QpWarp {
         for (int k = 0; k < C; ++k) {
             const int g = lane * C + k;
             const StagePred sp = pred(k);
-            const float l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
+            const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
                         s0 = S(FX + 4, k), s1 = S(FX + 5, k);
             if (sp.real) {
                 const int i = g - 1;
@@ -1350,8 +1374,8 @@ struct QpWarp {
                 sol[1 * nmax + i] = (double)ps;
                 sol[2 * nmax + i] = (double)kp;
                 sol[3 * nmax + i] = sp.mid ? (double)u : 0.0;
-                cost += 0.5f * (P.w_l * l * l + P.w_kappa * kp * kp + (sp.mid ? P.w_dkappa * u * u : 0.0f) +
-                                P.w_slack * s0 * s0 + (sp.act1 ? P.w_slack * s1 * s1 : 0.0f));
+                cost += real(0.5) * (w_l * l * l + w_kappa * kp * kp + (sp.mid ? w_dkappa * u * u : real(0.0)) +
+                                w_slack * s0 * s0 + (sp.act1 ? w_slack * s1 * s1 : real(0.0)));
                 if (xf) {
                     xf[3 * i] = l; xf[3 * i + 1] = ps; xf[3 * i + 2] = kp;
                     if (sp.mid) xf[3 * n + i] = u;
@@ -1367,7 +1391,7 @@ struct QpWarp {
                     if (g <= n - 1) row = 3 * g + r;           // outgoing rows of stage g = block g
                     else if (sp.last && r < 2) row = (4 * n + p + n) + r;  // m-2, m-1
                     if (row >= 0) {
-                        const float z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
+                        const real z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
                         if (yf) yf[row] = (double)(S(FOR_ + r, k) * S(FOY + r, k));
                         if (zf) zf[row] = (double)z;
                     }
@@ -1390,19 +1414,19 @@ struct QpWarp {
             for (int j = 0; j < 6; ++j) G(gwarm, WX + j, k) = S(FX + j, k) / G(gscal, GD + j, k);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float e = G(gscal, GE + r, k);
-                const float z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
+                const real e = G(gscal, GE + r, k);
+                const real z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
                 G(gwarm, WOZ + r, k) = e * z;
                 G(gwarm, WOY + r, k) = c * S(FOR_ + r, k) * S(FOY + r, k) / e;
             }
             {
-                const float e = G(gscal, GE + 3, k);
+                const real e = G(gscal, GE + 3, k);
                 G(gwarm, WKZ, k) = e * S(FKZ, k);
                 G(gwarm, WKY, k) = c * S(FKR, k) * S(FKY, k) / e;
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float e = G(gscal, GE + 4 + j, k);
+                const real e = G(gscal, GE + 4 + j, k);
                 G(gwarm, WCZ + j, k) = e * S(FCZ + j, k);
                 G(gwarm, WCY + j, k) = c * S(FCR + j, k) * S(FCY + j, k) / e;
             }
@@ -1412,11 +1436,12 @@ struct QpWarp {
             if (ka.cost) ka.cost[qp] = (double)cost;
             if (ka.status) ka.status[qp] = status;
             if (ka.iters) ka.iters[qp] = iter;
+            if (ka.flags) ka.flags[qp] = (status == kMaxIter || status == kUnsolved) ? suspect : 0;
             if (ka.info) {
                 double *inf = ka.info + (size_t)qp * 4;
                 inf[0] = nr.pri; inf[1] = nr.dua; inf[2] = rho; inf[3] = rho_updates;
             }
-            ka.rho_state[qp + ka.qp0] = rho;
+            static_cast<real *>(ka.rho_state)[qp + ka.qp0] = rho;
         }
     }
 };

@@ -13,19 +13,20 @@ namespace {
 struct EmuHandle {
     pqp_params prm;
     int n_max, batch_max, chunk;
-    std::vector<float> warm, scal, dy, rho;
-    std::vector<float> smem;
+    bool fp64 = false;  // params.reserved bit 1: run the FP64 instantiation
+    std::vector<double> warm, scal, dy, rho;   // sized for the wider scalar type
+    std::vector<double> smem;
     bool solved = false;
 };
 
-template <int C>
-void run_one(const pqp::KernelArgs &ka, int qp, float *smem) {
+template <int C, typename real>
+void run_one(const pqp::KernelArgs &ka, int qp, real *smem) {
     warp_emu::Warp warp;
     warp_emu::current() = &warp;
     const double *src = ka.knots + (size_t)qp * 9 * ka.n_max;
     const int stride = ka.n_max;
     warp.run([&](int lane) {
-        pqp::QpWarp<C> w(ka, smem, lane, qp);
+        pqp::QpWarp<C, real> w(ka, smem, lane, qp);
         w.run(src, stride);
     });
     warp_emu::current() = nullptr;
@@ -52,6 +53,7 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     ka.cost = out->cost;
     ka.status = out->status;
     ka.iters = out->iters;
+    ka.flags = nullptr;
     ka.x_full = out->x_full;
     ka.y_full = out->y_full;
     ka.z_full = out->z_full;
@@ -61,12 +63,23 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     ka.dy = h->dy.data();
     ka.rho_state = h->rho.data();
     for (int b = 0; b < in->batch; ++b) {
-        std::fill(h->smem.begin(), h->smem.end(), 0.0f);
-        switch (h->chunk) {
-            case 1: run_one<1>(ka, b, h->smem.data()); break;
-            case 2: run_one<2>(ka, b, h->smem.data()); break;
-            case 4: run_one<4>(ka, b, h->smem.data()); break;
-            default: run_one<8>(ka, b, h->smem.data()); break;
+        std::fill(h->smem.begin(), h->smem.end(), 0.0);
+        if (h->fp64) {
+            double *sm = h->smem.data();
+            switch (h->chunk) {
+                case 1: run_one<1, double>(ka, b, sm); break;
+                case 2: run_one<2, double>(ka, b, sm); break;
+                case 4: run_one<4, double>(ka, b, sm); break;
+                default: run_one<8, double>(ka, b, sm); break;
+            }
+        } else {
+            float *sm = reinterpret_cast<float *>(h->smem.data());
+            switch (h->chunk) {
+                case 1: run_one<1, float>(ka, b, sm); break;
+                case 2: run_one<2, float>(ka, b, sm); break;
+                case 4: run_one<4, float>(ka, b, sm); break;
+                default: run_one<8, float>(ka, b, sm); break;
+            }
         }
     }
     h->solved = true;
@@ -85,11 +98,12 @@ void *emu_create(const pqp_params *prm, int n_max, int batch_max) {
     h->batch_max = batch_max;
     h->chunk = pqp::chunk_for(n_max);
     const int c = h->chunk;
-    h->warm.assign((size_t)batch_max * pqp::warm_floats(c), 0.0f);
-    h->scal.assign((size_t)batch_max * pqp::scal_floats(c), 0.0f);
-    h->dy.assign((size_t)batch_max * pqp::dy_floats(c), 0.0f);
-    h->rho.assign(batch_max, (float)prm->rho);
-    h->smem.assign(pqp::smem_floats(c), 0.0f);
+    h->fp64 = (prm->reserved & 2) != 0;
+    h->warm.assign((size_t)batch_max * pqp::warm_floats(c), 0.0);
+    h->scal.assign((size_t)batch_max * pqp::scal_floats(c), 0.0);
+    h->dy.assign((size_t)batch_max * pqp::dy_floats(c), 0.0);
+    h->rho.assign(batch_max, 0.0);
+    h->smem.assign(pqp::smem_floats(c), 0.0);
     return h;
 }
 void emu_destroy(void *h) { delete static_cast<EmuHandle *>(h); }

@@ -58,3 +58,28 @@ def test_emulated_fp32_factor_also_converges():
     params = abi.default_params(reserved=1)  # bit 0: factorise in FP32 instead of FP64
     hb = synthetic.make_batch(3, 3, 120)
     _check(hb, params, "emu f32 factor", warm=False)
+
+
+def test_emulated_fp64_instantiation_reproduces_oracle_iterates():
+    """The kernel source instantiated in double (params.reserved bit 1): same algorithm and
+    schedule as the oracle -> same iteration counts, rho, statuses (incl. PRIMAL_INFEASIBLE)
+    and iterates to ~1e-7, cold and warm."""
+    from oracle import oracle
+    p32, p64 = abi.default_params(), abi.default_params(reserved=2)
+    for cfg, batch, n in ((103, 6, 3), (3, 4, 60), (3, 2, 240)):
+        hb = synthetic.make_batch(cfg, batch, n)
+        es = emu.EmuSolver(p64, n, batch)
+        res = es.solve(hb)
+        res2 = es.resolve(hb.with_linearisation(res.sol))
+        for b in range(batch):
+            s = oracle.OracleSolver(p32, hb.knots[b], hb.inst[b], n)
+            st = s.solve()
+            assert res.status[b] == st and res.iters[b] == s.iters, (cfg, b)
+            assert abs(res.info[b, 2] - s.rho) <= 1e-5 * s.rho
+            if st != abi.PQP_SOLVED:
+                continue
+            assert np.max(np.abs(res.x_full[b, :s.nv] - s.x())) < 1e-5
+            sol = s.sol()
+            s.update(sol[0], sol[1], sol[2])
+            assert s.solve() == res2.status[b] and s.iters == res2.iters[b]
+            assert np.max(np.abs(res2.x_full[b, :s.nv] - s.x())) < 1e-5

@@ -14,14 +14,14 @@ def solver_mod():
     return solver
 
 
-def _run_and_check(solver_mod, hb, params, label, warm=True, check_all=True, max_check=16):
+def _run_and_check(solver_mod, hb, params, label, warm=True, check_all=True, max_check=16, strict=True):
     sv = solver_mod.PathQpSolver(params, n_max=hb.n_max, batch_max=hb.batch)
     res = sv.solve(hb, full=True)
     idx = range(hb.batch) if check_all else range(0, hb.batch, max(1, hb.batch // max_check))
     stats = []
     for b in idx:
         s = parity.oracle_reference(params, hb, b)
-        stats.append(parity.check_instance(params, hb, res, b, oracle_solver=s, label=label))
+        stats.append(parity.check_instance(params, hb, res, b, oracle_solver=s, label=label, strict_status=strict))
     if warm:
         hb2 = hb.with_linearisation(res.sol)
         res2 = sv.resolve(hb2, full=True)
@@ -124,4 +124,44 @@ def test_api_errors(solver_mod):
         sv.solve(synthetic.make_batch(3, 3, 60))
     sv.solve(hb)
     sv.resolve(None, batch=2)  # relinearise about the device-resident solution
+    sv.close()
+
+
+def test_fp64_mode_reproduces_oracle_iterates(solver_mod):
+    """params.reserved bit 1: the same kernel instantiated in double. Same algorithm, same
+    schedule -> the oracle's iteration counts, rho and iterates are reproduced."""
+    from oracle import oracle
+    p32 = abi.default_params()
+    p64 = abi.default_params(reserved=2)
+    for n in (3, 60, 240):
+        hb = synthetic.make_batch(100 + n if n == 3 else 3, 6 if n < 100 else 4, n)
+        sv = solver_mod.PathQpSolver(p64, n_max=n, batch_max=hb.batch)
+        res = sv.solve(hb, full=True)
+        for b in range(hb.batch):
+            s = oracle.OracleSolver(p32, hb.knots[b], hb.inst[b], n)
+            st = s.solve()
+            assert res.status[b] == st and res.iters[b] == s.iters
+            assert abs(res.info[b, 2] - s.rho) <= 1e-5 * s.rho
+            if st == abi.PQP_SOLVED:
+                assert np.max(np.abs(res.x_full[b, :s.nv] - s.x())) < 1e-5
+        sv.close()
+
+
+def test_infeasible_instance_escalates_to_fp64(solver_mod):
+    """FP32 cannot resolve OSQP's infeasibility certificate; the host API re-solves
+    such instances with the FP64 instantiation and reports the reference's status."""
+    from oracle import oracle
+    hb = synthetic.make_batch(103, 6, 3)
+    ref = [oracle.OracleSolver(abi.default_params(), hb.knots[b], hb.inst[b], 3) for b in range(6)]
+    exp = np.array([s.solve() for s in ref])
+    assert abi.PQP_PRIMAL_INFEASIBLE in exp
+    sv = solver_mod.PathQpSolver(abi.default_params(), n_max=3, batch_max=6)
+    res = sv.solve(hb)
+    assert np.array_equal(res.status, exp)
+    sv.close()
+    sv = solver_mod.PathQpSolver(abi.default_params(reserved=4), n_max=3, batch_max=6)  # escalation off
+    res = sv.solve(hb)
+    bad = exp == abi.PQP_PRIMAL_INFEASIBLE
+    assert np.all(np.isin(res.status[bad], [abi.PQP_PRIMAL_INFEASIBLE, abi.PQP_MAX_ITER_REACHED]))
+    assert np.array_equal(res.status[~bad], exp[~bad])
     sv.close()
