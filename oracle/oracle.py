@@ -40,6 +40,7 @@ def lib():
         L.pqo_free.argtypes = [vp]
         L.pqo_solve.argtypes = [vp]
         L.pqo_update.argtypes = [vp, vp, vp, vp]
+        L.pqo_update_full.argtypes = [vp, vp, C.c_int, vp]
         for f in ("pqo_nv", "pqo_m", "pqo_iters", "pqo_status", "pqo_rho_updates", "pqo_nnz_L",
                   "pqo_nnz_A"):
             getattr(L, f).argtypes = [vp]
@@ -92,6 +93,12 @@ class OracleSolver:
         rc = self.L.pqo_update(self.ws, l.ctypes.data, psi.ctypes.data, k.ctypes.data)
         if rc:
             raise RuntimeError("pqo_update failed")
+
+    def update_full(self, knots, inst):
+        knots = np.ascontiguousarray(knots, dtype=np.float64)
+        inst = np.ascontiguousarray(inst, dtype=np.float64)
+        if self.L.pqo_update_full(self.ws, knots.ctypes.data, knots.shape[1], inst.ctypes.data):
+            raise RuntimeError("pqo_update_full failed")
 
     @property
     def iters(self):

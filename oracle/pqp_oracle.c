@@ -857,9 +857,9 @@ int pqo_solve(pqo_ws *w) {
 
 /* ------------------------------------------------------------------ warm update */
 int pqo_update(pqo_ws *w, const double *l, const double *psi, const double *k) {
-    memcpy(w->lin_l, l, sizeof(double) * w->n);
-    memcpy(w->lin_psi, psi, sizeof(double) * w->n);
-    memcpy(w->lin_k, k, sizeof(double) * w->n);
+    if (l != w->lin_l) memcpy(w->lin_l, l, sizeof(double) * w->n);
+    if (psi != w->lin_psi) memcpy(w->lin_psi, psi, sizeof(double) * w->n);
+    if (k != w->lin_k) memcpy(w->lin_k, k, sizeof(double) * w->n);
     if (assemble(w, 0)) return -1;
     /* osqp_update_bounds: scale the new bounds with the CURRENT E, refresh constraint types */
     for (int i = 0; i < w->m; ++i) { w->l[i] = w->l0[i] * w->E[i]; w->u[i] = w->u0[i] * w->E[i]; }
@@ -875,6 +875,17 @@ int pqo_update(pqo_ws *w, const double *l, const double *psi, const double *k) {
     if (refactor(w)) return -1;
     w->status = PQP_UNSOLVED;
     return 0;
+}
+
+/* Receding-horizon update: every input of the instance changes (window shifted along the
+ * reference, new clearance bounds, new x0), the sparsity pattern does not. Same OSQP calls as
+ * pqo_update: osqp_update_bounds, then osqp_update_A. */
+int pqo_update_full(pqo_ws *w, const double *knots, int stride, const double *inst) {
+    double **fields[9] = {&w->s, &w->kref, &w->lin_l, &w->lin_psi, &w->lin_k,
+                          &w->b0lb, &w->b0ub, &w->b1lb, &w->b1ub};
+    for (int f = 0; f < PQP_NFIELDS; ++f) memcpy(*fields[f], knots + (size_t)f * stride, sizeof(double) * w->n);
+    memcpy(w->inst, inst, sizeof(double) * PQP_NINST);
+    return pqo_update(w, w->lin_l, w->lin_psi, w->lin_k);
 }
 
 /* ------------------------------------------------------------------ getters */

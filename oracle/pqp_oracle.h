@@ -41,6 +41,10 @@ int pqo_solve(pqo_ws *ws);
  * about (l, psi, k), osqp_update_bounds, osqp_update_A (same pattern). */
 int pqo_update(pqo_ws *ws, const double *l, const double *psi, const double *k);
 
+/* same, but the whole instance changes (receding-horizon window shift): new knots block and
+ * per-instance scalars; the pattern (n, p) must be unchanged. */
+int pqo_update_full(pqo_ws *ws, const double *knots, int stride, const double *inst);
+
 int pqo_nv(const pqo_ws *ws);
 int pqo_m(const pqo_ws *ws);
 int pqo_iters(const pqo_ws *ws);

@@ -135,3 +135,21 @@ CONFIGS = {
     4: dict(batch=65536, n=240),
     5: dict(batch=4096, n=240, max_iter=50, ticks=20),
 }
+
+
+def shift_window(ext_knots, inst, sol, tick, n):
+    """Receding-horizon bookkeeping of BASELINE configs[4]: the planning
+    window advances by one knot per tick along an extended reference `ext_knots[B, 9, n+T]`
+    (only its S / KREF / bounds rows are used); the new linearisation point is the previous
+    solution shifted by one knot (last knot repeated) and the new x0 is the previous solution at
+    knot 1. Works on numpy arrays and on torch tensors (same slicing)."""
+    lo = tick
+    knots = ext_knots[:, :, lo:lo + n].clone() if hasattr(ext_knots, "clone") else ext_knots[:, :, lo:lo + n].copy()
+    for f_dst, f_src in ((abi.F_L, 0), (abi.F_PSI, 1), (abi.F_K, 2)):
+        knots[:, f_dst, :n - 1] = sol[:, f_src, 1:n]
+        knots[:, f_dst, n - 1] = sol[:, f_src, n - 1]
+    new_inst = inst.clone() if hasattr(inst, "clone") else inst.copy()
+    new_inst[:, abi.I_L0] = sol[:, 0, 1]
+    new_inst[:, abi.I_PSI0] = sol[:, 1, 1]
+    new_inst[:, abi.I_K0] = sol[:, 2, 1]
+    return knots, new_inst

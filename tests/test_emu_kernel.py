@@ -83,3 +83,29 @@ def test_emulated_fp64_instantiation_reproduces_oracle_iterates():
             s.update(sol[0], sol[1], sol[2])
             assert s.solve() == res2.status[b] and s.iters == res2.iters[b]
             assert np.max(np.abs(res2.x_full[b, :s.nv] - s.x())) < 1e-5
+
+
+def test_emulated_receding_horizon_ticks():
+    """BASELINE configs[4] semantics: the window advances one knot per tick, everything in the
+    instance changes (reference slice, bounds, x0, linearisation), warm state persists."""
+    params = abi.default_params()
+    n, ticks, batch = 60, 3, 3
+    ext = synthetic.make_batch(5, batch, n + ticks)
+    hb = abi.HostBatch(ext.knots[:, :, :n].copy(), ext.inst, np.full(batch, n, dtype=np.int32))
+    es = emu.EmuSolver(params, n, batch)
+    res = es.solve(hb)
+    from oracle import oracle
+    ors = [oracle.OracleSolver(params, hb.knots[b], hb.inst[b], n) for b in range(batch)]
+    for o in ors:
+        o.solve()
+    inst, sol = hb.inst, res.sol
+    for t in range(1, ticks + 1):
+        knots, inst = synthetic.shift_window(ext.knots, inst, sol, t, n)
+        hbt = abi.HostBatch(knots, inst, hb.n)
+        res = es.resolve(hbt)
+        sol = res.sol
+        for b in range(batch):
+            ors[b].update_full(knots[b], inst[b])
+            ors[b].solve()
+            ors[b].lin = None
+            parity.check_instance(params, hbt, res, b, oracle_solver=ors[b], label="tick %d" % t)

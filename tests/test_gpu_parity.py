@@ -165,3 +165,28 @@ def test_infeasible_instance_escalates_to_fp64(solver_mod):
     assert np.all(np.isin(res.status[bad], [abi.PQP_PRIMAL_INFEASIBLE, abi.PQP_MAX_ITER_REACHED]))
     assert np.array_equal(res.status[~bad], exp[~bad])
     sv.close()
+
+
+def test_receding_horizon_ticks(solver_mod):
+    from oracle import oracle
+    params = abi.default_params()
+    n, ticks, batch = 120, 3, 4
+    ext = synthetic.make_batch(5, batch, n + ticks)
+    hb = abi.HostBatch(ext.knots[:, :, :n].copy(), ext.inst, np.full(batch, n, dtype=np.int32))
+    sv = solver_mod.PathQpSolver(params, n_max=n, batch_max=batch)
+    res = sv.solve(hb, full=True)
+    ors = [oracle.OracleSolver(params, hb.knots[b], hb.inst[b], n) for b in range(batch)]
+    for o in ors:
+        o.solve()
+    inst, sol = hb.inst, res.sol
+    for t in range(1, ticks + 1):
+        knots, inst = synthetic.shift_window(ext.knots, inst, sol, t, n)
+        hbt = abi.HostBatch(knots, inst, hb.n)
+        res = sv.resolve(hbt, full=True)
+        sol = res.sol
+        for b in range(batch):
+            ors[b].update_full(knots[b], inst[b])
+            ors[b].solve()
+            ors[b].lin = None
+            parity.check_instance(params, hbt, res, b, oracle_solver=ors[b], label="tick %d" % t)
+    sv.close()
