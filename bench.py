@@ -40,6 +40,15 @@ def algorithmic_bytes(n, warm=False):
     return (296 * n + 72) if warm else (104 * n + 56)
 
 
+def measured_traffic(n, instances):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "traffic_cold_n%d.json" % n)) as f:
+            return float(json.load(f)["dram_bytes_per_instance"]) * instances
+    except Exception:
+        return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -448,7 +457,7 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(n, B), "peak_source": peak_src,
                          "kernel": "pqp_admm_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "state is shared-memory resident; the path is latency/issue bound, "
