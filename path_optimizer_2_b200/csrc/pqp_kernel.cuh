@@ -297,7 +297,8 @@ struct QpWarp {
     PQP_DEV Vec4 &V(int g, int k) { return reinterpret_cast<Vec4 *>(sm)[(g * C + k) * 32 + lane]; }
     PQP_DEV real &G(real *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
     PQP_DEV real &GL(real *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
-    PQP_DEV int &GCLSI(int k) { return *reinterpret_cast<int *>(&gscal[(GCLS * C + k) * 32 + lane]); }
+    // row-class bitmask of stage k, kept in the pad component of the yhat group (exact small integer)
+    PQP_DEV int cls_of(int k) { return (int)S(FOY + 3, k); }
     PQP_DEV StagePred pred(int k) const { return stage_pred(lane * C + k, n, p, lf, lr); }
 
     // -------------------------------------------------------------- assembly
@@ -490,7 +491,7 @@ struct QpWarp {
                 else if (r == 3) S(FKR, k) = Rw;
                 else S(FCR + r - 4, k) = Rw;
             }
-            GCLSI(k) = cls;
+            S(FOY + 3, k) = (real)cls;
         }
     }
 
@@ -753,11 +754,12 @@ struct QpWarp {
             f[4 * g] = v.x; f[4 * g + 1] = v.y; f[4 * g + 2] = v.z; f[4 * g + 3] = v.w;
         }
     }
-    PQP_DEV void solve() {
-        real acc[3] = {real(0.0), real(0.0), real(0.0)};
+    // forward sweep over the interior stages: on return bk = rhs of this lane's separator
+    // (before the contribution of the right neighbour's interior), acc = sum_k F_k b_k
+    PQP_DEV void forward_sweep(real (&bk)[3], real (&acc)[3]) {
+        acc[0] = acc[1] = acc[2] = real(0.0);
         Vec4 bv = V(GBV, 0);
-        real bk[3] = {bv.x, bv.y, bv.z};
-        // forward sweep; the factor of stage k+1 is prefetched while stage k is processed
+        bk[0] = bv.x; bk[1] = bv.y; bk[2] = bv.z;
         real f[24], fnx[24];
         if (C > 1) load_factor(0, f, false);
         PQP_ROLL
@@ -778,6 +780,15 @@ struct QpWarp {
 #pragma unroll
             for (int j = 4; j < 24; ++j) f[j] = fnx[j];
         }
+    }
+    PQP_DEV void solve() {
+        real bk[3], acc[3];
+        forward_sweep(bk, acc);
+        solve_tail(bk, acc);
+    }
+    // separators (cyclic reduction across lanes) + backward sweep; x~ ends up in GBV
+    PQP_DEV void solve_tail(const real (&bk)[3], const real (&acc)[3]) {
+        real f[24], fnx[24];
         real bs[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -974,9 +985,110 @@ struct QpWarp {
     // out: iterates advanced in shared memory, GBV = rhs of the next solve.
     // first: first iteration of a solve, where the outgoing equality rows' previous z is
     // z0 (cold: 0, warm: the previous solve's z) rather than their bound.
+    // one stage of the ADMM update: advances x, z, yhat of stage k in shared memory from
+    // x~_k (xt) and x~_{k+1} (xn); returns the stage-local part of the next rhs (bk) and the
+    // outgoing-row vector w (wo, row 2 including the u-condensation)
     template <bool kCheck>
-    PQP_DEV void admm_update(bool first, bool warm) {
+    PQP_DEV void update_stage(int k, bool first, bool warm, const real (&xt)[3], const real (&xn)[3],
+                              real (&wo)[3], real (&bk)[3]) {
         const real oma = real(1.0) - alpha;
+        const StagePred sp = pred(k);
+        StageRO q;
+        load_ro(k, q);
+        Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+        const real lt = xt[0], pt = xt[1], kt = xt[2];
+        const real ln = xn[0], pn = xn[1], kn = xn[2];
+        // previous z of the outgoing rows
+        real zo_old[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (sp.last && r < 2) zo_old[r] = zend[r];
+            else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
+        }
+        const real oyv[3] = {oy.x, oy.y, oy.z};
+        // recover the eliminated variables of x~ (rhs recomputed from the old iterates)
+        const real aux_u = q.Sw[3] * x0.w + q.ds * (q.Ro[2] * (zo_old[2] - oyv[2]));
+        const real aux_s0 = q.Sw[4] * x1.x + q.Rc[0] * (cz.x - cz.z);
+        const real aux_s1 = q.Sw[5] * x1.y + q.Rc[1] * (cz.y - cz.w);
+        const real ut = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * kt + sp.gn * kn));
+        const real s0t = q.mis0 * (aux_s0 - q.Rc[0] * (lt + sp.h0 * pt));
+        const real s1t = q.mis1 * (aux_s1 - q.Rc[1] * (lt + sp.h1 * pt));
+        // z~ = A x~
+        real zo[3];
+        zo[0] = q.a00 * lt + q.a01 * pt + sp.gn * ln;
+        zo[1] = q.a10 * lt + q.a11 * pt + q.a12 * kt + sp.gn * pn;
+        zo[2] = sp.a22 * kt + q.ds * ut + sp.gn * kn;
+        const real zk = sp.real ? kt : real(0.0);
+        const real zc0 = sp.act0 ? (lt + sp.h0 * pt + s0t) : real(0.0);
+        const real zc1 = sp.act1 ? (lt + sp.h1 * pt + s1t) : real(0.0);
+        // x+ = alpha x~ + (1 - alpha) x
+        x0.x = alpha * lt + oma * x0.x;
+        x0.y = alpha * pt + oma * x0.y;
+        x0.z = alpha * kt + oma * x0.z;
+        x0.w = alpha * ut + oma * x0.w;
+        x1.x = alpha * s0t + oma * x1.x;
+        x1.y = alpha * s1t + oma * x1.y;
+        // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
+        real wk, wc[2], oyn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const real bnd = q.ob[r];
+            const real zt = alpha * zo[r] + oma * zo_old[r];
+            const real zh = zt + oyv[r];
+            real zn;
+            if (sp.last && r < 2) {
+                zn = clampf(zh, bnd, bnd + endw[r]);
+                zend[r] = zn;
+            } else {
+                zn = bnd;
+            }
+            oyn[r] = zh - zn;
+            wo[r] = q.Ro[r] * (zn - oyn[r]);
+            if (kCheck) cert_row(r, k, q.Ro[r] * (zt - zn), bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
+        }
+        oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
+        {
+            const real zt = alpha * zk + oma * x1.z;
+            const real zh = zt + x1.w;
+            const real zn = clampf(zh, -kmax, kmax);
+            x1.z = zn;
+            x1.w = zh - zn;
+            wk = q.Rk * (zn - x1.w);
+            if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
+        }
+        {
+            const real zt = alpha * zc0 + oma * cz.x;
+            const real zh = zt + cz.z;
+            const real zn = clampf(zh, q.clo[0], q.chi[0]);
+            cz.x = zn;
+            cz.z = zh - zn;
+            wc[0] = q.Rc[0] * (zn - cz.z);
+            if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
+        }
+        {
+            const real zt = alpha * zc1 + oma * cz.y;
+            const real zh = zt + cz.w;
+            const real zn = clampf(zh, q.clo[1], q.chi[1]);
+            cz.y = zn;
+            cz.w = zh - zn;
+            wc[1] = q.Rc[1] * (zn - cz.w);
+            if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
+        }
+        V(GX0, k) = x0;
+        V(GX1, k) = x1;
+        V(GOY, k) = oy;
+        V(GCZ, k) = cz;
+        const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+        local_rhs(q, sp, x, wo, wk, wc, bk);
+    }
+
+    // ADMM update of all stages fused with the forward sweep of the next solve. The last stage is
+    // updated first (its outgoing rows feed the right neighbour lane's first stage), then the
+    // stages ascend; as soon as b_k is final the sweep step b_k -= G_{k-1} b_{k-1} is applied, so
+    // the sweep's dependent chain hides behind the independent update work.
+    // in: GBV = x~; out: GBV(k < C-1) = swept rhs, bk/acc as after forward_sweep().
+    template <bool kCheck>
+    PQP_DEV void admm_update_fused(bool first, bool warm, real (&bk_out)[3], real (&acc)[3]) {
         real xnb[3];
         {
             const Vec4 v = V(GBV, 0);
@@ -986,112 +1098,72 @@ struct QpWarp {
             if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = real(0.0); }
         }
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
-        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
-        Vec4 xt = V(GBV, 0);
+        acc[0] = acc[1] = acc[2] = real(0.0);
+        real wo_last[3], bp_last[3], wL0[3], bprev[3], wprev[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { wo_last[r] = bp_last[r] = wL0[r] = bprev[r] = wprev[r] = real(0.0); }
         PQP_ROLL
-        for (int k = 0; k < C; ++k) {
-            const StagePred sp = pred(k);
-            StageRO q;
-            load_ro(k, q);
-            Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
-            const Vec4 xtn = V(GBV, k < C - 1 ? k + 1 : k);
-            const real lt = xt.x, pt = xt.y, kt = xt.z;
-            const real ln = (k == C - 1) ? xnb[0] : xtn.x;
-            const real pn = (k == C - 1) ? xnb[1] : xtn.y;
-            const real kn = (k == C - 1) ? xnb[2] : xtn.z;
-            // previous z of the outgoing rows
-            real zo_old[3];
+        for (int j = 0; j < C; ++j) {
+            const int k = (j == 0) ? C - 1 : j - 1;
+            const Vec4 xv = V(GBV, k);
+            const Vec4 xw = V(GBV, k < C - 1 ? k + 1 : k);
+            const real xt[3] = {xv.x, xv.y, xv.z};
+            real xn[3];
+            xn[0] = (k == C - 1) ? xnb[0] : xw.x;
+            xn[1] = (k == C - 1) ? xnb[1] : xw.y;
+            xn[2] = (k == C - 1) ? xnb[2] : xw.z;
+            real wo[3], bp[3];
+            update_stage<kCheck>(k, first, warm, xt, xn, wo, bp);
+            if (j == 0) {
+                const StagePred sp0 = pred(0);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                if (sp.last && r < 2) zo_old[r] = zend[r];
-                else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
-            }
-            const real oyv[3] = {oy.x, oy.y, oy.z};
-            // recover the eliminated variables of x~ (rhs recomputed from the old iterates)
-            const real aux_u = q.Sw[3] * x0.w + q.ds * (q.Ro[2] * (zo_old[2] - oyv[2]));
-            const real aux_s0 = q.Sw[4] * x1.x + q.Rc[0] * (cz.x - cz.z);
-            const real aux_s1 = q.Sw[5] * x1.y + q.Rc[1] * (cz.y - cz.w);
-            const real ut = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * kt + sp.gn * kn));
-            const real s0t = q.mis0 * (aux_s0 - q.Rc[0] * (lt + sp.h0 * pt));
-            const real s1t = q.mis1 * (aux_s1 - q.Rc[1] * (lt + sp.h1 * pt));
-            // z~ = A x~
-            real zo[3];
-            zo[0] = q.a00 * lt + q.a01 * pt + sp.gn * ln;
-            zo[1] = q.a10 * lt + q.a11 * pt + q.a12 * kt + sp.gn * pn;
-            zo[2] = sp.a22 * kt + q.ds * ut + sp.gn * kn;
-            const real zk = sp.real ? kt : real(0.0);
-            const real zc0 = sp.act0 ? (lt + sp.h0 * pt + s0t) : real(0.0);
-            const real zc1 = sp.act1 ? (lt + sp.h1 * pt + s1t) : real(0.0);
-            // x+ = alpha x~ + (1 - alpha) x
-            x0.x = alpha * lt + oma * x0.x;
-            x0.y = alpha * pt + oma * x0.y;
-            x0.z = alpha * kt + oma * x0.z;
-            x0.w = alpha * ut + oma * x0.w;
-            x1.x = alpha * s0t + oma * x1.x;
-            x1.y = alpha * s1t + oma * x1.y;
-            // rows: z+ = clamp(alpha z~ + (1-alpha) z + yhat), yhat+ = (..) - z+, w = R (z+ - yhat+)
-            real wo[3], wk, wc[2], bk[3], oyn[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const real bnd = q.ob[r];
-                const real zt = alpha * zo[r] + oma * zo_old[r];
-                const real zh = zt + oyv[r];
-                real zn;
-                if (sp.last && r < 2) {
-                    zn = clampf(zh, bnd, bnd + endw[r]);
-                    zend[r] = zn;
-                } else {
-                    zn = bnd;
+                for (int r = 0; r < 3; ++r) {
+                    wo_last[r] = wo[r];
+                    bp_last[r] = bp[r];
+                    real w = shfl_up(wo[r], 1, lane);
+                    wL0[r] = (lane == 0 || !sp0.real) ? real(0.0) : w;
                 }
-                oyn[r] = zh - zn;
-                wo[r] = q.Ro[r] * (zn - oyn[r]);
-                if (kCheck) cert_row(r, k, q.Ro[r] * (zt - zn), bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
-            }
-            oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
-            {
-                const real zt = alpha * zk + oma * x1.z;
-                const real zh = zt + x1.w;
-                const real zn = clampf(zh, -kmax, kmax);
-                x1.z = zn;
-                x1.w = zh - zn;
-                wk = q.Rk * (zn - x1.w);
-                if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
-            }
-            {
-                const real zt = alpha * zc0 + oma * cz.x;
-                const real zh = zt + cz.z;
-                const real zn = clampf(zh, q.clo[0], q.chi[0]);
-                cz.x = zn;
-                cz.z = zh - zn;
-                wc[0] = q.Rc[0] * (zn - cz.z);
-                if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
-            }
-            {
-                const real zt = alpha * zc1 + oma * cz.y;
-                const real zh = zt + cz.w;
-                const real zn = clampf(zh, q.clo[1], q.chi[1]);
-                cz.y = zn;
-                cz.w = zh - zn;
-                wc[1] = q.Rc[1] * (zn - cz.w);
-                if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
-            }
-            V(GX0, k) = x0;
-            V(GX1, k) = x1;
-            V(GOY, k) = oy;
-            V(GCZ, k) = cz;
-            const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-            local_rhs(q, sp, x, wo, wk, wc, bk);
-            Vec4 bv;
-            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
-            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
-            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
-            bv.w = real(0.0);
-            V(GBV, k) = bv;
+                if (C > 1) continue;
+            } else {
+                const StagePred sp = pred(k);
+                real bfin[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
-            xt = xtn;
+                for (int r = 0; r < 3; ++r) bfin[r] = bp[r] - ((k == 0) ? wL0[r] : (sp.real ? wprev[r] : real(0.0)));
+                if (k >= 1) {
+                    real f[24];
+                    load_factor(k - 1, f, false);
+                    const real *Gm = f + 6, *Fm = f + 15;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        bfin[r] -= Gm[3 * r] * bprev[0] + Gm[3 * r + 1] * bprev[1] + Gm[3 * r + 2] * bprev[2];
+                        acc[r] += Fm[3 * r] * bprev[0] + Fm[3 * r + 1] * bprev[1] + Fm[3 * r + 2] * bprev[2];
+                    }
+                }
+                Vec4 bv;
+                bv.x = bfin[0]; bv.y = bfin[1]; bv.z = bfin[2]; bv.w = real(0.0);
+                V(GBV, k) = bv;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { bprev[r] = bfin[r]; wprev[r] = wo[r]; }
+            }
         }
-        fix_first_stage(wprev);
+        // the separator stage's rhs
+        {
+            const StagePred spl = pred(C - 1);
+            if (C == 1) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) bk_out[r] = bp_last[r] - wL0[r];
+            } else {
+                real f[24];
+                load_factor(C - 2, f, false);
+                const real *Gm = f + 6, *Fm = f + 15;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    bk_out[r] = bp_last[r] - (spl.real ? wprev[r] : real(0.0)) -
+                                (Gm[3 * r] * bprev[0] + Gm[3 * r + 1] * bprev[1] + Gm[3 * r + 2] * bprev[2]);
+                    acc[r] += Fm[3 * r] * bprev[0] + Fm[3 * r + 1] * bprev[1] + Fm[3 * r + 2] * bprev[2];
+                }
+            }
+        }
     }
 
     // -------------------------------------------------------------- residuals (OSQP update_info)
@@ -1120,10 +1192,21 @@ struct QpWarp {
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            // Ruiz scalings (global scratch): issued first so their latency overlaps the rest
+            // Ruiz scalings recovered from the weights held on chip: R_r = base_r e_r^2 / c and
+            // S_j = sigma / (c d_j^2)  (no global loads in the check path)
             real ev[6], dv[6];
+            {
+                const int cls = cls_of(k);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { ev[j] = G(gscal, GE + j, k); dv[j] = c * G(gscal, GD + j, k); }
+                for (int r = 0; r < 6; ++r) {
+                    const int cl = (cls >> (2 * r)) & 3;
+                    const real Rr = (r < 3) ? S(FOR_ + r, k) : (r == 3 ? S(FKR, k) : S(FCR + r - 4, k));
+                    const real base = cl == 1 ? real(kRhoEqOverIneq) * rho : (cl == 0 ? rho : real(kRhoMin));
+                    ev[r] = cl == 3 ? real(0.0) : xsqrt(Rr * c / base);
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) dv[j] = c * xsqrt(sigma / (c * S(FS + j, k)));
+            }
             const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
             const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
@@ -1251,7 +1334,7 @@ struct QpWarp {
         rho = est;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
-            const int cls = GCLSI(k);
+            const int cls = cls_of(k);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const int cl = (cls >> (2 * r)) & 3;
@@ -1308,15 +1391,19 @@ struct QpWarp {
             PQP_ROLL
             int to_check = P.check_every > 0 ? P.check_every : -1;
             int to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
+            bool fwd_done = false;  // GBV already forward-swept by the fused update
+            real bsep[3], facc[3];
             for (iter = 1; iter <= P.max_iter; ++iter) {
-                solve();
+                if (!fwd_done) forward_sweep(bsep, facc);
+                solve_tail(bsep, facc);
                 // iter % interval == 0 without an integer division in the loop
                 const bool can_check = (--to_check == 0);
                 const bool can_adapt = (--to_adapt == 0);
                 if (can_check) to_check = P.check_every;
                 if (can_adapt) to_adapt = P.adaptive_interval;
-                if (can_check) admm_update<true>(iter == 1, warm);
-                else admm_update<false>(iter == 1, warm);
+                if (can_check) admm_update_fused<true>(iter == 1, warm, bsep, facc);
+                else admm_update_fused<false>(iter == 1, warm, bsep, facc);
+                fwd_done = true;
                 checked = false;
                 if (can_check || can_adapt) {
                     nr = residuals();
@@ -1332,6 +1419,7 @@ struct QpWarp {
                             if (!ok2) { status = kNumerical; break; }
                             sync_warp(lane);
                             build_rhs(false, warm);
+                            fwd_done = false;
                         }
                     }
                 }
