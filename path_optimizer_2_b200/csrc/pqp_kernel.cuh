@@ -151,6 +151,13 @@ PQP_DEV double xabs(double a) { return fabs(a); }
 PQP_DEV float xsqrt(float a) { return sqrtf(a); }
 PQP_DEV double xsqrt(double a) { return sqrt(a); }
 template <typename T> PQP_DEV T frsqrt(T x) { return T(1) / xsqrt(x); }
+// fast reciprocal square root (MUFU.RSQ in FP32); used only for the scaled norms of the rho estimate
+#ifdef PQP_EMU
+PQP_DEV float xfast_rsqrt(float a) { return 1.0f / std::sqrt(a); }
+#else
+PQP_DEV float xfast_rsqrt(float a) { return rsqrtf(a); }
+#endif
+PQP_DEV double xfast_rsqrt(double a) { return 1.0 / sqrt(a); }
 
 template <typename T> PQP_DEV T warp_max(T v, int lane) {
 #pragma unroll
@@ -265,6 +272,9 @@ PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, doubl
 // this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction
 // cache (40 % no_inst stalls in profiles/r1/ncu_v1_unrolled_summary.txt).
 #define PQP_ROLL _Pragma("unroll 1")
+#ifndef PQP_UPDATE_UNROLL
+#define PQP_UPDATE_UNROLL _Pragma("unroll 1")
+#endif
 
 template <int C, typename real>
 struct QpWarp {
@@ -1082,13 +1092,12 @@ struct QpWarp {
         local_rhs(q, sp, x, wo, wk, wc, bk);
     }
 
-    // ADMM update of all stages fused with the forward sweep of the next solve. The last stage is
-    // updated first (its outgoing rows feed the right neighbour lane's first stage), then the
-    // stages ascend; as soon as b_k is final the sweep step b_k -= G_{k-1} b_{k-1} is applied, so
-    // the sweep's dependent chain hides behind the independent update work.
-    // in: GBV = x~; out: GBV(k < C-1) = swept rhs, bk/acc as after forward_sweep().
+    // ADMM update of all stages (ascending; the left neighbour's outgoing rows are carried in
+    // registers). A variant fused with the next forward sweep was measured slower (in-order issue
+    // serialises the sweep step behind each stage's update; profiles/r1/README.md).
+    // in: GBV = x~; out: iterates advanced, GBV = rhs of the next solve.
     template <bool kCheck>
-    PQP_DEV void admm_update_fused(bool first, bool warm, real (&bk_out)[3], real (&acc)[3]) {
+    PQP_DEV void admm_update(bool first, bool warm) {
         real xnb[3];
         {
             const Vec4 v = V(GBV, 0);
@@ -1098,72 +1107,30 @@ struct QpWarp {
             if (lane == 31) { xnb[0] = xnb[1] = xnb[2] = real(0.0); }
         }
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
-        acc[0] = acc[1] = acc[2] = real(0.0);
-        real wo_last[3], bp_last[3], wL0[3], bprev[3], wprev[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { wo_last[r] = bp_last[r] = wL0[r] = bprev[r] = wprev[r] = real(0.0); }
-        PQP_ROLL
-        for (int j = 0; j < C; ++j) {
-            const int k = (j == 0) ? C - 1 : j - 1;
-            const Vec4 xv = V(GBV, k);
+        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
+        Vec4 xv = V(GBV, 0);
+        PQP_UPDATE_UNROLL
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
             const Vec4 xw = V(GBV, k < C - 1 ? k + 1 : k);
             const real xt[3] = {xv.x, xv.y, xv.z};
             real xn[3];
             xn[0] = (k == C - 1) ? xnb[0] : xw.x;
             xn[1] = (k == C - 1) ? xnb[1] : xw.y;
             xn[2] = (k == C - 1) ? xnb[2] : xw.z;
-            real wo[3], bp[3];
-            update_stage<kCheck>(k, first, warm, xt, xn, wo, bp);
-            if (j == 0) {
-                const StagePred sp0 = pred(0);
+            real wo[3], bk[3];
+            update_stage<kCheck>(k, first, warm, xt, xn, wo, bk);
+            Vec4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
+            bv.w = real(0.0);
+            V(GBV, k) = bv;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    wo_last[r] = wo[r];
-                    bp_last[r] = bp[r];
-                    real w = shfl_up(wo[r], 1, lane);
-                    wL0[r] = (lane == 0 || !sp0.real) ? real(0.0) : w;
-                }
-                if (C > 1) continue;
-            } else {
-                const StagePred sp = pred(k);
-                real bfin[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) bfin[r] = bp[r] - ((k == 0) ? wL0[r] : (sp.real ? wprev[r] : real(0.0)));
-                if (k >= 1) {
-                    real f[24];
-                    load_factor(k - 1, f, false);
-                    const real *Gm = f + 6, *Fm = f + 15;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        bfin[r] -= Gm[3 * r] * bprev[0] + Gm[3 * r + 1] * bprev[1] + Gm[3 * r + 2] * bprev[2];
-                        acc[r] += Fm[3 * r] * bprev[0] + Fm[3 * r + 1] * bprev[1] + Fm[3 * r + 2] * bprev[2];
-                    }
-                }
-                Vec4 bv;
-                bv.x = bfin[0]; bv.y = bfin[1]; bv.z = bfin[2]; bv.w = real(0.0);
-                V(GBV, k) = bv;
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { bprev[r] = bfin[r]; wprev[r] = wo[r]; }
-            }
+            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
+            xv = xw;
         }
-        // the separator stage's rhs
-        {
-            const StagePred spl = pred(C - 1);
-            if (C == 1) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) bk_out[r] = bp_last[r] - wL0[r];
-            } else {
-                real f[24];
-                load_factor(C - 2, f, false);
-                const real *Gm = f + 6, *Fm = f + 15;
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    bk_out[r] = bp_last[r] - (spl.real ? wprev[r] : real(0.0)) -
-                                (Gm[3 * r] * bprev[0] + Gm[3 * r + 1] * bprev[1] + Gm[3 * r + 2] * bprev[2]);
-                    acc[r] += Fm[3 * r] * bprev[0] + Fm[3 * r + 1] * bprev[1] + Fm[3 * r + 2] * bprev[2];
-                }
-            }
-        }
+        fix_first_stage(wprev);
     }
 
     // -------------------------------------------------------------- residuals (OSQP update_info)
@@ -1189,11 +1156,14 @@ struct QpWarp {
 #pragma unroll
         for (int j = 0; j < 12; ++j) m[j] = real(0.0);
         const real c = cscale;
+        // e_r = sqrt(R_r) * sqrt(c / base_class), c d_j = sqrt(sigma c) / sqrt(S_j)
+        const real ke_in = xsqrt(c / rho), ke_eq = xsqrt(c / (real(kRhoEqOverIneq) * rho)),
+                   ke_lo = xsqrt(c / real(kRhoMin)), kd = xsqrt(sigma * c);
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             // Ruiz scalings recovered from the weights held on chip: R_r = base_r e_r^2 / c and
-            // S_j = sigma / (c d_j^2)  (no global loads in the check path)
+            // S_j = sigma / (c d_j^2)  (no global loads, no divisions in the check path)
             real ev[6], dv[6];
             {
                 const int cls = cls_of(k);
@@ -1201,11 +1171,11 @@ struct QpWarp {
                 for (int r = 0; r < 6; ++r) {
                     const int cl = (cls >> (2 * r)) & 3;
                     const real Rr = (r < 3) ? S(FOR_ + r, k) : (r == 3 ? S(FKR, k) : S(FCR + r - 4, k));
-                    const real base = cl == 1 ? real(kRhoEqOverIneq) * rho : (cl == 0 ? rho : real(kRhoMin));
-                    ev[r] = cl == 3 ? real(0.0) : xsqrt(Rr * c / base);
+                    const real kc = cl == 1 ? ke_eq : (cl == 0 ? ke_in : ke_lo);
+                    ev[r] = (cl == 3 || !(Rr > real(0.0))) ? real(0.0) : Rr * xfast_rsqrt(Rr) * kc;
                 }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) dv[j] = c * xsqrt(sigma / (c * S(FS + j, k)));
+                for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(S(FS + j, k));
             }
             const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
@@ -1391,19 +1361,15 @@ struct QpWarp {
             PQP_ROLL
             int to_check = P.check_every > 0 ? P.check_every : -1;
             int to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
-            bool fwd_done = false;  // GBV already forward-swept by the fused update
-            real bsep[3], facc[3];
             for (iter = 1; iter <= P.max_iter; ++iter) {
-                if (!fwd_done) forward_sweep(bsep, facc);
-                solve_tail(bsep, facc);
+                solve();
                 // iter % interval == 0 without an integer division in the loop
                 const bool can_check = (--to_check == 0);
                 const bool can_adapt = (--to_adapt == 0);
                 if (can_check) to_check = P.check_every;
                 if (can_adapt) to_adapt = P.adaptive_interval;
-                if (can_check) admm_update_fused<true>(iter == 1, warm, bsep, facc);
-                else admm_update_fused<false>(iter == 1, warm, bsep, facc);
-                fwd_done = true;
+                if (can_check) admm_update<true>(iter == 1, warm);
+                else admm_update<false>(iter == 1, warm);
                 checked = false;
                 if (can_check || can_adapt) {
                     nr = residuals();
@@ -1419,7 +1385,6 @@ struct QpWarp {
                             if (!ok2) { status = kNumerical; break; }
                             sync_warp(lane);
                             build_rhs(false, warm);
-                            fwd_done = false;
                         }
                     }
                 }
