@@ -129,8 +129,10 @@ struct pqp_handle {
     int n_max = 0, batch_max = 0, device = 0, chunk = 0;
     int sm_count = 0, warps_per_sm = 0;
     size_t smem_bytes = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t evs[2] = {nullptr, nullptr};
+    static const int kStreams = 8;
+    cudaStream_t stream = nullptr;            // streams[0]
+    cudaStream_t streams[kStreams] = {};      // one per pipeline chunk
+    cudaEvent_t evs[kStreams] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device buffers owned by the handle
     double *d_knots = nullptr, *d_inst = nullptr, *d_sol = nullptr, *d_cost = nullptr, *d_info = nullptr;
@@ -372,26 +374,26 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     if (out->x_full && !h->d_xf) PQP_CUDA(h, dmalloc(&h->d_xf, (size_t)h->batch_max * nvm));
     if (out->y_full && !h->d_yf) PQP_CUDA(h, dmalloc(&h->d_yf, (size_t)h->batch_max * mm));
     if (out->z_full && !h->d_zf) PQP_CUDA(h, dmalloc(&h->d_zf, (size_t)h->batch_max * mm));
-    // Chunked two-stream pipeline: chunk c+1's H2D copy and chunk c-1's D2H copy overlap chunk
-    // c's kernel (fully asynchronous when the caller's buffers are pinned). Scratch slots are
-    // addressed by the instance's index in the whole batch (qp0), so chunking is invisible to
-    // the warm state.
+    // Chunked pipeline, one stream per chunk: chunk c+1's H2D copy and chunk c-1's D2H copy
+    // overlap chunk c's kernel (fully asynchronous when the caller's buffers are pinned), and
+    // because every chunk's kernel sits in its own stream the block scheduler back-fills SMs
+    // from the next chunk as soon as its inputs have landed (no partial-wave bubble between
+    // chunks). Scratch slots are addressed by the instance's index in the whole batch (qp0),
+    // so chunking is invisible to the warm state.
     const int kMinChunk = 1024;
     int nchunks = (B + kMinChunk - 1) / kMinChunk;
-    if (nchunks > 8) nchunks = 8;
+    if (nchunks > pqp_handle::kStreams) nchunks = pqp_handle::kStreams;
     if (nchunks < 1) nchunks = 1;
     const int per = (B + nchunks - 1) / nchunks;
-    cudaStream_t streams[2] = {h->stream, h->stream2};
-    if (!in) {  // relinearise ran on streams[0]: make stream2 wait for it
-        PQP_CUDA(h, cudaEventRecord(h->evs[0], streams[0]));
-        PQP_CUDA(h, cudaStreamWaitEvent(streams[1], h->evs[0], 0));
-    }
+    cudaStream_t *streams = h->streams;
+    // every chunk stream starts after whatever the handle's main stream has queued so far
     PQP_CUDA(h, cudaEventRecord(h->ev0, streams[0]));
+    for (int c = 1; c < nchunks; ++c) PQP_CUDA(h, cudaStreamWaitEvent(streams[c], h->ev0, 0));
     for (int c = 0; c < nchunks; ++c) {
         const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
         if (lo >= hi) break;
         const size_t nb = (size_t)(hi - lo);
-        cudaStream_t s = streams[c & 1];
+        cudaStream_t s = streams[c];
         if (in) {
             PQP_CUDA(h, cudaMemcpyAsync(h->d_knots + (size_t)lo * PQP_NFIELDS * nmax, in->knots + (size_t)lo * PQP_NFIELDS * nmax,
                                         nb * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -433,9 +435,11 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full + lo * mm, dout.z_full, nb * mm * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     h->last_batch = B;
-    // join: stream[0] waits for stream[1]; ev1 marks the end of the whole pipeline
-    PQP_CUDA(h, cudaEventRecord(h->evs[1], streams[1]));
-    PQP_CUDA(h, cudaStreamWaitEvent(streams[0], h->evs[1], 0));
+    // join: stream[0] waits for every chunk stream; ev1 marks the end of the whole pipeline
+    for (int c = 1; c < nchunks; ++c) {
+        PQP_CUDA(h, cudaEventRecord(h->evs[c], streams[c]));
+        PQP_CUDA(h, cudaStreamWaitEvent(streams[0], h->evs[c], 0));
+    }
     PQP_CUDA(h, cudaEventRecord(h->ev1, streams[0]));
     PQP_CUDA(h, cudaStreamSynchronize(streams[0]));
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
@@ -505,10 +509,11 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
         PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps));
     }
     h->warps_per_sm = bps;
-    PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[0], cudaEventDisableTiming));
-    PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[1], cudaEventDisableTiming));
+    for (int i = 0; i < pqp_handle::kStreams; ++i) {
+        PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+        PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[i], cudaEventDisableTiming));
+    }
+    h->stream = h->streams[0];
     PQP_CREATE_CUDA(cudaEventCreate(&h->ev0));
     PQP_CREATE_CUDA(cudaEventCreate(&h->ev1));
     const size_t B = batch_max, c = h->chunk;
@@ -540,7 +545,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
 int pqp_destroy(pqp_handle *h) {
     if (!h) return PQP_OK;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < pqp_handle::kStreams; ++i) if (h->streams[i]) cudaStreamSynchronize(h->streams[i]);
     cudaFree(h->d_knots); cudaFree(h->d_inst); cudaFree(h->d_n); cudaFree(h->d_p);
     cudaFree(h->d_sol); cudaFree(h->d_cost); cudaFree(h->d_status); cudaFree(h->d_iters);
     cudaFree(h->d_info); cudaFree(h->d_xf); cudaFree(h->d_yf); cudaFree(h->d_zf);
@@ -554,10 +559,10 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->e_status); cudaFree(h->e_iters); cudaFree(h->e_warm); cudaFree(h->e_scal); cudaFree(h->e_dy); cudaFree(h->e_rho);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
-    if (h->evs[0]) cudaEventDestroy(h->evs[0]);
-    if (h->evs[1]) cudaEventDestroy(h->evs[1]);
+    for (int i = 0; i < pqp_handle::kStreams; ++i) {
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+        if (h->evs[i]) cudaEventDestroy(h->evs[i]);
+    }
     delete h;
     return PQP_OK;
 }
