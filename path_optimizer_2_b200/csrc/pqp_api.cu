@@ -83,8 +83,127 @@ __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pq
         mbar_wait(bar, 0);
         src = stage;
     }
-    pqp::QpWarp<C, real> w(ka, smem, lane, qp);
+    pqp::QpWarp<C, real> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
     w.run(src, ka.n_max);
+}
+
+
+// ------------------------------------------------------------------ device: tensor-memory storage policy
+// The solver keeps a QP's per-stage state as [group][stage][lane] float4. Tensor memory is 128
+// lanes x 512 32-bit columns per SM and a warp reaches the 32 lanes of its own sub-partition
+// with tcgen05.ld/st (32x32b shapes: each thread gets N consecutive columns of "its" lane), so
+// the layout maps 1:1 with column = (k * kGroups + slot(g)) * 4 + component. A CTA of four
+// warps (four QPs) owns all 512 columns; at C = 8 sixteen of the eighteen groups fit and the two
+// least-frequently read ones (clearance weights / proximal weights) stay in shared memory.
+// Measured on B200 (profiles/r1/tmem_probe_result.txt): dependent tcgen05.ld latency <= LDS.128,
+// streaming bandwidth ~6x shared memory.
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t a) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(a) : "memory");
+    tmem_wait_ld();
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_st1(uint32_t a, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t a, float (&o)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a) : "memory");
+    o[0] = __uint_as_float(r0); o[1] = __uint_as_float(r1); o[2] = __uint_as_float(r2); o[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t a, const float4 &v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(v.x)),
+                 "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+                 : "memory");
+}
+
+template <int C>
+struct TmemStore {
+    typedef float4 Vec4;
+    static constexpr int kAll = pqp::NFIELD / 4;                       // 18 groups
+    static constexpr int kFit = 512 / (4 * C);                         // groups that fit in 512 columns
+    static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
+    static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8, else 0
+    uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
+    float *sm;    // spill area (shared memory) of this warp: [spill slot][k][lane] float4
+    int lane;
+    __device__ TmemStore(uint32_t t, float *s, int l) : tb(t), sm(s), lane(l) {}
+    // groups GR5 (5) and GS6 (6) spill first; everything else keeps its relative order
+    __device__ static constexpr bool spilled(int g) { return kSpill > 0 && (g == pqp::GR5 || g == pqp::GS6) && (g - pqp::GR5) < kSpill; }
+    __device__ static constexpr int slot(int g) { return (kSpill > 0 && g > pqp::GS6) ? g - kSpill : g; }
+    __device__ uint32_t col(int g, int k) const { return tb + (uint32_t)((k * kGroups + slot(g)) * 4); }
+    __device__ float4 *sp(int g, int k) const { return reinterpret_cast<float4 *>(sm) + (((g - pqp::GR5) * C + k) * 32 + lane); }
+    __device__ float ld(int f, int k) const {
+        const int g = f >> 2;
+        if (spilled(g)) return reinterpret_cast<const float *>(sp(g, k))[f & 3];
+        return tmem_ld1(col(g, k) + (f & 3));
+    }
+    __device__ void st(int f, int k, float v) {
+        const int g = f >> 2;
+        if (spilled(g)) { reinterpret_cast<float *>(sp(g, k))[f & 3] = v; return; }
+        tmem_st1(col(g, k) + (f & 3), v);
+        tmem_wait_st();
+    }
+    __device__ float4 ld4(int g, int k) const {
+        if (spilled(g)) return *sp(g, k);
+        float o[4];
+        tmem_ld4_nowait(col(g, k), o);
+        tmem_wait_ld();
+        return make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __device__ void st4(int g, int k, const float4 &v) {
+        if (spilled(g)) { *sp(g, k) = v; return; }
+        tmem_st4(col(g, k), v);
+    }
+    template <int N> __device__ void ld4n(int g0, int k, float (&out)[4 * N]) const {
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+            float o[4];
+            if (spilled(g0 + g)) {
+                const float4 v = *sp(g0 + g, k);
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            } else {
+                tmem_ld4_nowait(col(g0 + g, k), o);
+            }
+            out[4 * g] = o[0]; out[4 * g + 1] = o[1]; out[4 * g + 2] = o[2]; out[4 * g + 3] = o[3];
+        }
+        tmem_wait_ld();
+    }
+    __device__ void fence() { tmem_wait_st(); }
+};
+
+// One CTA = four warps = four QP instances, state in tensor memory (FP32 only).
+template <int C>
+__global__ void __launch_bounds__(128) pqp_admm_kernel_tmem(const __grid_constant__ pqp::KernelArgs ka) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t tbase_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t need = TmemStore<C>::kGroups * 4 * C;
+    constexpr uint32_t ncols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    if (warp == 0) tmem_alloc(&tbase_s, ncols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tbase_s + ((uint32_t)(32 * warp) << 16);
+    float *spill = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 1) * C * 32 * 4;
+    const int qp = blockIdx.x * 4 + warp;
+    if (qp < ka.batch) {
+        const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+        pqp::QpWarp<C, float, TmemStore<C> > w(ka, TmemStore<C>(tb, spill, lane), lane, qp);
+        w.run(src, ka.n_max);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase_s, ncols);
 }
 
 // BaseSolver::getOptimizedPath (base_solver.cpp:263-288) in FP64, one thread per knot.
@@ -139,6 +258,7 @@ struct pqp_handle {
     double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
     int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
     void *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    bool use_tmem = false;         // params.reserved bit 3: state in tensor memory (FP32 kernel)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
     size_t smem_bytes64 = 0;
@@ -207,6 +327,31 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
     }
 }
 
+// tensor-memory variant: 4 QPs per CTA; the dynamic shared-memory request is padded so that only
+// one CTA (which owns all 512 TMEM columns) is resident per SM
+constexpr size_t kTmemSmem = 120 * 1024;
+template <int C>
+cudaError_t launch_tmem(const pqp::KernelArgs &ka, cudaStream_t s) {
+    pqp_admm_kernel_tmem<C><<<(ka.batch + 3) / 4, 128, kTmemSmem, s>>>(ka);
+    return cudaGetLastError();
+}
+cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s) {
+    switch (chunk) {
+        case 1: return launch_tmem<1>(ka, s);
+        case 2: return launch_tmem<2>(ka, s);
+        case 4: return launch_tmem<4>(ka, s);
+        default: return launch_tmem<8>(ka, s);
+    }
+}
+cudaError_t prepare_tmem_chunk(int chunk) {
+    switch (chunk) {
+        case 1: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+        case 2: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+        case 4: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+        default: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+    }
+}
+
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
     if (!h) return PQP_E_INVALID;
     if (!in || !out) return fail(h, PQP_E_INVALID, "null batch");
@@ -252,6 +397,9 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
             h->prepared64 = true;
         }
         PQP_CUDA(h, launch_chunk<double>(h->chunk, ka, h->smem_bytes64, s));
+    } else if (h->use_tmem) {
+        ka.use_tma = 0;
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s));
     } else {
         PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
     }
@@ -500,6 +648,8 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(cudaSetDevice(device));
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
+    h->use_tmem = (params->reserved & 8) != 0 && !h->fp64;
+    if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
     if (h->fp64) {

@@ -267,6 +267,33 @@ PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, doubl
     oub = ub - shrink;
 }
 
+
+// ------------------------------------------------------------------ storage policies
+// Where a QP's per-stage state lives. Logical field f = 4*group + component; the policy maps
+// (field, local stage k, this lane) to storage. Only the owning lane ever touches an element:
+// neighbour values travel by warp shuffle, never by cross-lane loads, so the same solver code
+// runs on shared memory (SmemStore) and on tensor memory (TmemStore in pqp_api.cu).
+template <int C, typename real>
+struct SmemStore {
+    typedef typename Vec4T<real>::type Vec4;
+    real *sm;
+    int lane;
+    PQP_DEV SmemStore(real *s, int l) : sm(s), lane(l) {}
+    PQP_DEV real ld(int f, int k) const { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
+    PQP_DEV void st(int f, int k, real v) { sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)] = v; }
+    PQP_DEV Vec4 ld4(int g, int k) const { return reinterpret_cast<const Vec4 *>(sm)[(g * C + k) * 32 + lane]; }
+    PQP_DEV void st4(int g, int k, const Vec4 &v) { reinterpret_cast<Vec4 *>(sm)[(g * C + k) * 32 + lane] = v; }
+    // n consecutive groups g0.. of stage k into out[4n] (one latency for all of them)
+    template <int N> PQP_DEV void ld4n(int g0, int k, real (&out)[4 * N]) const {
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+            const Vec4 v = ld4(g0 + g, k);
+            out[4 * g] = v.x; out[4 * g + 1] = v.y; out[4 * g + 2] = v.z; out[4 * g + 3] = v.w;
+        }
+    }
+    PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
+};
+
 // =========================================================================================
 // All per-stage loops are deliberately NOT unrolled (#pragma unroll 1): the first version of
 // this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction
@@ -276,11 +303,11 @@ PQP_DEV void soft_bounds(double lb, double ub, double margin, double &olb, doubl
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
 
-template <int C, typename real>
+template <int C, typename real, typename Store = SmemStore<C, real> >
 struct QpWarp {
     typedef typename Vec4T<real>::type Vec4;
     const KernelArgs &ka;
-    real *sm;
+    Store store;
     const int lane, qp;
     int n, p;
     real lf, lr, kmax;
@@ -298,13 +325,25 @@ struct QpWarp {
     // solver parameters in the kernel's scalar type
     real w_l, w_kappa, w_dkappa, w_slack, sigma, alpha, eps_abs, eps_rel, eps_pinf, rho_tol;
 
-    PQP_DEV QpWarp(const KernelArgs &k, real *s, int l, int q) : ka(k), sm(s), lane(l), qp(q) {}
+    PQP_DEV QpWarp(const KernelArgs &k, const Store &st, int l, int q) : ka(k), store(st), lane(l), qp(q) {}
 
-    // scalar view of logical field f (group f>>2, component f&3)
-    PQP_DEV real &S(int f, int k) { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
-    PQP_DEV real &SL(int f, int k, int ln) { return sm[(((f >> 2) * C + k) * 32 + ln) * 4 + (f & 3)]; }
-    // vector view of group g
-    PQP_DEV Vec4 &V(int g, int k) { return reinterpret_cast<Vec4 *>(sm)[(g * C + k) * 32 + lane]; }
+    // proxy views of the policy-backed state: S(f,k) behaves like a real&, V(g,k) like a Vec4&
+    struct SRef {
+        Store &st; int f, k;
+        PQP_DEV operator real() const { return st.ld(f, k); }
+        PQP_DEV SRef &operator=(real v) { st.st(f, k, v); return *this; }
+        PQP_DEV SRef &operator=(const SRef &o) { st.st(f, k, (real)o); return *this; }
+        PQP_DEV SRef &operator*=(real v) { st.st(f, k, st.ld(f, k) * v); return *this; }
+        PQP_DEV SRef &operator+=(real v) { st.st(f, k, st.ld(f, k) + v); return *this; }
+        PQP_DEV SRef &operator-=(real v) { st.st(f, k, st.ld(f, k) - v); return *this; }
+    };
+    struct VRef {
+        Store &st; int g, k;
+        PQP_DEV operator Vec4() const { return st.ld4(g, k); }
+        PQP_DEV VRef &operator=(const Vec4 &v) { st.st4(g, k, v); return *this; }
+    };
+    PQP_DEV SRef S(int f, int k) { return SRef{store, f, k}; }
+    PQP_DEV VRef V(int g, int k) { return VRef{store, g, k}; }
     PQP_DEV real &G(real *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
     PQP_DEV real &GL(real *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
     // row-class bitmask of stage k, kept in the pad component of the yhat group (exact small integer)
@@ -401,6 +440,15 @@ struct QpWarp {
             sync_warp(lane);
             const int FD0 = FT + 12 * cur, FE0 = FD0 + 6, FD1 = FT + 12 * (1 - cur), FE1 = FD1 + 6;
             real psum = real(0.0);
+            // neighbour lanes' boundary values: e of the left stage's outgoing rows, d of the right stage's x
+            real eLb[3], dRb[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                eLb[r] = shfl_up((real)S(FE0 + r, C - 1), 1, lane);
+                dRb[r] = shfl_down((real)S(FD0 + r, 0), 1, lane);
+                if (lane == 0) eLb[r] = real(0.0);
+                if (lane == 31) dRb[r] = real(0.0);
+            }
             PQP_ROLL
             for (int k = 0; k < C; ++k) {
                 const StagePred sp = pred(k);
@@ -412,8 +460,8 @@ struct QpWarp {
                 for (int j = 0; j < 6; ++j) { dk[j] = S(FD0 + j, k); ek[j] = S(FE0 + j, k); }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    eL[r] = (k > 0) ? S(FE0 + r, k > 0 ? k - 1 : 0) : (lane > 0 ? SL(FE0 + r, C - 1, lane > 0 ? lane - 1 : 0) : real(0.0));
-                    dR[r] = (k < C - 1) ? S(FD0 + r, k < C - 1 ? k + 1 : k) : (lane < 31 ? SL(FD0 + r, 0, lane < 31 ? lane + 1 : lane) : real(0.0));
+                    eL[r] = (k > 0) ? (real)S(FE0 + r, k > 0 ? k - 1 : 0) : eLb[r];
+                    dR[r] = (k < C - 1) ? (real)S(FD0 + r, k < C - 1 ? k + 1 : k) : dRb[r];
                 }
                 // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
                 const real hasL = sp.real ? real(1.0) : real(0.0);
@@ -468,12 +516,10 @@ struct QpWarp {
                 e[j] = S(FEc + j, k);
                 G(gscal, GD + j, k) = d;
                 G(gscal, GE + j, k) = e[j];
-                S(FS + j, k) = sigma * cinv / (d * d);
+                // dummy variables get an identity pivot (accessor calls stay warp-uniform)
+                const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
+                S(FS + j, k) = exists ? sigma * cinv / (d * d) : real(1.0);
             }
-            // dummy variables get an identity pivot
-            if (!sp.real) { S(FS + 0, k) = real(1.0); S(FS + 1, k) = real(1.0); S(FS + 2, k) = real(1.0); S(FS + 4, k) = real(1.0); }
-            if (!sp.mid) S(FS + 3, k) = real(1.0);
-            if (!sp.act1) S(FS + 5, k) = real(1.0);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 real lo, hi;
@@ -758,10 +804,13 @@ struct QpWarp {
     // b lives in shared memory (group GBV); overwritten by the solution. The factor of one
     // stage is 6 Vec4 (Dinv[6] G[9] F[9] packed contiguously).
     PQP_DEV void load_factor(int k, real (&f)[24], bool with_dinv) {
+        if (with_dinv) {
+            store.template ld4n<6>(GF0, k, f);
+        } else {
+            real t[20];
+            store.template ld4n<5>(GF0 + 1, k, t);
 #pragma unroll
-        for (int g = with_dinv ? 0 : 1; g < 6; ++g) {
-            const Vec4 v = V(GF0 + g, k);
-            f[4 * g] = v.x; f[4 * g + 1] = v.y; f[4 * g + 2] = v.z; f[4 * g + 3] = v.w;
+            for (int j = 0; j < 20; ++j) f[4 + j] = t[j];
         }
     }
     // forward sweep over the interior stages: on return bk = rhs of this lane's separator
@@ -794,7 +843,9 @@ struct QpWarp {
     PQP_DEV void solve() {
         real bk[3], acc[3];
         forward_sweep(bk, acc);
+        store.fence();  // the backward sweep re-reads the swept rhs
         solve_tail(bk, acc);
+        store.fence();  // the update reads x~ from GBV
     }
     // separators (cyclic reduction across lanes) + backward sweep; x~ ends up in GBV
     PQP_DEV void solve_tail(const real (&bk)[3], const real (&acc)[3]) {
@@ -897,15 +948,24 @@ struct QpWarp {
         real a00, a01, a10, a11, a12, ds, miu, mis0, mis1, ob[3], Ro[3], Rk, clo[2], chi[2], Rc[2], Sw[6];
     };
     PQP_DEV void load_ro(int k, StageRO &q) {
-        const Vec4 g0 = V(GA0, k), g1 = V(GA1, k), g2 = V(GB2, k), g3 = V(GR3, k), g4 = V(GC4, k),
-                     g5 = V(GR5, k), g6 = V(GS6, k);
-        q.a00 = g0.x; q.a01 = g0.y; q.a10 = g0.z; q.a11 = g0.w;
-        q.a12 = g1.x; q.ds = g1.y; q.miu = g1.z; q.mis0 = g1.w;
-        q.mis1 = g2.x; q.ob[0] = g2.y; q.ob[1] = g2.z; q.ob[2] = g2.w;
-        q.Ro[0] = g3.x; q.Ro[1] = g3.y; q.Ro[2] = g3.z; q.Rk = g3.w;
-        q.clo[0] = g4.x; q.clo[1] = g4.y; q.chi[0] = g4.z; q.chi[1] = g4.w;
-        q.Rc[0] = g5.x; q.Rc[1] = g5.y; q.Sw[0] = g5.z; q.Sw[1] = g5.w;
-        q.Sw[2] = g6.x; q.Sw[3] = g6.y; q.Sw[4] = g6.z; q.Sw[5] = g6.w;
+        real t[28];
+        store.template ld4n<7>(GA0, k, t);
+        q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
+        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
+        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
+        q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
+        q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
+        q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
+        q.Sw[2] = t[24]; q.Sw[3] = t[25]; q.Sw[4] = t[26]; q.Sw[5] = t[27];
+    }
+    // the four read-write groups of stage k (x, s/kappa-row, yhat, clearance z/yhat)
+    PQP_DEV void load_rw(int k, Vec4 &x0, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
+        real t[16];
+        store.template ld4n<4>(GX0, k, t);
+        x0.x = t[0]; x0.y = t[1]; x0.z = t[2]; x0.w = t[3];
+        x1.x = t[4]; x1.y = t[5]; x1.z = t[6]; x1.w = t[7];
+        oy.x = t[8]; oy.y = t[9]; oy.z = t[10]; oy.w = t[11];
+        cz.x = t[12]; cz.y = t[13]; cz.z = t[14]; cz.w = t[15];
     }
 
     // -------------------------------------------------------------- right-hand side
@@ -927,6 +987,7 @@ struct QpWarp {
     // subtract the left neighbour lane's last-stage rows from this lane's first stage
     PQP_DEV void fix_first_stage(const real (&wlast)[3]) {
         const StagePred sp0 = pred(0);
+        store.fence();  // GBV(0) was just written by the stage loop
         Vec4 v = V(GBV, 0);
         real wL[3];
 #pragma unroll
@@ -936,6 +997,7 @@ struct QpWarp {
         }
         v.x -= wL[0]; v.y -= wL[1]; v.z -= wL[2];
         V(GBV, 0) = v;
+        store.fence();  // the solve reads GBV next
     }
 
     // rhs from the iterates held in shared memory (before the first iteration and after a
@@ -948,7 +1010,8 @@ struct QpWarp {
             const StagePred sp = pred(k);
             StageRO q;
             load_ro(k, q);
-            const Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+            Vec4 x0, x1, oy, cz;
+            load_rw(k, x0, x1, oy, cz);
             const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
             const real oyv[3] = {oy.x, oy.y, oy.z};
             real wo[3], wk, wc[2], bk[3];
@@ -1005,7 +1068,8 @@ struct QpWarp {
         const StagePred sp = pred(k);
         StageRO q;
         load_ro(k, q);
-        Vec4 x0 = V(GX0, k), x1 = V(GX1, k), oy = V(GOY, k), cz = V(GCZ, k);
+        Vec4 x0, x1, oy, cz;
+        load_rw(k, x0, x1, oy, cz);
         const real lt = xt[0], pt = xt[1], kt = xt[2];
         const real ln = xn[0], pn = xn[1], kn = xn[2];
         // previous z of the outgoing rows
@@ -1138,17 +1202,6 @@ struct QpWarp {
         real pri, ax, z, dua, px, aty;          // unscaled inf-norms
         real spri, sax, sz, sdua, spx, saty;    // scaled (for the rho estimate)
     };
-    // y of the left stage's outgoing row r as seen from local stage k
-    PQP_DEV real left_out_y(int r, int k) {
-        if (k > 0) return S(FOR_ + r, k - 1) * S(FOY + r, k - 1);
-        if (lane == 0) return real(0.0);
-        return SL(FOR_ + r, C - 1, lane - 1) * SL(FOY + r, C - 1, lane - 1);
-    }
-    PQP_DEV real next_x(int c, int k) {
-        if (k < C - 1) return S(FX + c, k + 1);
-        if (lane == 31) return real(0.0);
-        return SL(FX + c, 0, lane + 1);
-    }
     PQP_DEV Norms residuals() {
         const DevParams &P = ka.prm;
         sync_warp(lane);
@@ -1157,6 +1210,16 @@ struct QpWarp {
         for (int j = 0; j < 12; ++j) m[j] = real(0.0);
         const real c = cscale;
         // e_r = sqrt(R_r) * sqrt(c / base_class), c d_j = sqrt(sigma c) / sqrt(S_j)
+        // boundary values of the neighbour lanes (y of the left lane's last outgoing rows, x of the
+        // right lane's first stage) travel by shuffle
+        real yLb[3], xNb[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            yLb[r] = shfl_up((real)S(FOR_ + r, C - 1) * (real)S(FOY + r, C - 1), 1, lane);
+            xNb[r] = shfl_down((real)S(FX + r, 0), 1, lane);
+            if (lane == 0) yLb[r] = real(0.0);
+            if (lane == 31) xNb[r] = real(0.0);
+        }
         const real ke_in = xsqrt(c / rho), ke_eq = xsqrt(c / (real(kRhoEqOverIneq) * rho)),
                    ke_lo = xsqrt(c / real(kRhoMin)), kd = xsqrt(sigma * c);
         PQP_ROLL
@@ -1181,7 +1244,14 @@ struct QpWarp {
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
             const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
                         s0 = S(FX + 4, k), s1 = S(FX + 5, k);
-            const real ln = next_x(0, k), pn = next_x(1, k), kn = next_x(2, k);
+            const int kn1 = k < C - 1 ? k + 1 : k;
+            const real ln = (k < C - 1) ? (real)S(FX + 0, kn1) : xNb[0];
+            const real pn = (k < C - 1) ? (real)S(FX + 1, kn1) : xNb[1];
+            const real kn = (k < C - 1) ? (real)S(FX + 2, kn1) : xNb[2];
+            const int kp1 = k > 0 ? k - 1 : 0;
+            real yl[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) yl[r] = (k > 0) ? (real)S(FOR_ + r, kp1) * (real)S(FOY + r, kp1) : yLb[r];
             real ax[6], z[6], y[6];
             ax[0] = a00 * l + a01 * ps + sp.gn * ln;
             ax[1] = a10 * l + a11 * ps + a12 * kp + sp.gn * pn;
@@ -1191,8 +1261,9 @@ struct QpWarp {
             ax[5] = sp.act1 ? (l + sp.h1 * ps + s1) : real(0.0);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                z[r] = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
-                y[r] = S(FOR_ + r, k) * S(FOY + r, k);
+                const real obr = S(FOB + r, k);
+                z[r] = (sp.last && r < 2) ? zend[r] : obr;
+                y[r] = (real)S(FOR_ + r, k) * (real)S(FOY + r, k);
             }
             z[3] = S(FKZ, k); y[3] = S(FKR, k) * S(FKY, k);
             z[4] = S(FCZ + 0, k); y[4] = S(FCR + 0, k) * S(FCY + 0, k);
@@ -1206,9 +1277,9 @@ struct QpWarp {
             }
             const real hasL = sp.real ? real(1.0) : real(0.0);
             real aty[6], px[6];
-            aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - hasL * left_out_y(0, k);
-            aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - hasL * left_out_y(1, k);
-            aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - hasL * left_out_y(2, k);
+            aty[0] = a00 * y[0] + a10 * y[1] + y[4] + y[5] - hasL * yl[0];
+            aty[1] = a01 * y[0] + a11 * y[1] + sp.h0 * y[4] + sp.h1 * y[5] - hasL * yl[1];
+            aty[2] = a12 * y[1] + sp.a22 * y[2] + y[3] - hasL * yl[2];
             aty[3] = ds * y[2];
             aty[4] = sp.act0 ? y[4] : real(0.0);
             aty[5] = sp.act1 ? y[5] : real(0.0);
@@ -1308,14 +1379,15 @@ struct QpWarp {
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const int cl = (cls >> (2 * r)) & 3;
-                if (cl <= 1) {
-                    if (r < 3) { S(FOR_ + r, k) *= ratio; S(FOY + r, k) *= rinv; }
-                    else if (r == 3) { S(FKR, k) *= ratio; S(FKY, k) *= rinv; }
-                    else { S(FCR + r - 4, k) *= ratio; S(FCY + r - 4, k) *= rinv; }
-                }
+                const real fr = cl <= 1 ? ratio : real(1.0), fi = cl <= 1 ? rinv : real(1.0);
+                if (r < 3) { S(FOR_ + r, k) *= fr; S(FOY + r, k) *= fi; }
+                else if (r == 3) { S(FKR, k) *= fr; S(FKY, k) *= fi; }
+                else { S(FCR + r - 4, k) *= fr; S(FCY + r - 4, k) *= fi; }
             }
         }
+        store.fence();
         factor_ok = refactor();
+        store.fence();
         return true;
     }
 
@@ -1344,11 +1416,15 @@ struct QpWarp {
         rho = xmin(xmax(rho, real(kRhoMin)), real(kRhoMax));
 
         assemble(src, stride);
+        store.fence();
         sync_warp(lane);
         scale_and_classify();
+        store.fence();
         sync_warp(lane);
         init_iterates(warm);
+        store.fence();
         bool fok = refactor();
+        store.fence();
         sync_warp(lane);
         build_rhs(true, warm);
 
@@ -1436,6 +1512,17 @@ struct QpWarp {
                     else xf[4 * n - 1 + 2 * p + (i - p)] = s0;
                 }
             }
+            // row values, read uniformly (the writes below are lane-divergent)
+            real zo_[3], yo_[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const real obr = S(FOB + r, k);
+                zo_[r] = (sp.last && r < 2) ? zend[r] : obr;
+                yo_[r] = (real)S(FOR_ + r, k) * (real)S(FOY + r, k);
+            }
+            const real zk_ = S(FKZ, k), yk_ = (real)S(FKR, k) * (real)S(FKY, k);
+            const real zc0_ = S(FCZ + 0, k), zc1_ = S(FCZ + 1, k);
+            const real yc0_ = (real)S(FCR + 0, k) * (real)S(FCY + 0, k), yc1_ = (real)S(FCR + 1, k) * (real)S(FCY + 1, k);
             // rows in the reference's order
             if (yf || zf) {
 #pragma unroll
@@ -1444,44 +1531,44 @@ struct QpWarp {
                     if (g <= n - 1) row = 3 * g + r;           // outgoing rows of stage g = block g
                     else if (sp.last && r < 2) row = (4 * n + p + n) + r;  // m-2, m-1
                     if (row >= 0) {
-                        const real z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
-                        if (yf) yf[row] = (double)(S(FOR_ + r, k) * S(FOY + r, k));
-                        if (zf) zf[row] = (double)z;
+                        if (yf) yf[row] = (double)yo_[r];
+                        if (zf) zf[row] = (double)zo_[r];
                     }
                 }
                 if (sp.real) {
                     const int i = g - 1;
-                    if (yf) yf[3 * n + i] = (double)(S(FKR, k) * S(FKY, k));
-                    if (zf) zf[3 * n + i] = (double)S(FKZ, k);
+                    if (yf) yf[3 * n + i] = (double)yk_;
+                    if (zf) zf[3 * n + i] = (double)zk_;
                     const int r0 = sp.act1 ? 4 * n + 2 * i : 4 * n + 2 * p + (i - p);
-                    if (yf) yf[r0] = (double)(S(FCR + 0, k) * S(FCY + 0, k));
-                    if (zf) zf[r0] = (double)S(FCZ + 0, k);
+                    if (yf) yf[r0] = (double)yc0_;
+                    if (zf) zf[r0] = (double)zc0_;
                     if (sp.act1) {
-                        if (yf) yf[r0 + 1] = (double)(S(FCR + 1, k) * S(FCY + 1, k));
-                        if (zf) zf[r0 + 1] = (double)S(FCZ + 1, k);
+                        if (yf) yf[r0 + 1] = (double)yc1_;
+                        if (zf) zf[r0 + 1] = (double)zc1_;
                     }
                 }
             }
             // warm state: scaled iterates (x/d, e z, c y / e)
+            const real x6[6] = {l, ps, kp, u, s0, s1};
 #pragma unroll
-            for (int j = 0; j < 6; ++j) G(gwarm, WX + j, k) = S(FX + j, k) / G(gscal, GD + j, k);
+            for (int j = 0; j < 6; ++j) G(gwarm, WX + j, k) = x6[j] / G(gscal, GD + j, k);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const real e = G(gscal, GE + r, k);
-                const real z = (sp.last && r < 2) ? zend[r] : S(FOB + r, k);
-                G(gwarm, WOZ + r, k) = e * z;
-                G(gwarm, WOY + r, k) = c * S(FOR_ + r, k) * S(FOY + r, k) / e;
+                G(gwarm, WOZ + r, k) = e * zo_[r];
+                G(gwarm, WOY + r, k) = c * yo_[r] / e;
             }
             {
                 const real e = G(gscal, GE + 3, k);
-                G(gwarm, WKZ, k) = e * S(FKZ, k);
-                G(gwarm, WKY, k) = c * S(FKR, k) * S(FKY, k) / e;
+                G(gwarm, WKZ, k) = e * zk_;
+                G(gwarm, WKY, k) = c * yk_ / e;
             }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const real e = G(gscal, GE + 4 + j, k);
-                G(gwarm, WCZ + j, k) = e * S(FCZ + j, k);
-                G(gwarm, WCY + j, k) = c * S(FCR + j, k) * S(FCY + j, k) / e;
+            {
+                const real e0 = G(gscal, GE + 4, k), e1 = G(gscal, GE + 5, k);
+                G(gwarm, WCZ + 0, k) = e0 * zc0_;
+                G(gwarm, WCY + 0, k) = c * yc0_ / e0;
+                G(gwarm, WCZ + 1, k) = e1 * zc1_;
+                G(gwarm, WCY + 1, k) = c * yc1_ / e1;
             }
         }
         cost = warp_sum(cost, lane);

@@ -20,7 +20,7 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PQP_LIB_PATH", os.path.join(_PKG, "libpqp_b200.so"))  # override: A/B builds
 _CSRC = os.path.join(_PKG, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "607",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "607,177",
               "--shared", "-Xcompiler", "-fPIC"]
 _lib = None
 

@@ -26,7 +26,7 @@ void run_one(const pqp::KernelArgs &ka, int qp, real *smem) {
     const double *src = ka.knots + (size_t)qp * 9 * ka.n_max;
     const int stride = ka.n_max;
     warp.run([&](int lane) {
-        pqp::QpWarp<C, real> w(ka, smem, lane, qp);
+        pqp::QpWarp<C, real> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
         w.run(src, stride);
     });
     warp_emu::current() = nullptr;
