@@ -312,6 +312,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--option-bits", type=int, default=0,
+                    help="pqp_params.reserved: 1 FP32 factorisation, 2 FP64 iterates, 4 no FP64 escalation, "
+                         "8 state in tensor memory")
     ap.add_argument("--workload", default="cold", choices=["cold", "receding"],
                     help="cold: BASELINE configs[2]/[3] (default); receding: configs[4], warm re-solves with a "
                          "50-iteration cap on a window that advances one knot per step")
@@ -344,7 +347,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    params = abi.default_params()
+    params = abi.default_params(reserved=args.option_bits)
     B, n = args.batch, args.n
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
     hb = synthetic.make_batch(CFG_ID, B, n, first=rank * B)

@@ -181,25 +181,72 @@ struct TmemStore {
     __device__ void fence() { tmem_wait_st(); }
 };
 
-// One CTA = four warps = four QP instances, state in tensor memory (FP32 only).
-template <int C>
-__global__ void __launch_bounds__(128) pqp_admm_kernel_tmem(const __grid_constant__ pqp::KernelArgs ka) {
+// Hybrid persistent kernel (FP32): one CTA per SM, 4 + WS warps, every warp solves one QP at a
+// time and takes the next unsolved instance from a global work counter. Warps 0-3 keep their
+// QP's state in tensor memory (one warp per TMEM sub-partition), warps 4.. keep it in shared
+// memory (with the TMA bulk-copy input staging of the plain kernel) — so both on-chip memories
+// hold QPs: 4 + 2 per SM at n = 240 instead of 3.
+template <int C, int WS>
+__global__ void __launch_bounds__(32 * (4 + WS), 1) pqp_admm_kernel_hybrid(const __grid_constant__ pqp::KernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t tbase_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t need = TmemStore<C>::kGroups * 4 * C;
     constexpr uint32_t ncols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    constexpr size_t kSpillFloats = (size_t)(TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 0) * C * 32 * 4;
+    constexpr size_t kSmemWarpFloats = (size_t)pqp::NFIELD * C * 32 + 4;  // + mbarrier (16 B)
     if (warp == 0) tmem_alloc(&tbase_s, ncols);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tb = tbase_s + ((uint32_t)(32 * warp) << 16);
-    float *spill = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 1) * C * 32 * 4;
-    const int qp = blockIdx.x * 4 + warp;
-    if (qp < ka.batch) {
-        const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
-        pqp::QpWarp<C, float, TmemStore<C> > w(ka, TmemStore<C>(tb, spill, lane), lane, qp);
-        w.run(src, ka.n_max);
+    float *base = reinterpret_cast<float *>(smem_raw);
+    if (warp < 4) {
+        const uint32_t tb = tbase_s + ((uint32_t)(32 * warp) << 16);
+        float *spill = base + (size_t)warp * kSpillFloats;
+        for (;;) {
+            int qp = 0;
+            if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
+            qp = __shfl_sync(0xffffffffu, qp, 0);
+            if (qp >= ka.batch) break;
+            const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+            pqp::QpWarp<C, float, TmemStore<C> > w(ka, TmemStore<C>(tb, spill, lane), lane, qp);
+            w.run(src, ka.n_max);
+        }
+    } else {
+        float *smem = base + 4 * kSpillFloats + (size_t)(warp - 4) * kSmemWarpFloats;
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pqp::NFIELD * C * 32);
+        double *stage = reinterpret_cast<double *>(smem + pqp::FDI * C * 32);
+        const uint32_t bytes = (uint32_t)(PQP_NFIELDS * ka.n_max * sizeof(double));
+        uint32_t parity = 0;
+        if (ka.use_tma) {
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+        }
+        for (;;) {
+            int qp = 0;
+            if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
+            qp = __shfl_sync(0xffffffffu, qp, 0);
+            if (qp >= ka.batch) break;
+            const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+            if (ka.use_tma) {
+                // the staging buffer was last touched through the generic proxy (previous QP)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_1d(stage, src, bytes, bar);
+                }
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                src = stage;
+            }
+            pqp::QpWarp<C, float> w(ka, pqp::SmemStore<C, float>(smem, lane), lane, qp);
+            w.run(src, ka.n_max);
+            __syncwarp();
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -258,6 +305,9 @@ struct pqp_handle {
     double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
     int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
     void *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    static const int kCounters = 64;
+    int *d_counters = nullptr;
+    unsigned counter_next = 0;
     bool use_tmem = false;         // params.reserved bit 3: state in tensor memory (FP32 kernel)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
@@ -327,30 +377,46 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
     }
 }
 
-// tensor-memory variant: 4 QPs per CTA; the dynamic shared-memory request is padded so that only
-// one CTA (which owns all 512 TMEM columns) is resident per SM
-constexpr size_t kTmemSmem = 120 * 1024;
+// hybrid persistent variant: one CTA per SM (it owns the SM's tensor memory); shared-memory
+// warps per CTA by chunk size (register file: (4 + WS) x 32 x 255 <= 64 K)
+template <int C> struct HybridCfg { static constexpr int WS = C >= 8 ? 2 : 4; };
 template <int C>
-cudaError_t launch_tmem(const pqp::KernelArgs &ka, cudaStream_t s) {
-    pqp_admm_kernel_tmem<C><<<(ka.batch + 3) / 4, 128, kTmemSmem, s>>>(ka);
+size_t hybrid_smem_bytes() {
+    const size_t spill = (size_t)(TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 0) * C * 32 * 16;
+    size_t bytes = 4 * spill + (size_t)HybridCfg<C>::WS * ((size_t)pqp::NFIELD * C * 32 * 4 + 16);
+    if (bytes < 116 * 1024) bytes = 116 * 1024;  // keep it at one CTA per SM
+    return bytes;
+}
+template <int C>
+cudaError_t launch_hybrid(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
+    constexpr int W = 4 + HybridCfg<C>::WS;
+    int ctas = (ka.batch + W - 1) / W;
+    if (ctas > sm_count) ctas = sm_count;
+    pqp_admm_kernel_hybrid<C, HybridCfg<C>::WS><<<ctas, 32 * W, hybrid_smem_bytes<C>(), s>>>(ka);
     return cudaGetLastError();
 }
-cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s) {
+cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
     switch (chunk) {
-        case 1: return launch_tmem<1>(ka, s);
-        case 2: return launch_tmem<2>(ka, s);
-        case 4: return launch_tmem<4>(ka, s);
-        default: return launch_tmem<8>(ka, s);
+        case 1: return launch_hybrid<1>(ka, s, sm_count);
+        case 2: return launch_hybrid<2>(ka, s, sm_count);
+        case 4: return launch_hybrid<4>(ka, s, sm_count);
+        default: return launch_hybrid<8>(ka, s, sm_count);
     }
+}
+template <int C>
+cudaError_t prepare_hybrid() {
+    return cudaFuncSetAttribute(pqp_admm_kernel_hybrid<C, HybridCfg<C>::WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)hybrid_smem_bytes<C>());
 }
 cudaError_t prepare_tmem_chunk(int chunk) {
     switch (chunk) {
-        case 1: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
-        case 2: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
-        case 4: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
-        default: return cudaFuncSetAttribute(pqp_admm_kernel_tmem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+        case 1: return prepare_hybrid<1>();
+        case 2: return prepare_hybrid<2>();
+        case 4: return prepare_hybrid<4>();
+        default: return prepare_hybrid<8>();
     }
 }
+int hybrid_warps(int chunk) { return chunk >= 8 ? 6 : 8; }
 
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
     if (!h) return PQP_E_INVALID;
@@ -385,6 +451,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     ka.z_full = out->z_full;
     ka.info = out->info;
     ka.flags = flags;
+    ka.work_counter = nullptr;
     ka.warm = esc ? h->e_warm : h->d_warm;
     ka.scal = esc ? h->e_scal : h->d_scal;
     ka.dy = esc ? h->e_dy : h->d_dy;
@@ -398,8 +465,11 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         }
         PQP_CUDA(h, launch_chunk<double>(h->chunk, ka, h->smem_bytes64, s));
     } else if (h->use_tmem) {
-        ka.use_tma = 0;
-        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s));
+        // one work counter per concurrently running launch (pipeline chunk); counters rotate
+        int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
+        PQP_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), s));
+        ka.work_counter = ctr;
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count));
     } else {
         PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
     }
@@ -649,7 +719,10 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
     h->use_tmem = (params->reserved & 8) != 0 && !h->fp64;
-    if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
+    if (h->use_tmem) {
+        PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
+        h->warps_per_sm = hybrid_warps(h->chunk);
+    }
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
     if (h->fp64) {
@@ -682,6 +755,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, B * pqp::dy_floats(c) * esz));
     PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
     PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
+    PQP_CREATE_CUDA(dmalloc(&h->d_counters, (size_t)pqp_handle::kCounters));
     PQP_CREATE_CUDA(dmalloc(&h->d_flags, B));
     PQP_CREATE_CUDA(cudaMemset(h->d_flags, 0, B * sizeof(int)));
     PQP_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_status), B * sizeof(int)));
@@ -702,6 +776,7 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_ref); cudaFree(h->d_xy); cudaFree(h->d_sol2); cudaFree(h->d_n2);
     cudaFree(h->d_warm); cudaFree(h->d_scal); cudaFree(h->d_dy); cudaFree(h->d_rho);
     cudaFree(h->d_flags);
+    cudaFree(h->d_counters);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->e_knots); cudaFree(h->e_inst); cudaFree(h->e_sol); cudaFree(h->e_cost); cudaFree(h->e_info);

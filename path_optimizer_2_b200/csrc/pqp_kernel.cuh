@@ -113,6 +113,7 @@ struct KernelArgs {
     const int *n, *p;
     double *sol, *cost;
     int *status, *iters;
+    int *work_counter;  // persistent kernels: next instance to take (zeroed before the launch)
     int *flags;  // optional: bit 0 = infeasibility suspected (certificate conditions 1-2 held)
     double *x_full, *y_full, *z_full, *info;
     void *warm, *scal, *dy, *rho_state;  // per-instance scratch in the kernel's scalar type

@@ -54,6 +54,7 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     ka.status = out->status;
     ka.iters = out->iters;
     ka.flags = nullptr;
+    ka.work_counter = nullptr;
     ka.x_full = out->x_full;
     ka.y_full = out->y_full;
     ka.z_full = out->z_full;
