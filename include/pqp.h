@@ -112,9 +112,11 @@ typedef struct pqp_params {
     int32_t scaling;                /* 10 Ruiz passes */
     int32_t adaptive_rho;           /* 1     */
     int32_t adaptive_rho_interval;  /* 25: fixed; OSQP's default 0 = wall-clock rule, not reproducible */
-    int32_t reserved;               /* option bits, default 0: 1 = factorise in FP32 (default FP64),
+    int32_t reserved;               /* option bits, default 0: 1 = (unused),
                                        2 = iterate in FP64 (whole kernel in double precision),
-                                       4 = do not re-solve suspected-infeasible instances in FP64 */
+                                       4 = do not re-solve suspected-infeasible instances in FP64,
+                                       8 = FP32 state in tensor memory (persistent 4-warp CTAs),
+                                       bits 4-6 = extra shared-memory warps next to them (experimental) */
 } pqp_params;
 
 /* Batch input. All pointers are HOST pointers for pqp_solve/pqp_resolve and DEVICE

@@ -308,6 +308,7 @@ struct pqp_handle {
     static const int kCounters = 64;
     int *d_counters = nullptr;
     unsigned counter_next = 0;
+    int hybrid_ws = 0;             // shared-memory-backed warps next to the 4 tensor-memory warps
     bool use_tmem = false;         // params.reserved bit 3: state in tensor memory (FP32 kernel)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
@@ -377,46 +378,57 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
     }
 }
 
-// hybrid persistent variant: one CTA per SM (it owns the SM's tensor memory); shared-memory
-// warps per CTA by chunk size (register file: (4 + WS) x 32 x 255 <= 64 K)
-template <int C> struct HybridCfg { static constexpr int WS = C >= 8 ? 2 : 4; };
-template <int C>
+// hybrid persistent variant: one CTA per SM (it owns the SM's tensor memory) with WS additional
+// shared-memory-backed warps (register file: (4 + WS) x 32 x 255 <= 64 K)
+template <int C, int WS>
 size_t hybrid_smem_bytes() {
     const size_t spill = (size_t)(TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 0) * C * 32 * 16;
-    size_t bytes = 4 * spill + (size_t)HybridCfg<C>::WS * ((size_t)pqp::NFIELD * C * 32 * 4 + 16);
+    size_t bytes = 4 * spill + (size_t)WS * ((size_t)pqp::NFIELD * C * 32 * 4 + 16);
     if (bytes < 116 * 1024) bytes = 116 * 1024;  // keep it at one CTA per SM
     return bytes;
 }
-template <int C>
+template <int C, int WS>
 cudaError_t launch_hybrid(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
-    constexpr int W = 4 + HybridCfg<C>::WS;
+    constexpr int W = 4 + WS;
     int ctas = (ka.batch + W - 1) / W;
     if (ctas > sm_count) ctas = sm_count;
-    pqp_admm_kernel_hybrid<C, HybridCfg<C>::WS><<<ctas, 32 * W, hybrid_smem_bytes<C>(), s>>>(ka);
+    pqp_admm_kernel_hybrid<C, WS><<<ctas, 32 * W, hybrid_smem_bytes<C, WS>(), s>>>(ka);
     return cudaGetLastError();
 }
-cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
-    switch (chunk) {
-        case 1: return launch_hybrid<1>(ka, s, sm_count);
-        case 2: return launch_hybrid<2>(ka, s, sm_count);
-        case 4: return launch_hybrid<4>(ka, s, sm_count);
-        default: return launch_hybrid<8>(ka, s, sm_count);
-    }
-}
-template <int C>
+template <int C, int WS>
 cudaError_t prepare_hybrid() {
-    return cudaFuncSetAttribute(pqp_admm_kernel_hybrid<C, HybridCfg<C>::WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hybrid_smem_bytes<C>());
+    return cudaFuncSetAttribute(pqp_admm_kernel_hybrid<C, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)hybrid_smem_bytes<C, WS>());
 }
-cudaError_t prepare_tmem_chunk(int chunk) {
-    switch (chunk) {
-        case 1: return prepare_hybrid<1>();
-        case 2: return prepare_hybrid<2>();
-        case 4: return prepare_hybrid<4>();
-        default: return prepare_hybrid<8>();
+// (chunk, ws) dispatch; ws is clamped to what fits in shared memory for that chunk size
+int hybrid_ws_max(int chunk) { return chunk >= 8 ? 2 : 4; }
+#define PQP_HYB_CASE(C, WS, EXPR) case (C * 8 + WS): return EXPR<C, WS>
+cudaError_t launch_tmem_chunk(int chunk, int ws, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
+    switch (chunk * 8 + ws) {
+        case 8 * 8 + 0: return launch_hybrid<8, 0>(ka, s, sm_count);
+        case 8 * 8 + 1: return launch_hybrid<8, 1>(ka, s, sm_count);
+        case 8 * 8 + 2: return launch_hybrid<8, 2>(ka, s, sm_count);
+        case 4 * 8 + 0: return launch_hybrid<4, 0>(ka, s, sm_count);
+        case 4 * 8 + 2: return launch_hybrid<4, 2>(ka, s, sm_count);
+        case 4 * 8 + 4: return launch_hybrid<4, 4>(ka, s, sm_count);
+        case 2 * 8 + 0: return launch_hybrid<2, 0>(ka, s, sm_count);
+        case 1 * 8 + 0: return launch_hybrid<1, 0>(ka, s, sm_count);
+        default: return cudaErrorInvalidValue;
     }
 }
-int hybrid_warps(int chunk) { return chunk >= 8 ? 6 : 8; }
+cudaError_t prepare_tmem_chunk(int chunk, int ws) {
+    switch (chunk * 8 + ws) {
+        case 8 * 8 + 0: return prepare_hybrid<8, 0>();
+        case 8 * 8 + 1: return prepare_hybrid<8, 1>();
+        case 8 * 8 + 2: return prepare_hybrid<8, 2>();
+        case 4 * 8 + 0: return prepare_hybrid<4, 0>();
+        case 4 * 8 + 2: return prepare_hybrid<4, 2>();
+        case 4 * 8 + 4: return prepare_hybrid<4, 4>();
+        case 2 * 8 + 0: return prepare_hybrid<2, 0>();
+        case 1 * 8 + 0: return prepare_hybrid<1, 0>();
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
     if (!h) return PQP_E_INVALID;
@@ -469,7 +481,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
         PQP_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), s));
         ka.work_counter = ctr;
-        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count));
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, h->hybrid_ws, ka, s, h->sm_count));
     } else {
         PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
     }
@@ -720,8 +732,13 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->escalate = (params->reserved & 4) == 0;
     h->use_tmem = (params->reserved & 8) != 0 && !h->fp64;
     if (h->use_tmem) {
-        PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
-        h->warps_per_sm = hybrid_warps(h->chunk);
+        // bits 4-6 of reserved: number of extra shared-memory warps (experiments); default 0
+        int ws = (params->reserved >> 4) & 7;
+        if (h->chunk <= 2) ws = 0;
+        if (h->chunk == 4 && ws != 0 && ws != 2 && ws != 4) ws = 0;
+        if (ws > hybrid_ws_max(h->chunk)) ws = hybrid_ws_max(h->chunk);
+        h->hybrid_ws = ws;
+        PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk, ws));
     }
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
@@ -731,7 +748,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     } else {
         PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps));
     }
-    h->warps_per_sm = bps;
+    h->warps_per_sm = h->use_tmem ? 4 + h->hybrid_ws : bps;
     for (int i = 0; i < pqp_handle::kStreams; ++i) {
         PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
         PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[i], cudaEventDisableTiming));

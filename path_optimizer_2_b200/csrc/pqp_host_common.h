@@ -46,24 +46,24 @@ inline DevParams make_dev_params(const pqp_params &p) {
     d.safety_margin = p.expected_safety_margin;
     d.end_l_lb = p.end_l_lb;
     d.end_l_ub = p.end_l_ub;
-    d.w_l = (float)p.weight_l;
-    d.w_kappa = (float)p.weight_kappa;
-    d.w_dkappa = (float)p.weight_dkappa;
-    d.w_slack = (float)p.weight_slack;
-    d.rho0 = (float)p.rho;
-    d.sigma = (float)p.sigma;
-    d.alpha = (float)p.alpha;
-    d.eps_abs = (float)p.eps_abs;
-    d.eps_rel = (float)p.eps_rel;
-    d.eps_pinf = (float)p.eps_prim_inf;
-    d.eps_dinf = (float)p.eps_dual_inf;
-    d.rho_tol = (float)p.adaptive_rho_tolerance;
+    d.w_l = p.weight_l;
+    d.w_kappa = p.weight_kappa;
+    d.w_dkappa = p.weight_dkappa;
+    d.w_slack = p.weight_slack;
+    d.rho0 = p.rho;
+    d.sigma = p.sigma;
+    d.alpha = p.alpha;
+    d.eps_abs = p.eps_abs;
+    d.eps_rel = p.eps_rel;
+    d.eps_pinf = p.eps_prim_inf;
+    d.eps_dinf = p.eps_dual_inf;
+    d.rho_tol = p.adaptive_rho_tolerance;
     d.max_iter = p.max_iter;
     d.check_every = p.check_termination;
     d.scaling = p.scaling;
     d.adaptive_rho = p.adaptive_rho;
     d.adaptive_interval = p.adaptive_rho_interval;
-    d.factor_fp64 = (p.reserved & 1) ? 0 : 1;  // reserved bit 0: factor in fp32 (experiments)
+    d.reserved0 = 0;
     return d;
 }
 

@@ -102,7 +102,7 @@ struct DevParams {
     double w_l, w_kappa, w_dkappa, w_slack;
     double rho0, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, rho_tol;
     int max_iter, check_every, scaling, adaptive_rho, adaptive_interval;
-    int factor_fp64;
+    int reserved0;
 };
 
 struct KernelArgs {
@@ -1306,15 +1306,19 @@ struct QpWarp {
         return nr;
     }
 
-    // OSQP is_primal_infeasible; |dy| and the bound term were accumulated by admm_update<true>
-    PQP_DEV bool primal_infeasible(real eps) {
-        const real c = cscale;
-        const real nrm = warp_max(cert_nrm, lane);
-        const real lhs = warp_sum(cert_lhs, lane);
-        suspect = 0;
-        if (!(c * nrm > eps)) return false;
-        if (!(lhs < -eps * nrm)) return false;
-        suspect = 1;
+    // OSQP is_primal_infeasible, evaluated once per check: |dy|_inf and the bound term were
+    // accumulated by admm_update<true>; |A'dy|_inf is only computed when the first two
+    // conditions hold at the normal tolerance. The caller applies the normal and, on the last
+    // iteration, the 10x tolerance to the returned raw terms.
+    struct Cert { real nrm, lhs, aty; };
+    PQP_DEV Cert primal_infeasibility_terms(real eps) {
+        Cert ct;
+        ct.nrm = warp_max(cert_nrm, lane);
+        ct.lhs = warp_sum(cert_lhs, lane);
+        ct.aty = real(kOsqpInfty);
+        // conditions 1-2 at the normal tolerance (they are only harder at 10x)
+        suspect = ((cscale * ct.nrm > eps) && (ct.lhs < -eps * ct.nrm)) ? 1 : 0;
+        if (!suspect) return ct;
         sync_warp(lane);
         real mx = real(0.0);
         PQP_ROLL
@@ -1341,31 +1345,38 @@ struct QpWarp {
 #pragma unroll
             for (int j = 0; j < 6; ++j) mx = xmax(mx, xabs(aty[j]));
         }
-        mx = warp_max(mx, lane);
-        return mx < eps * nrm;
+        ct.aty = warp_max(mx, lane);
+        return ct;
+    }
+    PQP_DEV bool cert_holds(const Cert &ct, real eps) const {
+        return (cscale * ct.nrm > eps) && (ct.lhs < -eps * ct.nrm) && (ct.aty < eps * ct.nrm);
     }
 
-    // OSQP check_termination; returns status or kUnsolved
-    PQP_DEV int check_termination(const Norms &nr, bool approx) {
-        const DevParams &P = ka.prm;
-        real ea = eps_abs, er = eps_rel, epi = eps_pinf;
+    // OSQP check_termination (and, when `last`, the 10x "approximate" re-check that osqp_solve
+    // performs after the final iteration). Returns a status or kUnsolved.
+    PQP_DEV int check_termination(const Norms &nr, bool last) {
         if (!(nr.pri <= real(kOsqpInfty)) || !(nr.dua <= real(kOsqpInfty))) return kNumerical;
-        if (approx) { ea *= real(10.0); er *= real(10.0); epi *= real(10.0); }
-        const real eps_prim = ea + er * xmax(nr.ax, nr.z);
-        const real eps_dual = ea + er * xmax(nr.px, nr.aty);
-        const bool pok = nr.pri < eps_prim, dok = nr.dua < eps_dual;
-        bool pinf = false;
-        if (!pok) pinf = primal_infeasible(epi);
+        const real mp = xmax(nr.ax, nr.z), md = xmax(nr.px, nr.aty);
+        const bool pok = nr.pri < eps_abs + eps_rel * mp, dok = nr.dua < eps_abs + eps_rel * md;
+        if (pok && dok) return kSolved;
         // dual infeasibility needs q' dx < 0; q = 0 on this path, so it can never trigger
-        if (pok && dok) return approx ? kSolvedInacc : kSolved;
-        if (pinf) return approx ? kPrimInfInacc : kPrimInf;
-        return kUnsolved;
+        Cert ct;
+        ct.nrm = ct.lhs = real(0.0);
+        ct.aty = real(kOsqpInfty);
+        const bool pok10 = nr.pri < real(10.0) * (eps_abs + eps_rel * mp);
+        if (!pok) ct = primal_infeasibility_terms(eps_pinf);
+        if (!pok && cert_holds(ct, eps_pinf)) return kPrimInf;
+        if (!last) return kUnsolved;
+        const bool dok10 = nr.dua < real(10.0) * (eps_abs + eps_rel * md);
+        if (pok10 && dok10) return kSolvedInacc;
+        if (!pok10 && cert_holds(ct, real(10.0) * eps_pinf)) return kPrimInfInacc;
+        return kMaxIter;
     }
 
-    PQP_DEV bool refactor() { return (sizeof(real) == 8 || ka.prm.factor_fp64) ? factor<double>() : factor<real>(); }
 
-    // OSQP compute_rho_estimate + update; returns true if rho changed (and refactors)
-    PQP_DEV bool adapt_rho(const Norms &nr, bool &factor_ok) {
+    // OSQP compute_rho_estimate + update of the weights; returns true if rho changed (the caller
+    // refactors and rebuilds the rhs)
+    PQP_DEV bool adapt_rho(const Norms &nr) {
         const DevParams &P = ka.prm;
         const real pri = nr.spri / (xmax(nr.sz, nr.sax) + real(1e-10));
         const real dua = nr.sdua / (xmax(nr.saty, nr.spx) + real(1e-10));
@@ -1386,9 +1397,6 @@ struct QpWarp {
                 else { S(FCR + r - 4, k) *= fr; S(FCY + r - 4, k) *= fi; }
             }
         }
-        store.fence();
-        factor_ok = refactor();
-        store.fence();
         return true;
     }
 
@@ -1423,58 +1431,48 @@ struct QpWarp {
         store.fence();
         sync_warp(lane);
         init_iterates(warm);
-        store.fence();
-        bool fok = refactor();
-        store.fence();
-        sync_warp(lane);
-        build_rhs(true, warm);
 
-        int status = fok ? kUnsolved : kNumerical;
+        int status = kUnsolved;
         int iter = 0, rho_updates = 0;
         Norms nr;
         nr.pri = nr.dua = real(0.0);
-        bool checked = false;
-        if (fok) {
-            PQP_ROLL
-            int to_check = P.check_every > 0 ? P.check_every : -1;
-            int to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
-            for (iter = 1; iter <= P.max_iter; ++iter) {
-                solve();
-                // iter % interval == 0 without an integer division in the loop
-                const bool can_check = (--to_check == 0);
-                const bool can_adapt = (--to_adapt == 0);
-                if (can_check) to_check = P.check_every;
-                if (can_adapt) to_adapt = P.adaptive_interval;
-                if (can_check) admm_update<true>(iter == 1, warm);
-                else admm_update<false>(iter == 1, warm);
-                checked = false;
-                if (can_check || can_adapt) {
-                    nr = residuals();
-                    if (can_check) {
-                        checked = true;
-                        status = check_termination(nr, false);
-                        if (status != kUnsolved) break;
-                    }
-                    if (can_adapt) {
-                        bool ok2 = true;
-                        if (adapt_rho(nr, ok2)) {
-                            ++rho_updates;
-                            if (!ok2) { status = kNumerical; break; }
-                            sync_warp(lane);
-                            build_rhs(false, warm);
-                        }
-                    }
-                }
+        int to_check = P.check_every > 0 ? P.check_every : -1;
+        int to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
+        bool need_factor = true, initial = true;
+        // Heavy, rarely executed pieces (factorisation, rhs rebuild, residuals, termination) have
+        // exactly one call site each: instruction-cache footprint matters once the resident
+        // warps of an SM drift out of phase (profiles/r1/README.md).
+        PQP_ROLL
+        for (;;) {
+            if (need_factor) {
+                store.fence();
+                const bool fok = factor<double>();  // FP64 factorisation, FP32 factors
+                store.fence();
+                sync_warp(lane);
+                if (!fok) { status = kNumerical; break; }
+                build_rhs(initial, warm);
+                need_factor = false;
+                initial = false;
             }
-            if (iter > P.max_iter) iter = P.max_iter;
-            if (status == kUnsolved) {
-                if (!checked) {
-                    nr = residuals();
-                    status = check_termination(nr, false);
+            ++iter;
+            solve();
+            // iter % interval == 0 without an integer division in the loop
+            const bool last = iter >= P.max_iter;
+            const bool can_check = (--to_check == 0) || last;
+            const bool can_adapt = (--to_adapt == 0) && !last;
+            if (to_check <= 0) to_check = P.check_every > 0 ? P.check_every : -1;
+            if (to_adapt <= 0) to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
+            if (can_check) admm_update<true>(iter == 1, warm);
+            else admm_update<false>(iter == 1, warm);
+            if (can_check || can_adapt) {
+                nr = residuals();
+                if (can_check) {
+                    status = check_termination(nr, last);
+                    if (status != kUnsolved) break;
                 }
-                if (status == kUnsolved) {
-                    status = check_termination(nr, true);
-                    if (status == kUnsolved) status = kMaxIter;
+                if (can_adapt && adapt_rho(nr)) {
+                    ++rho_updates;
+                    need_factor = true;
                 }
             }
         }

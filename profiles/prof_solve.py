@@ -11,9 +11,10 @@ ap.add_argument("--batch", type=int, default=444)
 ap.add_argument("--n", type=int, default=240)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--warm", action="store_true")
+ap.add_argument("--option-bits", type=int, default=0)
 a = ap.parse_args()
 hb = synthetic.make_batch(3, a.batch, a.n)
-sv = solver.PathQpSolver(abi.default_params(), n_max=a.n, batch_max=a.batch)
+sv = solver.PathQpSolver(abi.default_params(reserved=a.option_bits), n_max=a.n, batch_max=a.batch)
 for _ in range(a.reps):
     res = sv.solve(hb)
     if a.warm:

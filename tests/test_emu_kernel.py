@@ -54,12 +54,6 @@ def test_emulated_iteration_cap():
     _check(hb, params, "emu cap", warm=False)
 
 
-def test_emulated_fp32_factor_also_converges():
-    params = abi.default_params(reserved=1)  # bit 0: factorise in FP32 instead of FP64
-    hb = synthetic.make_batch(3, 3, 120)
-    _check(hb, params, "emu f32 factor", warm=False)
-
-
 def test_emulated_fp64_instantiation_reproduces_oracle_iterates():
     """The kernel source instantiated in double (params.reserved bit 1): same algorithm and
     schedule as the oracle -> same iteration counts, rho, statuses (incl. PRIMAL_INFEASIBLE)
