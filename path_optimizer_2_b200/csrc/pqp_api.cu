@@ -181,6 +181,29 @@ struct TmemStore {
     __device__ void fence() { tmem_wait_st(); }
 };
 
+
+// Run-time choice between the two backends (warp-uniform flag): the hybrid kernel's tensor-memory
+// warps and shared-memory warps execute ONE instantiation of the solver, so they share its
+// instructions in the instruction cache (two instantiations side by side were measured to spend
+// 59 % of their stall samples on instruction fetch: profiles/r1/README.md).
+template <int C>
+struct HybridStore {
+    typedef float4 Vec4;
+    TmemStore<C> t;
+    pqp::SmemStore<C, float> m;
+    bool tm;
+    __device__ HybridStore(const TmemStore<C> &ts, const pqp::SmemStore<C, float> &ms, bool use_t) : t(ts), m(ms), tm(use_t) {}
+    __device__ float ld(int f, int k) const { return tm ? t.ld(f, k) : m.ld(f, k); }
+    __device__ void st(int f, int k, float v) { if (tm) t.st(f, k, v); else m.st(f, k, v); }
+    __device__ float4 ld4(int g, int k) const { return tm ? t.ld4(g, k) : m.ld4(g, k); }
+    __device__ void st4(int g, int k, const float4 &v) { if (tm) t.st4(g, k, v); else m.st4(g, k, v); }
+    template <int N> __device__ void ld4n(int g0, int k, float (&out)[4 * N]) const {
+        if (tm) t.template ld4n<N>(g0, k, out);
+        else m.template ld4n<N>(g0, k, out);
+    }
+    __device__ void fence() { if (tm) t.fence(); }
+};
+
 // Hybrid persistent kernel (FP32): one CTA per SM, 4 + WS warps, every warp solves one QP at a
 // time and takes the next unsolved instance from a global work counter. Warps 0-3 keep their
 // QP's state in tensor memory (one warp per TMEM sub-partition), warps 4.. keep it in shared
@@ -200,53 +223,46 @@ __global__ void __launch_bounds__(32 * (4 + WS), 1) pqp_admm_kernel_hybrid(const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float *base = reinterpret_cast<float *>(smem_raw);
-    if (warp < 4) {
-        const uint32_t tb = tbase_s + ((uint32_t)(32 * warp) << 16);
-        float *spill = base + (size_t)warp * kSpillFloats;
-        for (;;) {
-            int qp = 0;
-            if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
-            qp = __shfl_sync(0xffffffffu, qp, 0);
-            if (qp >= ka.batch) break;
-            const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
-            pqp::QpWarp<C, float, TmemStore<C> > w(ka, TmemStore<C>(tb, spill, lane), lane, qp);
-            w.run(src, ka.n_max);
+    const bool tm = warp < 4;
+    const uint32_t tb = tbase_s + ((uint32_t)(32 * (warp & 3)) << 16);
+    float *spill = base + (size_t)(warp & 3) * kSpillFloats;
+    float *smem = base + 4 * kSpillFloats + (size_t)(tm ? 0 : warp - 4) * kSmemWarpFloats;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pqp::NFIELD * C * 32);
+    double *stage = reinterpret_cast<double *>(smem + pqp::FDI * C * 32);
+    const uint32_t bytes = (uint32_t)(PQP_NFIELDS * ka.n_max * sizeof(double));
+    const bool use_tma = !tm && ka.use_tma;
+    uint32_t parity = 0;
+    if (use_tma) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    } else {
-        float *smem = base + 4 * kSpillFloats + (size_t)(warp - 4) * kSmemWarpFloats;
-        uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pqp::NFIELD * C * 32);
-        double *stage = reinterpret_cast<double *>(smem + pqp::FDI * C * 32);
-        const uint32_t bytes = (uint32_t)(PQP_NFIELDS * ka.n_max * sizeof(double));
-        uint32_t parity = 0;
-        if (ka.use_tma) {
+        __syncwarp();
+    }
+    // persistent warps: each takes the next unsolved instance until the batch is exhausted
+    // (iteration counts vary 3x between instances; a static assignment would idle)
+    for (;;) {
+        int qp = 0;
+        if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
+        qp = __shfl_sync(0xffffffffu, qp, 0);
+        if (qp >= ka.batch) break;
+        const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+        if (use_tma) {
+            // the staging buffer was last touched through the generic proxy (previous QP)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
             if (lane == 0) {
-                mbar_init(bar, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(stage, src, bytes, bar);
             }
-            __syncwarp();
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            src = stage;
         }
-        for (;;) {
-            int qp = 0;
-            if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
-            qp = __shfl_sync(0xffffffffu, qp, 0);
-            if (qp >= ka.batch) break;
-            const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
-            if (ka.use_tma) {
-                // the staging buffer was last touched through the generic proxy (previous QP)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_expect_tx(bar, bytes);
-                    tma_load_1d(stage, src, bytes, bar);
-                }
-                mbar_wait(bar, parity);
-                parity ^= 1u;
-                src = stage;
-            }
-            pqp::QpWarp<C, float> w(ka, pqp::SmemStore<C, float>(smem, lane), lane, qp);
-            w.run(src, ka.n_max);
-            __syncwarp();
-        }
+        pqp::QpWarp<C, float, HybridStore<C> > w(
+            ka, HybridStore<C>(TmemStore<C>(tb, spill, lane), pqp::SmemStore<C, float>(smem, lane), tm), lane, qp);
+        w.run(src, ka.n_max);
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
