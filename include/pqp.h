@@ -115,8 +115,8 @@ typedef struct pqp_params {
     int32_t reserved;               /* option bits, default 0: 1 = (unused),
                                        2 = iterate in FP64 (whole kernel in double precision),
                                        4 = do not re-solve suspected-infeasible instances in FP64,
-                                       8 = FP32 state in tensor memory (persistent 4-warp CTAs),
-                                       bits 4-6 = extra shared-memory warps next to them (experimental) */
+                                       8 = FP32 state in tensor memory (persistent CTAs, tcgen05.ld/st),
+                                       16 = FP32 state in shared memory even where tensor memory is the default */
 } pqp_params;
 
 /* Batch input. All pointers are HOST pointers for pqp_solve/pqp_resolve and DEVICE

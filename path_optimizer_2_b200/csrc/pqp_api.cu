@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <algorithm>
@@ -126,11 +127,11 @@ __device__ __forceinline__ void tmem_st4(uint32_t a, const float4 &v) {
                  : "memory");
 }
 
-template <int C>
+template <int C, int COLS = 512>
 struct TmemStore {
     typedef float4 Vec4;
     static constexpr int kAll = pqp::NFIELD / 4;                       // 18 groups
-    static constexpr int kFit = 512 / (4 * C);                         // groups that fit in 512 columns
+    static constexpr int kFit = COLS / (4 * C);                        // groups that fit in this warp's columns
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
     static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8, else 0
     uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
@@ -182,87 +183,38 @@ struct TmemStore {
 };
 
 
-// Run-time choice between the two backends (warp-uniform flag): the hybrid kernel's tensor-memory
-// warps and shared-memory warps execute ONE instantiation of the solver, so they share its
-// instructions in the instruction cache (two instantiations side by side were measured to spend
-// 59 % of their stall samples on instruction fetch: profiles/r1/README.md).
-template <int C>
-struct HybridStore {
-    typedef float4 Vec4;
-    TmemStore<C> t;
-    pqp::SmemStore<C, float> m;
-    bool tm;
-    __device__ HybridStore(const TmemStore<C> &ts, const pqp::SmemStore<C, float> &ms, bool use_t) : t(ts), m(ms), tm(use_t) {}
-    __device__ float ld(int f, int k) const { return tm ? t.ld(f, k) : m.ld(f, k); }
-    __device__ void st(int f, int k, float v) { if (tm) t.st(f, k, v); else m.st(f, k, v); }
-    __device__ float4 ld4(int g, int k) const { return tm ? t.ld4(g, k) : m.ld4(g, k); }
-    __device__ void st4(int g, int k, const float4 &v) { if (tm) t.st4(g, k, v); else m.st4(g, k, v); }
-    template <int N> __device__ void ld4n(int g0, int k, float (&out)[4 * N]) const {
-        if (tm) t.template ld4n<N>(g0, k, out);
-        else m.template ld4n<N>(g0, k, out);
-    }
-    __device__ void fence() { if (tm) t.fence(); }
-};
-
-// Hybrid persistent kernel (FP32): one CTA per SM, 4 + WS warps, every warp solves one QP at a
-// time and takes the next unsolved instance from a global work counter. Warps 0-3 keep their
-// QP's state in tensor memory (one warp per TMEM sub-partition), warps 4.. keep it in shared
-// memory (with the TMA bulk-copy input staging of the plain kernel) — so both on-chip memories
-// hold QPs: 4 + 2 per SM at n = 240 instead of 3.
-template <int C, int WS>
-__global__ void __launch_bounds__(32 * (4 + WS), 1) pqp_admm_kernel_hybrid(const __grid_constant__ pqp::KernelArgs ka) {
+// Tensor-memory persistent kernel (FP32): one CTA per SM with WT warps (4, or 8 when two warps
+// can share a TMEM sub-partition: 256 columns each); every warp solves one QP at a time and takes
+// the next unsolved instance from a global work counter (iteration counts vary 3x between
+// instances; a static assignment would idle).
+// A hybrid variant that added shared-memory-backed warps to the same CTA was measured slower
+// (instruction-fetch bound either as two instantiations or as one with run-time backend
+// selection): profiles/r1/README.md.
+template <int C, int WT>
+__global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_constant__ pqp::KernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t tbase_s;
+    constexpr int kCols = 512 / (WT / 4);
+    typedef TmemStore<C, kCols> Store;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t need = TmemStore<C>::kGroups * 4 * C;
+    constexpr uint32_t need = (uint32_t)(Store::kGroups * 4 * C) * (WT / 4);
     constexpr uint32_t ncols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-    constexpr size_t kSpillFloats = (size_t)(TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 0) * C * 32 * 4;
-    constexpr size_t kSmemWarpFloats = (size_t)pqp::NFIELD * C * 32 + 4;  // + mbarrier (16 B)
+    constexpr size_t kSpillFloats = (size_t)(Store::kSpill > 0 ? Store::kSpill : 0) * C * 32 * 4;
     if (warp == 0) tmem_alloc(&tbase_s, ncols);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float *base = reinterpret_cast<float *>(smem_raw);
-    const bool tm = warp < 4;
-    const uint32_t tb = tbase_s + ((uint32_t)(32 * (warp & 3)) << 16);
-    float *spill = base + (size_t)(warp & 3) * kSpillFloats;
-    float *smem = base + 4 * kSpillFloats + (size_t)(tm ? 0 : warp - 4) * kSmemWarpFloats;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pqp::NFIELD * C * 32);
-    double *stage = reinterpret_cast<double *>(smem + pqp::FDI * C * 32);
-    const uint32_t bytes = (uint32_t)(PQP_NFIELDS * ka.n_max * sizeof(double));
-    const bool use_tma = !tm && ka.use_tma;
-    uint32_t parity = 0;
-    if (use_tma) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
-    // persistent warps: each takes the next unsolved instance until the batch is exhausted
-    // (iteration counts vary 3x between instances; a static assignment would idle)
+    // lanes of sub-partition (warp & 3); the second warp of a sub-partition takes the upper columns
+    const uint32_t tb = tbase_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * Store::kGroups * 4 * C);
+    float *spill = reinterpret_cast<float *>(smem_raw) + (size_t)warp * kSpillFloats;
     for (;;) {
         int qp = 0;
         if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
         qp = __shfl_sync(0xffffffffu, qp, 0);
         if (qp >= ka.batch) break;
         const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
-        if (use_tma) {
-            // the staging buffer was last touched through the generic proxy (previous QP)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                mbar_expect_tx(bar, bytes);
-                tma_load_1d(stage, src, bytes, bar);
-            }
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-            src = stage;
-        }
-        pqp::QpWarp<C, float, HybridStore<C> > w(
-            ka, HybridStore<C>(TmemStore<C>(tb, spill, lane), pqp::SmemStore<C, float>(smem, lane), tm), lane, qp);
+        pqp::QpWarp<C, float, Store> w(ka, Store(tb, spill, lane), lane, qp);
         w.run(src, ka.n_max);
-        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -324,7 +276,6 @@ struct pqp_handle {
     static const int kCounters = 64;
     int *d_counters = nullptr;
     unsigned counter_next = 0;
-    int hybrid_ws = 0;             // shared-memory-backed warps next to the 4 tensor-memory warps
     bool use_tmem = false;         // params.reserved bit 3: state in tensor memory (FP32 kernel)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
@@ -394,57 +345,39 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
     }
 }
 
-// hybrid persistent variant: one CTA per SM (it owns the SM's tensor memory) with WS additional
-// shared-memory-backed warps (register file: (4 + WS) x 32 x 255 <= 64 K)
-template <int C, int WS>
-size_t hybrid_smem_bytes() {
-    const size_t spill = (size_t)(TmemStore<C>::kSpill > 0 ? TmemStore<C>::kSpill : 0) * C * 32 * 16;
-    size_t bytes = 4 * spill + (size_t)WS * ((size_t)pqp::NFIELD * C * 32 * 4 + 16);
-    if (bytes < 116 * 1024) bytes = 116 * 1024;  // keep it at one CTA per SM
-    return bytes;
-}
-template <int C, int WS>
-cudaError_t launch_hybrid(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
-    constexpr int W = 4 + WS;
+// tensor-memory persistent variant: one CTA per SM (the dynamic shared-memory request is padded
+// so that a second CTA cannot be resident and spin on tcgen05.alloc)
+template <int C> struct TmemCfg { static constexpr int WT = (C == 4) ? 8 : 4; };
+constexpr size_t kTmemSmem = 120 * 1024;
+template <int C>
+cudaError_t launch_tmem(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
+    constexpr int W = TmemCfg<C>::WT;
     int ctas = (ka.batch + W - 1) / W;
     if (ctas > sm_count) ctas = sm_count;
-    pqp_admm_kernel_hybrid<C, WS><<<ctas, 32 * W, hybrid_smem_bytes<C, WS>(), s>>>(ka);
+    pqp_admm_kernel_tmem<C, W><<<ctas, 32 * W, kTmemSmem, s>>>(ka);
     return cudaGetLastError();
 }
-template <int C, int WS>
-cudaError_t prepare_hybrid() {
-    return cudaFuncSetAttribute(pqp_admm_kernel_hybrid<C, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hybrid_smem_bytes<C, WS>());
-}
-// (chunk, ws) dispatch; ws is clamped to what fits in shared memory for that chunk size
-int hybrid_ws_max(int chunk) { return chunk >= 8 ? 2 : 4; }
-#define PQP_HYB_CASE(C, WS, EXPR) case (C * 8 + WS): return EXPR<C, WS>
-cudaError_t launch_tmem_chunk(int chunk, int ws, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
-    switch (chunk * 8 + ws) {
-        case 8 * 8 + 0: return launch_hybrid<8, 0>(ka, s, sm_count);
-        case 8 * 8 + 1: return launch_hybrid<8, 1>(ka, s, sm_count);
-        case 8 * 8 + 2: return launch_hybrid<8, 2>(ka, s, sm_count);
-        case 4 * 8 + 0: return launch_hybrid<4, 0>(ka, s, sm_count);
-        case 4 * 8 + 2: return launch_hybrid<4, 2>(ka, s, sm_count);
-        case 4 * 8 + 4: return launch_hybrid<4, 4>(ka, s, sm_count);
-        case 2 * 8 + 0: return launch_hybrid<2, 0>(ka, s, sm_count);
-        case 1 * 8 + 0: return launch_hybrid<1, 0>(ka, s, sm_count);
-        default: return cudaErrorInvalidValue;
+cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
+    switch (chunk) {
+        case 1: return launch_tmem<1>(ka, s, sm_count);
+        case 2: return launch_tmem<2>(ka, s, sm_count);
+        case 4: return launch_tmem<4>(ka, s, sm_count);
+        default: return launch_tmem<8>(ka, s, sm_count);
     }
 }
-cudaError_t prepare_tmem_chunk(int chunk, int ws) {
-    switch (chunk * 8 + ws) {
-        case 8 * 8 + 0: return prepare_hybrid<8, 0>();
-        case 8 * 8 + 1: return prepare_hybrid<8, 1>();
-        case 8 * 8 + 2: return prepare_hybrid<8, 2>();
-        case 4 * 8 + 0: return prepare_hybrid<4, 0>();
-        case 4 * 8 + 2: return prepare_hybrid<4, 2>();
-        case 4 * 8 + 4: return prepare_hybrid<4, 4>();
-        case 2 * 8 + 0: return prepare_hybrid<2, 0>();
-        case 1 * 8 + 0: return prepare_hybrid<1, 0>();
-        default: return cudaErrorInvalidValue;
+template <int C>
+cudaError_t prepare_tmem() {
+    return cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+}
+cudaError_t prepare_tmem_chunk(int chunk) {
+    switch (chunk) {
+        case 1: return prepare_tmem<1>();
+        case 2: return prepare_tmem<2>();
+        case 4: return prepare_tmem<4>();
+        default: return prepare_tmem<8>();
     }
 }
+int tmem_warps(int chunk) { return chunk == 4 ? 8 : 4; }
 
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
     if (!h) return PQP_E_INVALID;
@@ -497,7 +430,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
         PQP_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), s));
         ka.work_counter = ctr;
-        PQP_CUDA(h, launch_tmem_chunk(h->chunk, h->hybrid_ws, ka, s, h->sm_count));
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count));
     } else {
         PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
     }
@@ -747,15 +680,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
     h->use_tmem = (params->reserved & 8) != 0 && !h->fp64;
-    if (h->use_tmem) {
-        // bits 4-6 of reserved: number of extra shared-memory warps (experiments); default 0
-        int ws = (params->reserved >> 4) & 7;
-        if (h->chunk <= 2) ws = 0;
-        if (h->chunk == 4 && ws != 0 && ws != 2 && ws != 4) ws = 0;
-        if (ws > hybrid_ws_max(h->chunk)) ws = hybrid_ws_max(h->chunk);
-        h->hybrid_ws = ws;
-        PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk, ws));
-    }
+    if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
     if (h->fp64) {
@@ -764,7 +689,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     } else {
         PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps));
     }
-    h->warps_per_sm = h->use_tmem ? 4 + h->hybrid_ws : bps;
+    h->warps_per_sm = h->use_tmem ? tmem_warps(h->chunk) : bps;
     for (int i = 0; i < pqp_handle::kStreams; ++i) {
         PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
         PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[i], cudaEventDisableTiming));

@@ -303,6 +303,9 @@ struct SmemStore {
 #ifndef PQP_UPDATE_UNROLL
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
+#ifndef PQP_CR_UNROLL
+#define PQP_CR_UNROLL _Pragma("unroll")
+#endif
 
 template <int C, typename real, typename Store = SmemStore<C, real> >
 struct QpWarp {
@@ -859,7 +862,7 @@ struct QpWarp {
             bs[r] = bk[r] - fr;
         }
         // cyclic reduction, forward (unrolled: lane masks become constants)
-#pragma unroll
+        PQP_CR_UNROLL
         for (int t = 0; t < 5; ++t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -887,7 +890,7 @@ struct QpWarp {
             xs[r] = ts[r];
         }
         // cyclic reduction, backward
-#pragma unroll
+        PQP_CR_UNROLL
         for (int t = 4; t >= 0; --t) {
             const int h = 1 << t;
             const bool elim = (lane & (2 * h - 1)) == h;
@@ -1420,7 +1423,7 @@ struct QpWarp {
         zend[0] = zend[1] = endw[0] = endw[1] = real(0.0);
         cert_nrm = cert_lhs = real(0.0);
         suspect = 0;
-        const bool warm = ka.mode == 1;
+        const bool warm = (ka.mode & 1) == 1;
         rho = warm ? static_cast<real *>(ka.rho_state)[qp + ka.qp0] : (real)P.rho0;
         rho = xmin(xmax(rho, real(kRhoMin)), real(kRhoMax));
 
