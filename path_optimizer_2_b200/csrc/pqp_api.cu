@@ -679,7 +679,10 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(cudaSetDevice(device));
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
-    h->use_tmem = (params->reserved & 8) != 0 && !h->fp64;
+    // storage policy of the FP32 kernel: tensor memory where shared memory limits residency to
+    // 3 QPs per SM (n_max >= 128: 819 k vs 628 k solves/s at n = 240), shared memory otherwise
+    // (equal at n = 120, 1.5x better at n = 60); bits 8 / 16 force one or the other
+    h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (h->chunk == 8 && (params->reserved & 16) == 0));
     if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;

@@ -194,17 +194,18 @@ def test_receding_horizon_ticks(solver_mod):
 
 @pytest.mark.parametrize("n", [20, 120, 240])
 def test_tensor_memory_policy_matches_shared_memory_policy(solver_mod, n):
-    """params.reserved bit 3: the same solver code with its per-stage state in tensor memory
-    (tcgen05.ld/st) instead of shared memory. Same arithmetic -> same answers."""
+    """params.reserved bit 3 / bit 4: the same solver code with its per-stage state in tensor
+    memory (tcgen05.ld/st, persistent CTAs) or in shared memory. Same arithmetic -> same answers.
+    (Default: tensor memory for n_max >= 128, shared memory below.)"""
     hb = synthetic.make_batch(3, 9, n)   # 9: exercises a partially filled last CTA (4 QPs per CTA)
     res = {}
-    for bits in (0, 8):
+    for bits in (16, 8):
         sv = solver_mod.PathQpSolver(abi.default_params(reserved=bits), n_max=n, batch_max=hb.batch)
         r1 = sv.solve(hb, full=True)
         r2 = sv.resolve(hb.with_linearisation(r1.sol), full=True)
         res[bits] = (r1, r2)
         sv.close()
-    for a, b in zip(res[0], res[8]):
+    for a, b in zip(res[16], res[8]):
         assert np.array_equal(a.status, b.status) and np.array_equal(a.iters, b.iters)
         assert np.allclose(a.x_full, b.x_full, atol=1e-5, rtol=0)
         assert np.allclose(a.y_full, b.y_full, atol=1e-3, rtol=1e-4)
