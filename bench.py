@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def stop(self):
         self._stop_evt.set()
@@ -454,6 +454,7 @@ def main():
                 "mean_admm_iters": float(np.mean(iters)),
                 "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
                 "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
+                "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if (n >= 128 and not (args.option_bits & 16)) or (args.option_bits & 8) else "shared memory",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -463,8 +464,8 @@ def main():
                          "frac": achieved / peak, "traffic": measured_traffic(n, B), "peak_source": peak_src,
                          "kernel": "pqp_admm_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "note": "state is shared-memory resident; the path is latency/issue bound, "
-                                 "not HBM bound (see DESIGN.md)"},
+                         "note": "per-iteration state is on-chip (tensor memory / shared memory); the path is "
+                                 "latency/issue bound, not HBM bound (see DESIGN.md)"},
         }
         if world == 1 and not args.no_cpu:
             from oracle import oracle
