@@ -212,9 +212,45 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
         if (lane == 0) qp = atomicAdd(ka.work_counter, 1);
         qp = __shfl_sync(0xffffffffu, qp, 0);
         if (qp >= ka.batch) break;
+        int chunk = 0;
+        if (ka.ready) {
+            // streamed launch: this instance's inputs may still be in flight
+            chunk = qp / ka.chunk_len;
+            bool landed = true;
+            if (lane == 0) {
+                const volatile int *flag = ka.ready + chunk;
+                const long long t0 = clock64();
+                while (*flag == 0) {
+                    __nanosleep(200);
+                    if (clock64() - t0 > 20000000000LL) {  // ~10 s: give up, never hang
+                        landed = false;
+                        atomicExch(ka.work_counter, 1 << 30);  // and stop everybody else from taking work
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            landed = __shfl_sync(0xffffffffu, landed ? 1 : 0, 0) != 0;
+            if (!landed) {
+                if (lane == 0 && ka.status) ka.status[qp] = pqp::kUnsolved;
+                continue;
+            }
+        }
         const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
         pqp::QpWarp<C, float, Store> w(ka, Store(tb, spill, lane), lane, qp);
         w.run(src, ka.n_max);
+        if (ka.done) {
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();  // this instance's outputs before the count
+                const int lo = chunk * ka.chunk_len;
+                const int len = (lo + ka.chunk_len <= ka.batch) ? ka.chunk_len : ka.batch - lo;
+                if (atomicAdd(ka.done + chunk, 1) + 1 == len) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int *>(ka.host_done + chunk) = 1;
+                }
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -273,6 +309,8 @@ struct pqp_handle {
     double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
     int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
     void *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    int *d_ready = nullptr, *d_done = nullptr;      // per-chunk flags of the streamed launch
+    int *h_done = nullptr, *d_hdone = nullptr;     // mapped pinned host memory + its device alias
     static const int kCounters = 64;
     int *d_counters = nullptr;
     unsigned counter_next = 0;
@@ -389,8 +427,15 @@ int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *o
 }
 
 // device pointers in `in`/`out`; asynchronous
+struct StreamedLaunch {
+    const int *ready = nullptr;
+    int *done = nullptr, *host_done = nullptr;
+    int chunk_len = 0;
+};
+
 int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode,
-               cudaStream_t s, bool timed, int qp0 = 0, bool esc = false, int *flags = nullptr) {
+               cudaStream_t s, bool timed, int qp0 = 0, bool esc = false, int *flags = nullptr,
+               const StreamedLaunch *sl = nullptr) {
     pqp::KernelArgs ka;
     ka.prm = pqp::make_dev_params(h->prm);
     ka.batch = in->batch;
@@ -413,6 +458,10 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     ka.info = out->info;
     ka.flags = flags;
     ka.work_counter = nullptr;
+    ka.ready = sl ? sl->ready : nullptr;
+    ka.done = sl ? sl->done : nullptr;
+    ka.host_done = sl ? sl->host_done : nullptr;
+    ka.chunk_len = sl ? sl->chunk_len : 0;
     ka.warm = esc ? h->e_warm : h->d_warm;
     ka.scal = esc ? h->e_scal : h->d_scal;
     ka.dy = esc ? h->e_dy : h->d_dy;
@@ -521,6 +570,80 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
 }
 
 
+
+// Host-buffer solve on the persistent tensor-memory kernel as ONE launch over the whole batch:
+// the kernel starts immediately and each warp waits (ready[chunk]) until the H2D copy of the
+// chunk its next instance belongs to has landed; finished chunks are announced through mapped
+// host memory (host_done[chunk]) so their D2H copies overlap the rest of the solve. Compared
+// with one launch per chunk this removes the per-launch tail of a persistent kernel.
+int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode, int B) {
+    const int nmax = h->n_max;
+    const size_t nvm = 6 * (size_t)nmax - 1, mm = 6 * (size_t)nmax + 2;
+    int nchunks = (B + 1023) / 1024;
+    if (nchunks > pqp_handle::kStreams) nchunks = pqp_handle::kStreams;
+    const int per = (B + nchunks - 1) / nchunks;
+    nchunks = (B + per - 1) / per;
+    cudaStream_t sk = h->streams[0], sc = h->streams[1], sd = h->streams[2];
+    for (int c = 0; c < pqp_handle::kStreams; ++c) h->h_done[c] = 0;
+    PQP_CUDA(h, cudaMemsetAsync(h->d_ready, 0, pqp_handle::kStreams * sizeof(int), sk));
+    PQP_CUDA(h, cudaMemsetAsync(h->d_done, 0, pqp_handle::kStreams * sizeof(int), sk));
+    if (out->x_full) PQP_CUDA(h, cudaMemsetAsync(h->d_xf, 0, (size_t)B * nvm * sizeof(double), sk));
+    if (out->y_full) PQP_CUDA(h, cudaMemsetAsync(h->d_yf, 0, (size_t)B * mm * sizeof(double), sk));
+    if (out->z_full) PQP_CUDA(h, cudaMemsetAsync(h->d_zf, 0, (size_t)B * mm * sizeof(double), sk));
+    PQP_CUDA(h, cudaEventRecord(h->ev0, sk));
+    PQP_CUDA(h, cudaStreamWaitEvent(sc, h->ev0, 0));
+    PQP_CUDA(h, cudaStreamWaitEvent(sd, h->ev0, 0));
+    pqp_batch_in din = {B, nmax, h->d_knots, h->d_inst, h->d_n, (h->d_p_valid = in->p != nullptr) ? h->d_p : nullptr};
+    pqp_batch_out dout = {h->d_sol, h->d_cost, h->d_status, h->d_iters, out->x_full ? h->d_xf : nullptr,
+                          out->y_full ? h->d_yf : nullptr, out->z_full ? h->d_zf : nullptr, h->d_info};
+    StreamedLaunch sl;
+    sl.ready = h->d_ready;
+    sl.done = h->d_done;
+    sl.host_done = h->d_hdone;
+    sl.chunk_len = per;
+    int rc = run_device(h, &din, &dout, mode, sk, false, 0, false, h->d_flags, &sl);
+    if (rc) return rc;
+    for (int c = 0; c < nchunks; ++c) {
+        const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
+        const size_t nb = (size_t)(hi - lo);
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_knots + (size_t)lo * PQP_NFIELDS * nmax, in->knots + (size_t)lo * PQP_NFIELDS * nmax,
+                                    nb * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, sc));
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_inst + (size_t)lo * PQP_NINST, in->inst + (size_t)lo * PQP_NINST,
+                                    nb * PQP_NINST * sizeof(double), cudaMemcpyHostToDevice, sc));
+        PQP_CUDA(h, cudaMemcpyAsync(h->d_n + lo, in->n + lo, nb * sizeof(int), cudaMemcpyHostToDevice, sc));
+        if (in->p) PQP_CUDA(h, cudaMemcpyAsync(h->d_p + lo, in->p + lo, nb * sizeof(int), cudaMemcpyHostToDevice, sc));
+        PQP_CUDA(h, cudaMemsetAsync(h->d_ready + c, 1, sizeof(int), sc));  // "chunk c has landed"
+    }
+    h->host_inputs_resident = true;
+    for (int c = 0; c < nchunks; ++c) {
+        const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
+        const size_t nb = (size_t)(hi - lo);
+        // wait until the kernel announces the chunk (or has ended, e.g. after an error)
+        volatile int *flag = h->h_done + c;
+        for (unsigned spin = 0; *flag == 0; ++spin) {
+            if ((spin & 0x3ff) == 0x3ff && cudaStreamQuery(sk) != cudaErrorNotReady) break;
+        }
+        PQP_CUDA(h, cudaMemcpyAsync(h->h_status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
+        PQP_CUDA(h, cudaMemcpyAsync(h->h_flags + lo, h->d_flags + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
+        PQP_CUDA(h, cudaMemcpyAsync(out->sol + (size_t)lo * 4 * nmax, h->d_sol + (size_t)lo * 4 * nmax, nb * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (out->cost) PQP_CUDA(h, cudaMemcpyAsync(out->cost + lo, h->d_cost + lo, nb * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (out->status) PQP_CUDA(h, cudaMemcpyAsync(out->status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
+        if (out->iters) PQP_CUDA(h, cudaMemcpyAsync(out->iters + lo, h->d_iters + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
+        if (out->info) PQP_CUDA(h, cudaMemcpyAsync(out->info + (size_t)lo * PQP_NINFO, h->d_info + (size_t)lo * PQP_NINFO, nb * PQP_NINFO * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (out->x_full) PQP_CUDA(h, cudaMemcpyAsync(out->x_full + lo * nvm, h->d_xf + lo * nvm, nb * nvm * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (out->y_full) PQP_CUDA(h, cudaMemcpyAsync(out->y_full + lo * mm, h->d_yf + lo * mm, nb * mm * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (out->z_full) PQP_CUDA(h, cudaMemcpyAsync(out->z_full + lo * mm, h->d_zf + lo * mm, nb * mm * sizeof(double), cudaMemcpyDeviceToHost, sd));
+    }
+    h->last_batch = B;
+    PQP_CUDA(h, cudaStreamSynchronize(sk));
+    PQP_CUDA(h, cudaStreamSynchronize(sc));
+    PQP_CUDA(h, cudaEventRecord(h->ev1, sd));
+    PQP_CUDA(h, cudaStreamSynchronize(sd));
+    PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (!h->fp64 && h->escalate) return escalate_fp64(h, in, out, B);
+    return PQP_OK;
+}
+
 int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode) {
     int rc;
     const int nmax = h->n_max;
@@ -538,6 +661,13 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         if (mode == 1 && (!h->solved || B != h->last_batch)) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
         h->host_inputs_resident = true;
         h->d_p_valid = in->p != nullptr;
+        if (h->use_tmem && B >= 2048) {
+            const size_t nvm0 = 6 * (size_t)nmax - 1, mm0 = 6 * (size_t)nmax + 2;
+            if (out->x_full && !h->d_xf) PQP_CUDA(h, dmalloc(&h->d_xf, (size_t)h->batch_max * nvm0));
+            if (out->y_full && !h->d_yf) PQP_CUDA(h, dmalloc(&h->d_yf, (size_t)h->batch_max * mm0));
+            if (out->z_full && !h->d_zf) PQP_CUDA(h, dmalloc(&h->d_zf, (size_t)h->batch_max * mm0));
+            return run_host_streamed(h, in, out, mode, B);
+        }
     } else {
         if (mode != 1) return fail(h, PQP_E_INVALID, "null batch");
         if (!out || !out->sol) return fail(h, PQP_E_INVALID, "null output");
@@ -717,6 +847,10 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
     PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
     PQP_CREATE_CUDA(dmalloc(&h->d_counters, (size_t)pqp_handle::kCounters));
+    PQP_CREATE_CUDA(dmalloc(&h->d_ready, (size_t)pqp_handle::kStreams));
+    PQP_CREATE_CUDA(dmalloc(&h->d_done, (size_t)pqp_handle::kStreams));
+    PQP_CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&h->h_done), pqp_handle::kStreams * sizeof(int), cudaHostAllocMapped));
+    PQP_CREATE_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_hdone), h->h_done, 0));
     PQP_CREATE_CUDA(dmalloc(&h->d_flags, B));
     PQP_CREATE_CUDA(cudaMemset(h->d_flags, 0, B * sizeof(int)));
     PQP_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->h_status), B * sizeof(int)));
@@ -738,6 +872,9 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_warm); cudaFree(h->d_scal); cudaFree(h->d_dy); cudaFree(h->d_rho);
     cudaFree(h->d_flags);
     cudaFree(h->d_counters);
+    cudaFree(h->d_ready);
+    cudaFree(h->d_done);
+    if (h->h_done) cudaFreeHost(h->h_done);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->e_knots); cudaFree(h->e_inst); cudaFree(h->e_sol); cudaFree(h->e_cost); cudaFree(h->e_info);

@@ -114,6 +114,14 @@ struct KernelArgs {
     double *sol, *cost;
     int *status, *iters;
     int *work_counter;  // persistent kernels: next instance to take (zeroed before the launch)
+    // streamed launch (host API): the kernel starts before the inputs have landed; instance qp
+    // belongs to chunk qp / chunk_len, whose H2D copy is followed by a write to ready[chunk];
+    // done[chunk] counts finished instances and host_done[chunk] (mapped host memory) is set
+    // when a chunk is complete so the host can start its D2H copy. All null for plain launches.
+    const int *ready;
+    int *done;
+    int *host_done;
+    int chunk_len;
     int *flags;  // optional: bit 0 = infeasibility suspected (certificate conditions 1-2 held)
     double *x_full, *y_full, *z_full, *info;
     void *warm, *scal, *dy, *rho_state;  // per-instance scratch in the kernel's scalar type
