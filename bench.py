@@ -36,6 +36,19 @@ UNIT = "solves/s"
 CFG_ID = 3
 
 
+def make_workload(args, batch, first):
+    """(HostBatch, description) of `batch` instances starting at global index `first`."""
+    if args.workload == "sharedmap":
+        from path_optimizer_2_b200 import sharedmap
+        hb = sharedmap.make_batch(batch, args.n, first=first)
+        return hb, ("BASELINE configs[1] per GPU: batch %d paths x %d knots through ONE shared obstacle map "
+                    "(gridmap.png distance field, bounds ray-marched as reference_path_impl.cpp:177-312 does), "
+                    "cold BaseSolver::solve (configs[0] is batch 1 of the same)" % (batch, args.n))
+    hb = synthetic.make_batch(CFG_ID, batch, args.n, first=first)
+    return hb, ("BASELINE configs[2] per GPU: batch %d paths, %d knots, per-instance clearance "
+                "bounds, cold BaseSolver::solve (configs[3] = 8 GPUs x 8192)" % (batch, args.n))
+
+
 def algorithmic_bytes(n, warm=False):
     return (296 * n + 72) if warm else (104 * n + 56)
 
@@ -139,7 +152,7 @@ def run_reference(args, rank, world):
     params = abi.default_params()
     threads = host_threads()
     sample = args.cpu_sample
-    hb = synthetic.make_batch(CFG_ID, sample, args.n)
+    hb, workload = make_workload(args, sample, 0)
     for _ in range(args.warmup):
         oracle.solve_batch(params, hb.slice(0, min(64, sample)), nthreads=threads)
     t_tot = 0.0
@@ -152,8 +165,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: batch 8192 paths, 240 knots, per-instance clearance "
-                               "bounds (each step = a bounded sample of %d instances)" % sample,
+        "config": {"workload": workload.replace("per GPU: batch %d paths" % sample, "per GPU, bounded sample: %d paths "
+                                                "per step" % sample),
                    "n_knots": args.n, "batch_per_step": sample, "cold_solve": True},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d instances per step, OSQP-algorithm restatement with direct CSC assembly "
@@ -315,12 +328,19 @@ def main():
     ap.add_argument("--option-bits", type=int, default=0,
                     help="pqp_params.reserved: 1 FP32 factorisation, 2 FP64 iterates, 4 no FP64 escalation, "
                          "8 state in tensor memory")
-    ap.add_argument("--workload", default="cold", choices=["cold", "receding"],
+    ap.add_argument("--workload", default="cold", choices=["cold", "receding", "sharedmap"],
                     help="cold: BASELINE configs[2]/[3] (default); receding: configs[4], warm re-solves with a "
-                         "50-iteration cap on a window that advances one knot per step")
+                         "50-iteration cap on a window that advances one knot per step; sharedmap: configs[1], "
+                         "1024 paths x 120 knots through the shared obstacle map")
     args = ap.parse_args()
     if args.workload == "receding" and args.batch == 8192:
         args.batch = 512  # configs[4]: 4096 instances over 8 GPUs
+    if args.workload == "sharedmap":
+        if args.batch == 8192:
+            args.batch = 1024
+        if args.n == 240:
+            args.n = 120
+        args.cpu_sample = min(args.cpu_sample, args.batch)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
 
@@ -350,8 +370,10 @@ def main():
     params = abi.default_params(reserved=args.option_bits)
     B, n = args.batch, args.n
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
-    hb = synthetic.make_batch(CFG_ID, B, n, first=rank * B)
+    hb, workload = make_workload(args, B, rank * B)
     sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
+    # inputs smaller than L2 (the shared-map config): evict them between timed steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if hb.knots.nbytes < (160 << 20) else None
 
     # ---- device-resident inputs/outputs (torch owns the memory, the C ABI gets raw pointers)
     d_knots = torch.from_numpy(hb.knots).to(dev)
@@ -389,6 +411,8 @@ def main():
     barrier()
     ev[0].record()
     for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 255)
         kev[i][0].record()
         sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
         kev[i][1].record()
@@ -445,11 +469,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "BASELINE configs[2] per GPU: batch %d paths, %d knots, per-instance clearance "
-                            "bounds, cold BaseSolver::solve (configs[3] = 8 GPUs x 8192)" % (B, n),
+                "workload": workload,
                 "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                 "eps_abs": params.eps_abs, "eps_rel": params.eps_rel, "max_iter": params.max_iter,
-                "l2_policy": "inputs larger than L2 (%.0f MB per step vs 126 MB)" % (hb.knots.nbytes / 1e6),
+                "l2_policy": ("inputs larger than L2 (%.0f MB per step vs 126 MB)" % (hb.knots.nbytes / 1e6))
+                if flush is None else "L2 flushed between timed steps (256 MB fill inside the timed region)",
                 "collective": "all_gather of {cost,status,iters} (16 B/instance)" if world > 1 else "none",
                 "mean_admm_iters": float(np.mean(iters)),
                 "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
