@@ -36,17 +36,82 @@ UNIT = "solves/s"
 CFG_ID = 3
 
 
-def make_workload(args, batch, first):
-    """(HostBatch, description) of `batch` instances starting at global index `first`."""
+def make_workload(args, batch, first, device=None):
+    """(HostBatch, description, extras) of `batch` instances starting at global index `first`.
+    Shared-map workload: the clearance bounds come from the CUDA bounds kernel (pqp_bounds.h) on
+    `device`; with device=None (the CPU reference arm) from the oracle's numpy restatement."""
     if args.workload == "sharedmap":
         from path_optimizer_2_b200 import sharedmap
-        hb = sharedmap.make_batch(batch, args.n, first=first)
+        dmap = sharedmap.DistanceMap()
+        lines = sharedmap.make_lines(batch, args.n, first=first, dmap=dmap)
+        extras = {}
+        if device is None:
+            from oracle import bounds_oracle
+            t0 = time.perf_counter()
+            bnd = np.zeros((batch, 6, args.n))
+            nv = np.zeros(batch, dtype=np.int32)
+            for b in range(batch):
+                bnd[b], nv[b] = bounds_oracle.update_bounds(dmap.dist, dmap.res, lines.spline_rows(b), *lines.states[b])
+            extras["bounds_cpu_s"] = time.perf_counter() - t0
+        else:
+            extras = bounds_stage(args, dmap, lines, device)
+            bnd, nv = extras.pop("bounds"), extras.pop("n_valid")
+        hb = lines.to_host_batch(bnd, nv)
         return hb, ("BASELINE configs[1] per GPU: batch %d paths x %d knots through ONE shared obstacle map "
-                    "(gridmap.png distance field, bounds ray-marched as reference_path_impl.cpp:177-312 does), "
-                    "cold BaseSolver::solve (configs[0] is batch 1 of the same)" % (batch, args.n))
+                    "(gridmap.png distance layer; clearance bounds = updateBoundsImproved, "
+                    "reference_path_impl.cpp:177-312), cold BaseSolver::solve (configs[0] is batch 1 of the "
+                    "same)" % (batch, args.n)), extras
     hb = synthetic.make_batch(CFG_ID, batch, args.n, first=first)
     return hb, ("BASELINE configs[2] per GPU: batch %d paths, %d knots, per-instance clearance "
-                "bounds, cold BaseSolver::solve (configs[3] = 8 GPUs x 8192)" % (batch, args.n))
+                "bounds, cold BaseSolver::solve (configs[3] = 8 GPUs x 8192)" % (batch, args.n)), {}
+
+
+def bounds_stage(args, dmap, lines, device):
+    """SURVEY.md §8 row f-1 on the GPU: bounds for the whole batch through the C ABI, timed with
+    CUDA events on the launching stream (device-resident inputs), next to the oracle on a sample."""
+    import torch
+    from oracle import bounds_oracle
+    from path_optimizer_2_b200 import bounds
+    dev = torch.device("cuda", device)
+    pbn = bounds.PathBounds(dmap.dist, dmap.res, device=device)
+    B, n = lines.batch, lines.n_max
+    d_states, d_spline = torch.from_numpy(lines.states).to(dev), torch.from_numpy(lines.spline).to(dev)
+    d_n, d_k = torch.from_numpy(lines.n).to(dev), torch.from_numpy(lines.k).to(dev)
+    d_bounds = torch.zeros((B, 6, n), dtype=torch.float64, device=dev)
+    d_nv = torch.zeros(B, dtype=torch.int32, device=dev)
+    bi = bounds.BoundsIn(B, n, lines.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
+    bo = bounds.BoundsOut(d_bounds.data_ptr(), d_nv.data_ptr(), None)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        pbn.compute_device(bi, bo, stream=stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        pbn.compute_device(bi, bo, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bnd, nv = d_bounds.cpu().numpy(), d_nv.cpu().numpy()
+    sample = min(B, 64)
+    t0 = time.perf_counter()
+    worst = 0.0
+    for b in range(sample):
+        ob, onv = bounds_oracle.update_bounds(dmap.dist, dmap.res, lines.spline_rows(b), *lines.states[b])
+        d = np.abs(ob - bnd[b])
+        worst = max(worst, float(d[d < 0.04].max()))
+        assert onv == nv[b], "bounds kernel and oracle cut path %d differently" % b
+    cpu_s = time.perf_counter() - t0
+    pbn.close()
+    # algorithmic bytes per state: 32 B state + 48 B bounds + the path's share of its spline
+    alg = B * n * 80 + lines.spline.nbytes + dmap.dist.nbytes
+    return {"bounds": bnd, "n_valid": nv,
+            "bounds_kernel": {"kernel": "clearance_bounds_kernel", "ms_per_batch": ms, "states_per_s": B * n / (ms * 1e-3),
+                              "rays_per_s": 3 * B * n / (ms * 1e-3), "algorithmic_bytes": int(alg),
+                              "achieved_GBps": alg / (ms * 1e-3) / 1e9, "gpu_launches_per_batch": 2,
+                              "max_abs_diff_vs_oracle": worst,
+                              "cpu_oracle_states_per_s": sample * n / cpu_s, "cpu_oracle_sample": sample}}
 
 
 def algorithmic_bytes(n, warm=False):
@@ -152,7 +217,7 @@ def run_reference(args, rank, world):
     params = abi.default_params()
     threads = host_threads()
     sample = args.cpu_sample
-    hb, workload = make_workload(args, sample, 0)
+    hb, workload, _ = make_workload(args, sample, 0)
     for _ in range(args.warmup):
         oracle.solve_batch(params, hb.slice(0, min(64, sample)), nthreads=threads)
     t_tot = 0.0
@@ -370,7 +435,7 @@ def main():
     params = abi.default_params(reserved=args.option_bits)
     B, n = args.batch, args.n
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
-    hb, workload = make_workload(args, B, rank * B)
+    hb, workload, extras = make_workload(args, B, rank * B, device=local_rank)
     sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
     # inputs smaller than L2 (the shared-map config): evict them between timed steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if hb.knots.nbytes < (160 << 20) else None
@@ -470,6 +535,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload,
+                **extras,
                 "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                 "eps_abs": params.eps_abs, "eps_rel": params.eps_rel, "max_iter": params.max_iter,
                 "l2_policy": ("inputs larger than L2 (%.0f MB per step vs 126 MB)" % (hb.knots.nbytes / 1e6))
@@ -478,7 +544,7 @@ def main():
                 "mean_admm_iters": float(np.mean(iters)),
                 "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
                 "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
-                "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if (n >= 128 and not (args.option_bits & 16)) or (args.option_bits & 8) else "shared memory",
+                "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if info["smem_per_warp"] < 72 * 128 else "shared memory",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -203,7 +203,9 @@ int pqp_last_kernel_ms(pqp_handle *h, float *ms);
 int pqp_launch_count(pqp_handle *h, int64_t *count);
 
 /* Device-side properties, for occupancy reporting: SM count, resident warps per SM of
- * the solve kernel, dynamic shared memory per warp in bytes. */
+ * the solve kernel, dynamic shared memory per warp in bytes (the whole per-QP state under the
+ * shared-memory policy; only the spilled groups - 8 KB at n_max >= 128, else 0 - when the state
+ * lives in tensor memory). */
 int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm,
                     int32_t *smem_per_warp);
 

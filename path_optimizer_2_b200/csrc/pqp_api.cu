@@ -811,8 +811,12 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->escalate = (params->reserved & 4) == 0;
     // storage policy of the FP32 kernel: tensor memory where shared memory limits residency to
     // 3 QPs per SM (n_max >= 128: 819 k vs 628 k solves/s at n = 240), shared memory otherwise
-    // (equal at n = 120, 1.5x better at n = 60); bits 8 / 16 force one or the other
-    h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (h->chunk == 8 && (params->reserved & 16) == 0));
+    // (1.5x better at n = 60). At 64 <= n_max <= 127 tensor memory holds 8 QPs per SM against 6:
+    // one wave instead of two for batches around 1024 (1.09 M vs 0.91 M solves/s at B = 1024,
+    // 1.37 vs 1.29 at 2048, 1.48 vs 1.52 at 8192), so it is chosen for handles of <= 4096
+    // instances. Bits 8 / 16 force one or the other.
+    const bool auto_tmem = h->chunk == 8 || (h->chunk == 4 && batch_max <= 4096);
+    h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (auto_tmem && (params->reserved & 16) == 0));
     if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
@@ -967,7 +971,9 @@ int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm, int
     if (!h) return PQP_E_INVALID;
     if (sm_count) *sm_count = h->sm_count;
     if (warps_per_sm) *warps_per_sm = h->warps_per_sm;
-    if (smem_per_warp) *smem_per_warp = (int32_t)h->smem_bytes;
+    // tensor-memory policy: only the two spilled groups (C = 8) live in shared memory
+    if (smem_per_warp)
+        *smem_per_warp = h->use_tmem ? (int32_t)(h->chunk == 8 ? 2 * 8 * 32 * 4 * sizeof(float) : 0) : (int32_t)h->smem_bytes;
     return PQP_OK;
 }
 

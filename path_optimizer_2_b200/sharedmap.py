@@ -1,17 +1,16 @@
 """Shared-obstacle-map workload (BASELINE configs[0] and configs[1]).
 
-Input generation only (host side, numpy): the solver consumes per-knot clearance bounds; in the
-reference those come from ray-marching a distance field of `gridmap.png`. This module restates
-that front end on the CPU so that the shared-map configurations have realistic inputs:
+Workload synthesis only (host side, numpy): reference lines through the free space of
+`tests/golden/gridmap.png`, as spline coefficients + reference states — the inputs of the
+clearance-bounds kernel (include/pqp_bounds.h, `bounds.PathBounds`), whose output then feeds the
+solver. What is restated from the reference here is only what produces those inputs:
 
-  distance field      src/test/demo.cpp:98-113  (cv2.distanceTransform(DIST_L2, MASK_PRECISE) * 0.2 m)
-  map lookup          src/tools/Map.cpp:16-22   (bilinear inside the map, 0 outside)  [grid_map: EXT]
-  reference spline    src/tools/spline.cpp:163-254  (natural cubic spline over arc length)
-  knots               src/data_struct/reference_path_impl.cpp:314-338, src/tools/tools.cpp:32-44
-  anchors + bounds    reference_path_impl.cpp:177-230 (front/rear anchors projected onto the spline
-                      along the knot normal, tools.cpp:156-189) and :232-312 (clearance ray-march)
+  distance layer      src/test/demo.cpp:98-113  (cv2.distanceTransform(DIST_L2, MASK_PRECISE), float, * 0.2 m)
+  reference spline    src/tools/spline.cpp:163-247  (natural cubic spline over arc length)
+  reference states    src/data_struct/reference_path_impl.cpp:314-338, src/tools/tools.cpp:32-44
 
-The GPU version of this front end is SURVEY.md §8f-1 ("next"); nothing here is on the solve path.
+The reference line itself comes from a greedy clearance-following walk that stands in for the
+reference's hybrid A* + smoother (out of scope).
 """
 import math
 import os
@@ -21,164 +20,99 @@ import numpy as np
 from . import abi
 
 RES = 0.2
-FRONT_LENGTH, REAR_LENGTH = 3.9, -1.0
-CAR_WIDTH, SAFETY_MARGIN = 2.0, 0.3
+SPLINE_ROWS, STATE_ROWS, BOUND_ROWS = 9, 4, 6
 _MAP_PNG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gridmap.png")
 
 
 class DistanceMap:
-    """grid_map "distance" layer of the demo: cell (i, j) = image pixel (row i, col j), its
-    centre at (+Lx/2 - (i + 1/2) res, +Ly/2 - (j + 1/2) res) with Lx = rows * res, Ly = cols * res."""
+    """grid_map "distance" layer of the demo (float32): cell (i, j) = image pixel (row i, col j),
+    centred at (+Lx/2 - (i + 1/2) res, +Ly/2 - (j + 1/2) res), Lx = rows * res, Ly = cols * res."""
 
-    def __init__(self, png_path=_MAP_PNG):
-        if not os.path.exists(png_path):
-            raise FileNotFoundError(png_path)
-        try:
-            import cv2
-            img = cv2.imread(png_path, cv2.IMREAD_GRAYSCALE)
-            free = (img > 127).astype(np.uint8)  # OCCUPY = 0, FREE = 255 (demo.cpp:103-106)
-            dist = cv2.distanceTransform(free, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
-        except ImportError:  # same exact Euclidean transform without OpenCV
-            from PIL import Image
-            from scipy.ndimage import distance_transform_edt
-            img = np.asarray(Image.open(png_path).convert("L"))
-            dist = distance_transform_edt(img > 127)
-        self.dist = dist.astype(np.float64) * RES
+    def __init__(self, png_path=_MAP_PNG, dist=None, res=RES):
+        self.res = res
+        if dist is None:
+            if not os.path.exists(png_path):
+                raise FileNotFoundError(png_path)
+            try:
+                import cv2
+                img = cv2.imread(png_path, cv2.IMREAD_GRAYSCALE)
+                free = (img > 127).astype(np.uint8)  # OCCUPY = 0, FREE = 255 (demo.cpp:103-106)
+                dist = cv2.distanceTransform(free, cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+            except ImportError:  # same exact Euclidean transform without OpenCV
+                from PIL import Image
+                from scipy.ndimage import distance_transform_edt
+                img = np.asarray(Image.open(png_path).convert("L"))
+                dist = distance_transform_edt(img > 127)
+            dist = dist.astype(np.float32) * np.float32(res)  # MatrixXf *= resolution (demo.cpp:113)
+        self.dist = np.ascontiguousarray(dist, dtype=np.float32)
         self.rows, self.cols = self.dist.shape
-        self.lx, self.ly = self.rows * RES, self.cols * RES
+        self.lx, self.ly = self.rows * res, self.cols * res
 
     def lookup(self, x, y):
-        """Map::getObstacleDistance, vectorised: bilinear between the four nearest cell centres."""
+        """Bilinear lookup for the walk below (the kernel has its own, pqp_bounds_core.cuh)."""
         x = np.asarray(x, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
-        fi = (self.lx / 2 - x) / RES - 0.5  # fractional row index
-        fj = (self.ly / 2 - y) / RES - 0.5
         inside = (np.abs(x) < self.lx / 2) & (np.abs(y) < self.ly / 2)
+        fi = (self.lx / 2 - np.where(inside, x, 0.0)) / self.res - 0.5
+        fj = (self.ly / 2 - np.where(inside, y, 0.0)) / self.res - 0.5
         i0 = np.clip(np.floor(fi).astype(np.int64), 0, self.rows - 2)
         j0 = np.clip(np.floor(fj).astype(np.int64), 0, self.cols - 2)
-        ti = np.clip(fi - i0, 0.0, 1.0)
-        tj = np.clip(fj - j0, 0.0, 1.0)
+        ti, tj = np.clip(fi - i0, 0.0, 1.0), np.clip(fj - j0, 0.0, 1.0)
         d = self.dist
         v = (d[i0, j0] * (1 - ti) * (1 - tj) + d[i0 + 1, j0] * ti * (1 - tj) +
              d[i0, j0 + 1] * (1 - ti) * tj + d[i0 + 1, j0 + 1] * ti * tj)
         return np.where(inside, v, 0.0)
 
 
-def _constrain(a):
-    return (a + math.pi) % (2 * math.pi) - math.pi
+def natural_spline_rows(s, x, y):
+    """Rows (abscissa; a, b, c, y of x(s); a, b, c, y of y(s)) in tk::spline's convention
+    f_i(h) = ((a_i h + b_i) h + c_i) h + y_i, incl. its right-end entries (spline.cpp:241-246)."""
+    from scipy.interpolate import CubicSpline
+    rows = [np.asarray(s, dtype=np.float64)]
+    for v in (x, y):
+        cs = CubicSpline(s, v, bc_type="natural")
+        k = len(s)
+        a, b, c = np.zeros(k), np.zeros(k), np.zeros(k)
+        a[:-1], b[:-1], c[:-1] = cs.c[0], cs.c[1], cs.c[2]
+        b[0] = 0.0  # natural end: the reference's first equation is 2 b0 = 0 exactly
+        c[-1] = float(cs(s[-1], 1))
+        rows += [a, b, c, np.asarray(v, dtype=np.float64)]
+    return np.stack(rows)
 
 
-def clearance(dmap, x, y, heading):
-    """ReferencePathImpl::getClearanceWithDirectionStrict (reference_path_impl.cpp:232-312),
-    vectorised over points. Returns (left = ub, right = lb)."""
-    x, y, heading = (np.asarray(v, dtype=np.float64) for v in (x, y, heading))
-    delta_s, search_radius = 0.3, 0.5
-    nstep = int(6.0 / delta_s)
-    la, ra = _constrain(heading + math.pi / 2), _constrain(heading - math.pi / 2)
-    ok = dmap.lookup(x, y) > search_radius
-
-    def march(angle):
-        s = np.zeros_like(x)
-        active = np.ones(x.shape, dtype=bool)
-        for _ in range(nstep):
-            s = np.where(active, s + delta_s, s)
-            c = dmap.lookup(x + s * np.cos(angle), y + s * np.sin(angle))
-            active &= ~(c < search_radius)
-        return s
-
-    right_s, left_s = march(ra), march(la)
-    left, right = left_s - delta_s, -(right_s - delta_s)
-    smaller = 0.05
-    act = np.ones(x.shape, dtype=bool)
-    for _ in range(1, int(delta_s / smaller)):  # refine forward (:272-283)
-        cand = np.where(act, left + smaller, left)
-        hit = dmap.lookup(x + cand * np.cos(la), y + cand * np.sin(la)) < search_radius
-        left = np.where(act & ~hit, cand, left)
-        act &= ~hit
-    act = np.ones(x.shape, dtype=bool)
-    for _ in range(1, int(delta_s / smaller)):  # (:284-295; negative bound x right-hand direction, as there)
-        cand = np.where(act, right - smaller, right)
-        hit = dmap.lookup(x + cand * np.cos(ra), y + cand * np.sin(ra)) < search_radius
-        right = np.where(act & ~hit, cand, right)
-        act &= ~hit
-    diff = CAR_WIDTH * 0.5 - search_radius
-    left, right = left - diff, right + diff
-    blocked = left < right
-    space = left - right
-    margin = np.minimum(SAFETY_MARGIN, np.maximum(0.0, (space - 0.2) / 2.0))
-    left, right = left - margin, right + margin
-    bad = ~ok | blocked
-    return np.where(bad, 0.0, left), np.where(bad, 0.0, right)
+def _eval(rows, s, which):
+    """value, first and second derivative of x(s) (which = 0) or y(s) (which = 1) inside the range."""
+    sx = rows[0]
+    a, b, c, y = rows[1 + 4 * which:5 + 4 * which]
+    idx = np.clip(np.searchsorted(sx, s, side="left") - 1, 0, len(sx) - 2)
+    h = s - sx[idx]
+    return (((a[idx] * h + b[idx]) * h + c[idx]) * h + y[idx], (3 * a[idx] * h + 2 * b[idx]) * h + c[idx],
+            6 * a[idx] * h + 2 * b[idx])
 
 
-class SplinePath:
-    """x(s), y(s) natural cubic splines (tk::spline defaults) + tools.cpp helpers."""
-
-    def __init__(self, s, x, y):
-        from scipy.interpolate import CubicSpline
-        self.xs, self.ys = CubicSpline(s, x, bc_type="natural"), CubicSpline(s, y, bc_type="natural")
-        self.max_s = float(s[-1])
-
-    def heading(self, s):  # tools.cpp:32-36
-        return np.arctan2(self.ys(s, 1), self.xs(s, 1))
-
-    def curvature(self, s):  # tools.cpp:38-44
-        dx, dy, ddx, ddy = self.xs(s, 1), self.ys(s, 1), self.xs(s, 2), self.ys(s, 2)
-        return (dx * ddy - dy * ddx) / np.power(dx * dx + dy * dy, 1.5)
-
-    def directional_projection(self, tx, ty, angle, hint_s):  # tools.cpp:156-189, vectorised
-        cur = np.minimum(np.asarray(hint_s, dtype=np.float64), self.max_s)
-        prev = cur.copy()
-        v1, v2 = np.sin(angle), -np.cos(angle)
-        act = np.ones(cur.shape, dtype=bool)
-        for _ in range(20):
-            xv, yv = self.xs(cur), self.ys(cur)
-            dx, dy, ddx, ddy = self.xs(cur, 1), self.ys(cur, 1), self.xs(cur, 2), self.ys(cur, 2)
-            p1 = v1 * (xv - tx) + v2 * (yv - ty)
-            p2 = v1 * dx + v2 * dy
-            h = p1 * (v1 * ddx + v2 * ddy) + p2 * p2
-            step = np.where(np.abs(h) > 1e-12, p1 * p2 / np.where(h == 0, 1.0, h), 0.0)
-            cur = np.where(act, cur - step, cur)
-            act &= ~(np.abs(cur - prev) < 1e-5)
-            prev = cur.copy()
-        cur = np.minimum(cur, self.max_s)
-        return self.xs(cur), self.ys(cur)
-
-
-def build_knots(path, n):
-    """buildReferenceFromSpline(0.15, 0.3): first n knots, or None if the spline is too short."""
+def reference_states(rows, n):
+    """buildReferenceFromSpline(0.15, 0.3) (reference_path_impl.cpp:314-338): the first n states as
+    (s, x, y, heading, curvature), or None when the spline is too short."""
+    max_s = float(rows[0][-1])
     s_list, s = [], 0.0
-    while s <= path.max_s and len(s_list) < n:
+    while s <= max_s and len(s_list) < n:
         s_list.append(s)
-        k = abs(float(path.curvature(s)))
+        _, dx, ddx = _eval(rows, s, 0)
+        _, dy, ddy = _eval(rows, s, 1)
+        k = abs(float((dx * ddy - dy * ddx) / math.pow(dx * dx + dy * dy, 1.5)))  # tools.cpp:38-44
         share = 1.0 if k > 0.2 else (0.0 if k < 0.08 else (k - 0.08) / 0.12)
         s += 0.3 - share * 0.15
     if len(s_list) < n:
         return None
     s = np.array(s_list)
-    return s, path.xs(s), path.ys(s), path.heading(s), path.curvature(s)
-
-
-def bounds_for(dmap, path, s, x, y, h):
-    """updateBoundsImproved (reference_path_impl.cpp:177-230) for all knots; returns
-    (f_lb, f_ub, r_lb, r_ub, c_lb, c_ub, blocked)."""
-    out = {}
-    for name, length in (("f", FRONT_LENGTH), ("r", REAR_LENGTH)):
-        ax, ay = x + length * np.cos(h), y + length * np.sin(h)
-        px, py = path.directional_projection(ax, ay, h + math.pi / 2, s + length)
-        ub, lb = clearance(dmap, px, py, h)
-        # offset of the projected anchor in the raw anchor's frame (global2Local(...).y)
-        off = -(px - ax) * np.sin(h) + (py - ay) * np.cos(h)
-        out[name] = (lb + off, ub + off)
-    cub, clb = clearance(dmap, x, y, h)
-    blocked = (np.abs(out["f"][1] - out["f"][0]) < 1e-6) | (np.abs(out["r"][1] - out["r"][0]) < 1e-6)
-    return out["f"][0], out["f"][1], out["r"][0], out["r"][1], clb, cub, blocked
+    x, dx, ddx = _eval(rows, s, 0)
+    y, dy, ddy = _eval(rows, s, 1)
+    return s, x, y, np.arctan2(dy, dx), (dx * ddy - dy * ddx) / np.power(dx * dx + dy * dy, 1.5)
 
 
 def _walk_free_line(dmap, rng, x0, y0, total, step=1.5, min_clear=1.6):
-    """Stand-in for the reference's hybrid-A* front end (out of scope): walk from
-    (x0, y0) in 1.5 m arcs, each time taking the curvature whose 6 m look-ahead keeps the most
-    clearance, and return control points (s, x, y) or None when the corridor closes."""
+    """Walk from (x0, y0) in 1.5 m arcs, each time taking the curvature whose 6 m look-ahead keeps
+    the most clearance; returns control points (s, x, y) or None when the corridor closes."""
     cand = np.linspace(-0.12, 0.12, 9)
     look = step * np.arange(1, 5)
     best_h, best_c = 0.0, -1.0
@@ -204,50 +138,70 @@ def _walk_free_line(dmap, rng, x0, y0, total, step=1.5, min_clear=1.6):
     return sc, xs, ys
 
 
-def make_instance(dmap, seed, n):
-    """One unblocked n-knot instance on the shared map (rejection sampling), as
-    (knots[9, n], inst[5], ref_xyh[3, n])."""
-    rng = np.random.default_rng(seed)
-    for _ in range(400):
-        x0 = rng.uniform(-dmap.lx / 2 + 5, dmap.lx / 2 - 5)
-        y0 = rng.uniform(-dmap.ly / 2 + 5, dmap.ly / 2 - 5)
-        if dmap.lookup(x0, y0) < 2.0:
-            continue
-        line = _walk_free_line(dmap, rng, x0, y0, 0.3 * n + 8.0)
-        if line is None:
-            continue
-        sc, xx, yy = line
-        path = SplinePath(sc, xx, yy)
-        kn = build_knots(path, n)
-        if kn is None:
-            continue
-        s, x, y, h, k = kn
-        flb, fub, rlb, rub, clb, cub, blocked = bounds_for(dmap, path, s, x, y, h)
-        if np.any(blocked) or np.any(fub - flb < 0.05) or np.any(rub - rlb < 0.05):
-            continue
-        knots = np.zeros((abi.NFIELDS, n))
-        knots[abi.F_S], knots[abi.F_KREF], knots[abi.F_K] = s, k, k
-        knots[abi.F_B0_LB], knots[abi.F_B0_UB] = flb, fub
-        knots[abi.F_B1_LB], knots[abi.F_B1_UB] = rlb, rub
-        inst = np.zeros(abi.NINST)
+class LineBatch:
+    """`batch` reference lines: what ReferencePathImpl holds before updateBoundsImproved — the
+    splines x_s_, y_s_ and reference_states_ — in the layout of include/pqp_bounds.h."""
+
+    def __init__(self, batch, n, k_max):
+        self.batch, self.n_max, self.k_max = batch, n, k_max
+        self.spline = np.zeros((batch, SPLINE_ROWS, k_max))
+        self.k = np.zeros(batch, dtype=np.int32)
+        self.states = np.zeros((batch, STATE_ROWS, n))
+        self.kref = np.zeros((batch, n))
+        self.n = np.full(batch, n, dtype=np.int32)
+        self.inst = np.zeros((batch, abi.NINST))
+
+    def spline_rows(self, b):
+        return self.spline[b, :, :int(self.k[b])]
+
+    def to_host_batch(self, bounds, n_valid=None):
+        """Solver input: knots from the states, the front/rear rows of `bounds[b][6][n]`;
+        n = n_valid (the reference cuts reference_states_ at the first blocked state)."""
+        knots = np.zeros((self.batch, abi.NFIELDS, self.n_max))
+        knots[:, abi.F_S] = self.states[:, 0]
+        knots[:, abi.F_KREF] = knots[:, abi.F_K] = self.kref
+        knots[:, abi.F_B0_LB:abi.F_B1_UB + 1] = bounds[:, 0:4]
+        n = self.n.copy() if n_valid is None else np.asarray(n_valid, dtype=np.int32).copy()
+        return abi.HostBatch(knots, self.inst.copy(), n)
+
+    @property
+    def ref_xyh(self):
+        return np.ascontiguousarray(self.states[:, 1:4])
+
+
+def make_lines(batch, n=120, first=0, cfg_id=2, dmap=None):
+    """Lines [first, first + batch) of the shared-map config; line i depends only on (cfg_id, i)."""
+    dmap = dmap or DistanceMap()
+    total = 0.3 * n + 8.0
+    lb = LineBatch(batch, n, int(math.ceil(total / 1.5)) + 1)
+    for b in range(batch):
+        rng = np.random.default_rng(cfg_id * 1_000_003 + first + b)
+        for _ in range(400):
+            x0 = rng.uniform(-dmap.lx / 2 + 5, dmap.lx / 2 - 5)
+            y0 = rng.uniform(-dmap.ly / 2 + 5, dmap.ly / 2 - 5)
+            if dmap.lookup(x0, y0) < 2.0:
+                continue
+            line = _walk_free_line(dmap, rng, x0, y0, total)
+            if line is None:
+                continue
+            rows = natural_spline_rows(*line)
+            st = reference_states(rows, n)
+            if st is None:
+                continue
+            break
+        else:
+            raise RuntimeError("no free reference line found for line %d" % (first + b))
+        k = rows.shape[1]
+        lb.spline[b, :, :k], lb.k[b] = rows, k
+        lb.spline[b, 0, k:] = rows[0, -1] + 1.0 + np.arange(lb.k_max - k)  # padding keeps abscissae increasing
+        lb.states[b] = np.stack(st[:4])
+        lb.kref[b] = st[4]
+        inst = lb.inst[b]
         inst[abi.I_L0] = rng.uniform(-0.3, 0.3)
         inst[abi.I_PSI0] = rng.uniform(-0.08, 0.08)
-        inst[abi.I_K0] = k[0]
+        inst[abi.I_K0] = st[4][0]
         inst[abi.I_EPSI_LO], inst[abi.I_EPSI_HI] = -abi.INFTY, abi.INFTY
         if rng.uniform() < 0.5:
             e = rng.uniform(-0.05, 0.05)
             inst[abi.I_EPSI_LO], inst[abi.I_EPSI_HI] = e - 0.087, e + 0.087
-        return knots, inst, np.stack((x, y, h))
-    raise RuntimeError("no free reference line found for seed %d" % seed)
-
-
-def make_batch(batch, n=120, first=0, cfg_id=2, with_ref=False, dmap=None):
-    """BASELINE configs[1]: `batch` paths of n knots through the shared obstacle map."""
-    dmap = dmap or DistanceMap()
-    knots = np.zeros((batch, abi.NFIELDS, n))
-    inst = np.zeros((batch, abi.NINST))
-    ref = np.zeros((batch, 3, n))
-    for b in range(batch):
-        knots[b], inst[b], ref[b] = make_instance(dmap, cfg_id * 1_000_003 + first + b, n)
-    hb = abi.HostBatch(knots, inst, np.full(batch, n, dtype=np.int32))
-    return (hb, ref) if with_ref else hb
+    return lb

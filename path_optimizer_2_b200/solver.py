@@ -33,13 +33,15 @@ class PqpError(RuntimeError):
 
 def build_library(force=False, verbose=False):
     """nvcc-compile the CUDA library in-tree for sm_100a (no GPU needed to compile)."""
-    srcs = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_kernel.cuh", "pqp_host_common.h")]
-    srcs.append(os.path.join(os.path.dirname(_PKG), "include", "pqp.h"))
+    root = os.path.dirname(_PKG)
+    cu = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_bounds.cu")]
+    deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh")]
+    deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h")]
     stale = not os.path.exists(LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in deps)
     if force or stale:
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-I", os.path.join(os.path.dirname(_PKG), "include"), "-o", LIB_PATH, srcs[0]]
+            "-I", os.path.join(root, "include"), "-o", LIB_PATH] + cu
         subprocess.check_call(cmd)
     return LIB_PATH
 

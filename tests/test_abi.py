@@ -28,6 +28,34 @@ def test_exports_every_declared_symbol(lib):
     assert lib.pqp_version() == 1
 
 
+def test_exports_every_declared_bounds_symbol(lib):
+    from path_optimizer_2_b200 import bounds
+    header = open(os.path.join(ROOT, "include", "pqp_bounds.h")).read()
+    declared = set(re.findall(r"\b(pqp_bounds_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(bounds.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    p = bounds.BoundsParams()
+    bounds._declare(lib).pqp_bounds_default_params(C.byref(p))
+    q = bounds.default_params()
+    for name, _ in bounds.BoundsParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+
+
+def test_bounds_fail_loudly_without_device(lib):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import numpy as np
+    from path_optimizer_2_b200 import bounds
+    with pytest.raises(solver.PqpError) as ei:
+        bounds.PathBounds(np.ones((4, 4), dtype=np.float32), 0.2)
+    assert ei.value.code == abi.PQP_E_NO_DEVICE
+
+
 def test_default_params_match_python_mirror(lib):
     p = abi.PqpParams()
     assert lib.pqp_default_params(C.byref(p)) == 0
