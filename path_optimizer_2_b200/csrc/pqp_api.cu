@@ -579,7 +579,14 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
 int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode, int B) {
     const int nmax = h->n_max;
     const size_t nvm = 6 * (size_t)nmax - 1, mm = 6 * (size_t)nmax + 2;
-    int nchunks = (B + 1023) / 1024;
+    // up to kStreams chunks of >= 256 instances: small batches (configs[1]: 1024) still overlap
+    // their copies with the solve, large ones (8192) move 1024 instances per chunk
+    static const int min_chunk = [] {
+        const char *e = getenv("PQP_STREAM_MIN_CHUNK");  // tuning knob, not part of the ABI
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 256;
+    }();
+    int nchunks = (B + min_chunk - 1) / min_chunk;
     if (nchunks > pqp_handle::kStreams) nchunks = pqp_handle::kStreams;
     const int per = (B + nchunks - 1) / nchunks;
     nchunks = (B + per - 1) / per;
@@ -661,7 +668,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         if (mode == 1 && (!h->solved || B != h->last_batch)) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
         h->host_inputs_resident = true;
         h->d_p_valid = in->p != nullptr;
-        if (h->use_tmem && B >= 2048) {
+        if (h->use_tmem && B >= 512) {
             const size_t nvm0 = 6 * (size_t)nmax - 1, mm0 = 6 * (size_t)nmax + 2;
             if (out->x_full && !h->d_xf) PQP_CUDA(h, dmalloc(&h->d_xf, (size_t)h->batch_max * nvm0));
             if (out->y_full && !h->d_yf) PQP_CUDA(h, dmalloc(&h->d_yf, (size_t)h->batch_max * mm0));

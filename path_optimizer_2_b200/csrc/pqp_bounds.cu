@@ -1,7 +1,7 @@
 // pqp_bounds.cu — clearance-bounds kernel and its C ABI (include/pqp_bounds.h).
 //
-// One thread per (path, reference state, anchor): adjacent threads work on the three anchors of
-// one state and on neighbouring states, so their ray-marches walk neighbouring map cells. The
+// One thread per (path, reference state, anchor); a warp = one anchor type of 32 consecutive
+// states, so its ray-marches walk neighbouring map cells in lock step. The
 // float distance layer (2 MB for the demo map) is read through the read-only path and stays in
 // the 126 MB L2; per state the kernel reads 32 B of state + its share of the spline and writes
 // 48 B of bounds - it is gather-latency bound, not HBM bound.
@@ -38,13 +38,16 @@ __global__ void init_n_valid_kernel(const int32_t *__restrict__ n, int32_t *__re
     }
 }
 
+// grid.x covers (path, state) pairs, grid.y the anchor: a warp handles one anchor type of 32
+// consecutive states (0.15-0.3 m apart), so its lanes run the same Newton / march phases over
+// neighbouring map cells.
 __global__ void __launch_bounds__(128) clearance_bounds_kernel(const BoundsArgs a) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)a.batch * a.n_max * 3;
+    const long long total = (long long)a.batch * a.n_max;
     if (t >= total) return;
-    const int anchor = (int)(t % 3);
-    const int i = (int)((t / 3) % a.n_max);
-    const int b = (int)(t / (3LL * a.n_max));
+    const int anchor = (int)blockIdx.y;
+    const int i = (int)(t % a.n_max);
+    const int b = (int)(t / a.n_max);
     int nb = a.n[b];
     nb = nb > a.n_max ? a.n_max : nb;
     if (i >= nb) return;
@@ -129,13 +132,13 @@ int launch(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_bounds_out *
     a.knots = out->knots;
     PQB_CUDA(h, cudaEventRecord(h->ev0, s));
     init_n_valid_kernel<<<(in->batch + 255) / 256, 256, 0, s>>>(in->n, out->n_valid, in->batch, in->n_max);
-    const long long total = (long long)in->batch * in->n_max * 3;
+    const long long total = (long long)in->batch * in->n_max;
     const long long blocks = (total + 127) / 128;
     if (blocks > 0x7fffffffLL) {
         h->err = "pqp_bounds: batch * n_max too large for one launch";
         return PQP_E_INVALID;
     }
-    clearance_bounds_kernel<<<(unsigned)blocks, 128, 0, s>>>(a);
+    clearance_bounds_kernel<<<dim3((unsigned)blocks, 3), 128, 0, s>>>(a);
     PQB_CUDA(h, cudaGetLastError());
     PQB_CUDA(h, cudaEventRecord(h->ev1, s));
     h->timed = true;
@@ -206,6 +209,7 @@ int pqp_bounds_create(const pqp_bounds_map *map, const pqp_bounds_params *params
     h->map.rows = map->rows;
     h->map.cols = map->cols;
     h->map.res = map->resolution;
+    h->map.inv_res = 1.0 / map->resolution;
     h->map.half_lx = 0.5 * map->rows * map->resolution;
     h->map.half_ly = 0.5 * map->cols * map->resolution;
     h->map.cx = map->center_x;

@@ -17,7 +17,7 @@ namespace pqb {
 struct MapView {
     const float *dist;  // [rows * cols]
     int rows, cols;
-    double res, half_lx, half_ly, cx, cy;
+    double res, inv_res, half_lx, half_ly, cx, cy;
 };
 
 struct Params {
@@ -38,8 +38,10 @@ struct SplineView {
 PQB_HD double map_distance(const MapView &m, double x, double y) {
     const double dx = x - m.cx, dy = y - m.cy;
     if (!(fabs(dx) < m.half_lx && fabs(dy) < m.half_ly)) return 0.0;
-    const double fi = (m.half_lx - dx) / m.res - 0.5;
-    const double fj = (m.half_ly - dy) / m.res - 0.5;
+    // (position - corner) / resolution as a multiplication: the interpolant is continuous across
+    // cell borders, so a last-bit difference in fi, fj cannot change the value beyond rounding
+    const double fi = (m.half_lx - dx) * m.inv_res - 0.5;
+    const double fj = (m.half_ly - dy) * m.inv_res - 0.5;
     int i0 = (int)floor(fi), j0 = (int)floor(fj);
     i0 = i0 < 0 ? 0 : (i0 > m.rows - 2 ? m.rows - 2 : i0);
     j0 = j0 < 0 ? 0 : (j0 > m.cols - 2 ? m.cols - 2 : j0);
@@ -89,7 +91,9 @@ PQB_HD void directional_projection(const SplineView &sp, double tx, double ty, d
                                    double hint_s, double &px, double &py) {
     hint_s = std_min(hint_s, max_s);
     double cur_s = hint_s, prev_s = hint_s;
-    const double v1 = sin(angle), v2 = -cos(angle);
+    double sa, ca;
+    sincos(angle, &sa, &ca);
+    const double v1 = sa, v2 = -ca;
     double x, y, dx, dy, ddx, ddy;
     for (int i = 0; i < 20; ++i) {
         spline_eval(sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, cur_s, x, dx, ddx);
@@ -123,7 +127,9 @@ PQB_HD void clearance(const MapView &m, const Params &P, double sx, double sy, d
     const int n = (int)(6.0 / delta_s);
     lb = ub = 0.0;
     if (!(map_distance(m, sx, sy) > search_radius)) return;
-    const double cl = cos(left_angle), sl = sin(left_angle), cr = cos(right_angle), sr = sin(right_angle);
+    double cl, sl, cr, sr;
+    sincos(left_angle, &sl, &cl);
+    sincos(right_angle, &sr, &cr);
     double right_s = 0.0;
     for (int j = 0; j != n; ++j) {
         right_s += delta_s;
@@ -173,7 +179,8 @@ PQB_HD void anchor_bounds(const MapView &m, const Params &P, const SplineView &s
         return;
     }
     const double len = anchor == 0 ? P.front_length : P.rear_length;
-    const double ch = cos(heading), sh = sin(heading);
+    double ch, sh;
+    sincos(heading, &sh, &ch);
     const double ax = x + len * ch, ay = y + len * sh;
     double px, py;
     directional_projection(sp, ax, ay, heading + M_PI_2, s + 5.0, s + len, px, py);

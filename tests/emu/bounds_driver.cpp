@@ -15,6 +15,7 @@ extern "C" int pqb_emu_compute(const pqp_bounds_map *map, const pqp_bounds_param
     m.rows = map->rows;
     m.cols = map->cols;
     m.res = map->resolution;
+    m.inv_res = 1.0 / map->resolution;
     m.half_lx = 0.5 * map->rows * map->resolution;
     m.half_ly = 0.5 * map->cols * map->resolution;
     m.cx = map->center_x;
