@@ -608,8 +608,9 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     sl.done = h->d_done;
     sl.host_done = h->d_hdone;
     sl.chunk_len = per;
-    int rc = run_device(h, &din, &dout, mode, sk, false, 0, false, h->d_flags, &sl);
-    if (rc) return rc;
+    // The chunk copies are queued BEFORE the launch: they are asynchronous (pinned buffers), so the
+    // kernel still overlaps them, and a tool that makes launches blocking (ncu serialises kernels)
+    // cannot leave the kernel waiting for copies the host has not issued yet.
     for (int c = 0; c < nchunks; ++c) {
         const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
         const size_t nb = (size_t)(hi - lo);
@@ -621,6 +622,8 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
         if (in->p) PQP_CUDA(h, cudaMemcpyAsync(h->d_p + lo, in->p + lo, nb * sizeof(int), cudaMemcpyHostToDevice, sc));
         PQP_CUDA(h, cudaMemsetAsync(h->d_ready + c, 1, sizeof(int), sc));  // "chunk c has landed"
     }
+    int rc = run_device(h, &din, &dout, mode, sk, false, 0, false, h->d_flags, &sl);
+    if (rc) return rc;
     h->host_inputs_resident = true;
     for (int c = 0; c < nchunks; ++c) {
         const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
