@@ -245,7 +245,7 @@ def run_reference(args, rank, world):
 
 def run_receding(args, rank, local_rank, world, dev):
     """BASELINE configs[4]: receding-horizon warm re-solves. One step =
-    one tick: advance the window by one knot (torch slicing on device tensors — plumbing),
+    one tick: advance the window by one knot (pqp_advance_window_device, one launch),
     re-linearise about the previous solution, warm re-solve with max_iter = 50 through
     pqp_resolve_device; x, z, y, rho stay resident in the handle between ticks."""
     import torch
@@ -283,12 +283,19 @@ def run_receding(args, rank, local_rank, world, dev):
 
     launch(d_knots, d_inst, False)  # tick 0: cold
     tick = 0
-    hold = []
+    ext_len = int(d_ext.shape[2])
+    stream = torch.cuda.current_stream().cuda_stream
+    bin_w = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+
+    def tick_device(t):
+        # window bookkeeping in one launch of the library's own kernel, in place: the previous
+        # tick's solve has consumed d_knots / d_inst (same stream), d_sol holds its result
+        sv.advance_window_device(B, ext_len, t, d_ext.data_ptr(), d_sol.data_ptr(), d_knots.data_ptr(),
+                                 d_inst.data_ptr(), stream=stream)
+
     for _ in range(args.warmup):
         tick += 1
-        d_knots, d_inst = synthetic.shift_window(d_ext, d_inst, d_sol, tick, n)
-        d_knots = d_knots.contiguous()
-        hold.append((d_knots, d_inst))
+        tick_device(tick)
         launch(d_knots, d_inst, True)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -301,12 +308,9 @@ def run_receding(args, rank, local_rank, world, dev):
     e0.record()
     for i in range(args.steps):
         tick += 1
-        d_knots, d_inst = synthetic.shift_window(d_ext, d_inst, d_sol, tick, n)
-        d_knots = d_knots.contiguous()
-        hold.append((d_knots, d_inst))  # keep the buffers alive until the kernels have run
+        tick_device(tick)
         kev[i][0].record()
-        bin_s = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream, warm=True)
+        sv.solve_device(bin_w, bout_s, stream=stream, warm=True)
         kev[i][1].record()
         if world > 1:
             sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)

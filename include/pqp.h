@@ -187,6 +187,16 @@ int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out 
 int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
                        void *stream);
 
+/* Receding-horizon bookkeeping between two pqp_resolve_device calls (the caller side of
+ * path_optimizer.cpp:153 when the plan is re-issued every tick, BASELINE configs[4]), one launch,
+ * device pointers, asynchronous on `stream`: knots[b][f][i] = ext_knots[b][f][tick + i] from an
+ * extended reference ext_knots[b][PQP_NFIELDS][ext_len], except the linearisation fields L, PSI, K,
+ * which take the previous solution shifted by one knot (sol[b][0..2][min(i + 1, n_max - 1)]);
+ * inst[b][L0, PSI0, K0] = the previous solution at knot 1. `sol` is the buffer of the last solve. */
+int pqp_advance_window_device(pqp_handle *h, int32_t batch, int32_t ext_len, int32_t tick,
+                              const double *ext_knots, const double *sol, double *knots, double *inst,
+                              void *stream);
+
 /* BaseSolver::getOptimizedPath (base_solver.cpp:263-288) for a batch, FP64, on device
  * pointers: ref_xyh[(b*3+f)*n_max+i] f=0:x 1:y 2:heading of the reference states;
  * sol as produced above; out_xyh same layout as ref_xyh (x, y, heading of the result). */

@@ -291,6 +291,36 @@ __global__ void relinearise_kernel(int batch, int n_max, const double *__restric
     knots[k + (size_t)PQP_F_K * n_max + i] = sol[s + 2 * (size_t)n_max + i];
 }
 
+// Receding-horizon tick (BASELINE configs[4]): the planning window advances by `tick` knots along
+// an extended reference ext[b][9][ext_len]; the new linearisation point is the previous solution
+// shifted by one knot (last knot repeated) and the new x0 is the previous solution at knot 1.
+__global__ void advance_window_kernel(int batch, int n_max, int ext_len, int tick, const double *__restrict__ ext,
+                                      const double *__restrict__ sol, double *__restrict__ knots,
+                                      double *__restrict__ inst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * n_max) return;
+    const int b = idx / n_max, i = idx - b * n_max;
+    const double *e = ext + (size_t)b * PQP_NFIELDS * ext_len + tick + i;
+    const double *sb = sol + (size_t)b * 4 * n_max;
+    double *k = knots + (size_t)b * PQP_NFIELDS * n_max + i;
+    const int src = i + 1 < n_max ? i + 1 : n_max - 1;
+#pragma unroll
+    for (int f = 0; f < PQP_NFIELDS; ++f) {
+        double v = e[(size_t)f * ext_len];
+        if (f == PQP_F_L) v = sb[src];
+        if (f == PQP_F_PSI) v = sb[n_max + src];
+        if (f == PQP_F_K) v = sb[2 * (size_t)n_max + src];
+        k[(size_t)f * n_max] = v;
+    }
+    if (i == 0) {
+        double *ib = inst + (size_t)b * PQP_NINST;
+        const int one = n_max > 1 ? 1 : 0;
+        ib[PQP_I_L0] = sb[one];
+        ib[PQP_I_PSI0] = sb[n_max + one];
+        ib[PQP_I_K0] = sb[2 * (size_t)n_max + one];
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ handle
@@ -938,6 +968,20 @@ int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *
     PQP_CUDA(h, cudaSetDevice(h->device));
     const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
     frenet_to_cartesian_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, n, ref_xyh, sol, out_xyh);
+    PQP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return PQP_OK;
+}
+
+int pqp_advance_window_device(pqp_handle *h, int32_t batch, int32_t ext_len, int32_t tick, const double *ext_knots,
+                              const double *sol, double *knots, double *inst, void *stream) {
+    if (!h) return PQP_E_INVALID;
+    if (!ext_knots || !sol || !knots || !inst || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
+    if (tick < 0 || tick + h->n_max > ext_len) return fail(h, PQP_E_INVALID, "window [tick, tick + n_max) leaves the extended reference");
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
+    advance_window_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, ext_len, tick, ext_knots, sol,
+                                                                                   knots, inst);
     PQP_CUDA(h, cudaGetLastError());
     h->launches++;
     return PQP_OK;

@@ -192,6 +192,48 @@ def test_receding_horizon_ticks(solver_mod):
     sv.close()
 
 
+def test_advance_window_on_device_matches_host_bookkeeping(solver_mod):
+    """pqp_advance_window_device (one launch) against synthetic.shift_window (numpy), and a
+    device-resident receding-horizon loop against the host-API loop: bit-identical."""
+    import torch
+    params = abi.default_params(max_iter=50, reserved=4)  # no FP64 escalation: host and device paths run the same kernel
+    n, ticks, batch = 120, 4, 6
+    ext = synthetic.make_batch(5, batch, n + ticks)
+    hb = abi.HostBatch(ext.knots[:, :, :n].copy(), ext.inst, np.full(batch, n, dtype=np.int32))
+    sv_h = solver_mod.PathQpSolver(params, n_max=n, batch_max=batch)
+    sv_d = solver_mod.PathQpSolver(params, n_max=n, batch_max=batch)
+    res = sv_h.solve(hb)
+    dev = torch.device("cuda", 0)
+    d_ext = torch.from_numpy(ext.knots).to(dev)
+    d_knots, d_inst = torch.from_numpy(hb.knots).to(dev), torch.from_numpy(hb.inst).to(dev)
+    d_n = torch.from_numpy(hb.n).to(dev)
+    d_sol = torch.zeros((batch, 4, n), dtype=torch.float64, device=dev)
+    d_cost = torch.zeros(batch, dtype=torch.float64, device=dev)
+    d_status, d_iters = (torch.zeros(batch, dtype=torch.int32, device=dev) for _ in range(2))
+    bi = abi.PqpBatchIn(batch, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+    bo = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(), None, None, None, None)
+    stream = torch.cuda.current_stream().cuda_stream
+    sv_d.solve_device(bi, bo, stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sol.cpu().numpy(), res.sol)
+    inst, sol = hb.inst, res.sol
+    for t in range(1, ticks + 1):
+        knots, inst = synthetic.shift_window(ext.knots, inst, sol, t, n)
+        sv_d.advance_window_device(batch, n + ticks, t, d_ext.data_ptr(), d_sol.data_ptr(), d_knots.data_ptr(),
+                                   d_inst.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_knots.cpu().numpy(), knots) and np.array_equal(d_inst.cpu().numpy(), inst)
+        sol = sv_h.resolve(abi.HostBatch(knots, inst, hb.n)).sol
+        sv_d.solve_device(bi, bo, stream=stream, warm=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_sol.cpu().numpy(), sol)
+    with pytest.raises(solver_mod.PqpError):  # window leaves the extended reference
+        sv_d.advance_window_device(batch, n + ticks, ticks + 1, d_ext.data_ptr(), d_sol.data_ptr(), d_knots.data_ptr(),
+                                   d_inst.data_ptr(), stream=stream)
+    sv_h.close()
+    sv_d.close()
+
+
 @pytest.mark.parametrize("n", [20, 120, 240])
 def test_tensor_memory_policy_matches_shared_memory_policy(solver_mod, n):
     """params.reserved bit 3 / bit 4: the same solver code with its per-stage state in tensor
