@@ -67,33 +67,42 @@ def make_workload(args, batch, first, device=None):
 
 
 def bounds_stage(args, dmap, lines, device):
-    """SURVEY.md §8 row f-1 on the GPU: bounds for the whole batch through the C ABI, timed with
-    CUDA events on the launching stream (device-resident inputs), next to the oracle on a sample."""
+    """SURVEY.md §8 rows f-2 + f-1 on the GPU: reference states from the splines, then the
+    clearance bounds, for the whole batch through the C ABI with device-resident buffers; timed
+    with CUDA events on the launching stream and checked against the oracle on a sample."""
     import torch
     from oracle import bounds_oracle
     from path_optimizer_2_b200 import bounds
     dev = torch.device("cuda", device)
     pbn = bounds.PathBounds(dmap.dist, dmap.res, device=device)
     B, n = lines.batch, lines.n_max
-    d_states, d_spline = torch.from_numpy(lines.states).to(dev), torch.from_numpy(lines.spline).to(dev)
-    d_n, d_k = torch.from_numpy(lines.n).to(dev), torch.from_numpy(lines.k).to(dev)
+    max_s = np.array([lines.spline_rows(b)[0, -1] for b in range(B)])
+    d_spline, d_k, d_maxs = (torch.from_numpy(v).to(dev) for v in (lines.spline, lines.k, max_s))
+    d_states = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
+    d_curv = torch.zeros((B, n), dtype=torch.float64, device=dev)
+    d_n, d_nv = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2))
     d_bounds = torch.zeros((B, 6, n), dtype=torch.float64, device=dev)
-    d_nv = torch.zeros(B, dtype=torch.int32, device=dev)
+    si = bounds.StatesIn(B, n, lines.k_max, d_spline.data_ptr(), d_k.data_ptr(), d_maxs.data_ptr(), 0.15, 0.3, 1)
+    so = bounds.StatesOut(d_states.data_ptr(), d_curv.data_ptr(), d_n.data_ptr(), None, None)
     bi = bounds.BoundsIn(B, n, lines.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
     bo = bounds.BoundsOut(d_bounds.data_ptr(), d_nv.data_ptr(), None)
     stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(3):
-        pbn.compute_device(bi, bo, stream=stream)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
-    e0.record()
-    for _ in range(reps):
-        pbn.compute_device(bi, bo, stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    bnd, nv = d_bounds.cpu().numpy(), d_nv.cpu().numpy()
+    ms = {}
+    for name, fn in (("states", lambda: pbn.build_states_device(si, so, stream=stream)),
+                     ("bounds", lambda: pbn.compute_device(bi, bo, stream=stream))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms[name] = e0.elapsed_time(e1) / reps
+    states, bnd, nv = d_states.cpu().numpy(), d_bounds.cpu().numpy(), d_nv.cpu().numpy()
+    assert np.max(np.abs(states - lines.states)) < 1e-9, "reference-states kernel disagrees with the workload's states"
     sample = min(B, 64)
     t0 = time.perf_counter()
     worst = 0.0
@@ -107,11 +116,13 @@ def bounds_stage(args, dmap, lines, device):
     # algorithmic bytes per state: 32 B state + 48 B bounds + the path's share of its spline
     alg = B * n * 80 + lines.spline.nbytes + dmap.dist.nbytes
     return {"bounds": bnd, "n_valid": nv,
-            "bounds_kernel": {"kernel": "clearance_bounds_kernel", "ms_per_batch": ms, "states_per_s": B * n / (ms * 1e-3),
-                              "rays_per_s": 3 * B * n / (ms * 1e-3), "algorithmic_bytes": int(alg),
-                              "achieved_GBps": alg / (ms * 1e-3) / 1e9, "gpu_launches_per_batch": 2,
-                              "max_abs_diff_vs_oracle": worst,
-                              "cpu_oracle_states_per_s": sample * n / cpu_s, "cpu_oracle_sample": sample}}
+            "bounds_kernel": {"kernel": "clearance_bounds_kernel", "ms_per_batch": ms["bounds"],
+                              "states_per_s": B * n / (ms["bounds"] * 1e-3), "rays_per_s": 3 * B * n / (ms["bounds"] * 1e-3),
+                              "algorithmic_bytes": int(alg), "achieved_GBps": alg / (ms["bounds"] * 1e-3) / 1e9,
+                              "gpu_launches_per_batch": 2, "max_abs_diff_vs_oracle": worst,
+                              "cpu_oracle_states_per_s": sample * n / cpu_s, "cpu_oracle_sample": sample},
+            "states_kernel": {"kernel": "reference_states_kernel", "ms_per_batch": ms["states"],
+                              "states_per_s": B * n / (ms["states"] * 1e-3)}}
 
 
 def algorithmic_bytes(n, warm=False):

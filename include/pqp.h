@@ -187,6 +187,12 @@ int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out 
 int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
                        void *stream);
 
+/* The caller's step between solve and updateProblemFormulationAndSolve (path_optimizer.cpp:153
+ * passes the first result back as the new input path): copy sol[b][0..2][i] (l, psi, kappa) into
+ * the linearisation fields PQP_F_L, PQP_F_PSI, PQP_F_K of knots[b][PQP_NFIELDS][n_max]. Device
+ * pointers, asynchronous on `stream`. (pqp_resolve with in = NULL does the same internally.) */
+int pqp_relinearise_device(pqp_handle *h, int32_t batch, const double *sol, double *knots, void *stream);
+
 /* Receding-horizon bookkeeping between two pqp_resolve_device calls (the caller side of
  * path_optimizer.cpp:153 when the plan is re-issued every tick, BASELINE configs[4]), one launch,
  * device pointers, asynchronous on `stream`: knots[b][f][i] = ext_knots[b][f][tick + i] from an

@@ -66,6 +66,30 @@ typedef struct pqp_bounds_out {
                             front bounds in PQP_F_B0_LB/UB and the rear bounds in PQP_F_B1_LB/UB */
 } pqp_bounds_out;
 
+/* ReferencePathImpl::buildReferenceFromSpline (reference_path_impl.cpp:314-338):
+ * walk each spline from s = 0 to max_s with the curvature-dependent step (delta_s_larger where
+ * |k| < 0.08, delta_s_smaller where |k| > 0.2, linear in between; fixed delta_s_larger when
+ * dynamic_segmentation = 0) and emit x, y, heading (tools.cpp:32-36), curvature (:38-44), s. */
+typedef struct pqp_states_in {
+    int32_t batch, n_max, k_max;
+    const double *spline;   /* [b][PQP_SPLINE_ROWS][k_max] */
+    const int32_t *k;       /* [b] */
+    const double *max_s;    /* [b] max_s_ of the reference path */
+    double delta_s_smaller; /* 0.15 (path_optimizer.cpp: buildReferenceFromSpline(0.15, 0.3)) */
+    double delta_s_larger;  /* 0.3 */
+    int32_t dynamic_segmentation; /* FLAGS_enable_dynamic_segmentation (default true) */
+} pqp_states_in;
+
+typedef struct pqp_states_out {
+    double *states;     /* [b][PQP_STATE_ROWS][n_max]: s, x, y, heading */
+    double *curvature;  /* [b][n_max] */
+    int32_t *n;         /* [b] states written = min(total, n_max) */
+    int32_t *total;     /* optional [b]: states the reference would emit (no n_max cap) */
+    double *knots;      /* optional solver knot block [b][PQP_NFIELDS][n_max]: receives PQP_F_S,
+                           PQP_F_KREF and the first linearisation point of path_optimizer.cpp:128-137
+                           (PQP_F_L = PQP_F_PSI = 0, PQP_F_K = curvature) */
+} pqp_states_out;
+
 typedef struct pqp_bounds_handle pqp_bounds_handle;
 
 void pqp_bounds_default_params(pqp_bounds_params *p);
@@ -77,6 +101,10 @@ int pqp_bounds_compute(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_
 /* Device buffers; asynchronous on `stream` (a cudaStream_t passed as void*). */
 int pqp_bounds_compute_device(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_bounds_out *out,
                               void *stream);
+/* buildReferenceFromSpline for a batch: host buffers (synchronous) / device buffers (async). */
+int pqp_bounds_build_states(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out);
+int pqp_bounds_build_states_device(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out,
+                                   void *stream);
 int pqp_bounds_last_kernel_ms(pqp_bounds_handle *h, float *ms);
 const char *pqp_bounds_last_error(pqp_bounds_handle *h);
 

@@ -14,6 +14,7 @@ Follows, relative to /root/reference/:
   directional_projection  src/tools/tools.cpp:156-189
   clearance               src/data_struct/reference_path_impl.cpp:232-312
   update_bounds           src/data_struct/reference_path_impl.cpp:177-230
+  build_states            src/data_struct/reference_path_impl.cpp:314-338, src/tools/tools.cpp:32-44
 """
 import math
 
@@ -211,3 +212,23 @@ def update_bounds(dist, res, spline_rows, s, x, y, heading, *, front_length=FRON
         blocked = (np.abs(out[1] - out[0]) < epsilon) | (np.abs(out[3] - out[2]) < epsilon)
     hits = np.nonzero(blocked)[0]
     return out, int(hits[0]) if len(hits) else len(s)
+
+
+def build_states(spline_rows, max_s, ds_small=0.15, ds_large=0.3, dynamic=True):
+    """buildReferenceFromSpline for one path: (s, x, y, heading, curvature) arrays, uncapped."""
+    sp = Spline2(spline_rows)
+    out = []
+    tmp_s = 0.0
+    while tmp_s <= max_s:
+        x, dx, ddx = (float(v) for v in sp.x(tmp_s))
+        y, dy, ddy = (float(v) for v in sp.y(tmp_s))
+        h = math.atan2(dy, dx)
+        k = (dx * ddy - dy * ddx) / math.pow(math.pow(dx, 2) + math.pow(dy, 2), 1.5)
+        out.append((tmp_s, x, y, h, k))
+        if dynamic:
+            ak = abs(k)
+            share = 1.0 if ak > 0.2 else (0.0 if ak < 0.08 else (ak - 0.08) / (0.2 - 0.08))
+            tmp_s += ds_large - share * (ds_large - ds_small)
+        else:
+            tmp_s += ds_large
+    return tuple(np.array(c) for c in zip(*out))

@@ -17,7 +17,8 @@ SPLINE_ROWS, STATE_ROWS, BOUND_ROWS = 9, 4, 6
 
 EXPORTED_SYMBOLS = [
     "pqp_bounds_default_params", "pqp_bounds_create", "pqp_bounds_destroy", "pqp_bounds_compute",
-    "pqp_bounds_compute_device", "pqp_bounds_last_kernel_ms", "pqp_bounds_last_error",
+    "pqp_bounds_compute_device", "pqp_bounds_build_states", "pqp_bounds_build_states_device",
+    "pqp_bounds_last_kernel_ms", "pqp_bounds_last_error",
 ]
 
 
@@ -40,6 +41,17 @@ class BoundsOut(C.Structure):
     _fields_ = [("bounds", C.c_void_p), ("n_valid", C.c_void_p), ("knots", C.c_void_p)]
 
 
+class StatesIn(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_max", C.c_int32), ("k_max", C.c_int32), ("spline", C.c_void_p),
+                ("k", C.c_void_p), ("max_s", C.c_void_p), ("delta_s_smaller", C.c_double),
+                ("delta_s_larger", C.c_double), ("dynamic_segmentation", C.c_int32)]
+
+
+class StatesOut(C.Structure):
+    _fields_ = [("states", C.c_void_p), ("curvature", C.c_void_p), ("n", C.c_void_p), ("total", C.c_void_p),
+                ("knots", C.c_void_p)]
+
+
 def default_params(**overrides):
     p = BoundsParams(3.9, -1.0, 2.0, 0.3, 1e-6)
     for k, v in overrides.items():
@@ -58,6 +70,8 @@ def _declare(L):
     L.pqp_bounds_destroy.restype = None
     L.pqp_bounds_compute.argtypes = [vp, C.POINTER(BoundsIn), C.POINTER(BoundsOut)]
     L.pqp_bounds_compute_device.argtypes = [vp, C.POINTER(BoundsIn), C.POINTER(BoundsOut), vp]
+    L.pqp_bounds_build_states.argtypes = [vp, C.POINTER(StatesIn), C.POINTER(StatesOut)]
+    L.pqp_bounds_build_states_device.argtypes = [vp, C.POINTER(StatesIn), C.POINTER(StatesOut), vp]
     L.pqp_bounds_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.pqp_bounds_last_error.argtypes = [vp]
     L.pqp_bounds_last_error.restype = C.c_char_p
@@ -112,6 +126,28 @@ class PathBounds:
         """Raw device pointers (e.g. torch tensors' data_ptr()), asynchronous on `stream`."""
         self._check(self.L.pqp_bounds_compute_device(self.h, C.byref(bin_struct), C.byref(bout_struct),
                                                      C.c_void_p(stream)))
+
+    def build_states(self, spline, k, max_s, n_max, *, ds_small=0.15, ds_large=0.3, dynamic=True, knots=None):
+        """buildReferenceFromSpline for a batch (host buffers): -> (states[b][4][n_max],
+        curvature[b][n_max], n[b], total[b]); `knots` (solver block) is filled in place."""
+        spline = np.ascontiguousarray(spline, dtype=np.float64)
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        max_s = np.ascontiguousarray(max_s, dtype=np.float64)
+        B = spline.shape[0]
+        states, curv = np.zeros((B, STATE_ROWS, n_max)), np.zeros((B, n_max))
+        n, total = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        if knots is not None:
+            assert knots.flags.c_contiguous and knots.dtype == np.float64 and knots.shape == (B, abi.NFIELDS, n_max)
+        si = StatesIn(B, n_max, spline.shape[2], spline.ctypes.data, k.ctypes.data, max_s.ctypes.data, ds_small, ds_large,
+                      1 if dynamic else 0)
+        so = StatesOut(states.ctypes.data, curv.ctypes.data, n.ctypes.data, total.ctypes.data,
+                       knots.ctypes.data if knots is not None else None)
+        self._check(self.L.pqp_bounds_build_states(self.h, C.byref(si), C.byref(so)))
+        return states, curv, n, total
+
+    def build_states_device(self, sin_struct: StatesIn, sout_struct: StatesOut, stream=0):
+        self._check(self.L.pqp_bounds_build_states_device(self.h, C.byref(sin_struct), C.byref(sout_struct),
+                                                          C.c_void_p(stream)))
 
     @property
     def last_kernel_ms(self):

@@ -973,6 +973,17 @@ int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *
     return PQP_OK;
 }
 
+int pqp_relinearise_device(pqp_handle *h, int32_t batch, const double *sol, double *knots, void *stream) {
+    if (!h) return PQP_E_INVALID;
+    if (!sol || !knots || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
+    PQP_CUDA(h, cudaSetDevice(h->device));
+    const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
+    relinearise_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, sol, knots);
+    PQP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return PQP_OK;
+}
+
 int pqp_advance_window_device(pqp_handle *h, int32_t batch, int32_t ext_len, int32_t tick, const double *ext_knots,
                               const double *sol, double *knots, double *inst, void *stream) {
     if (!h) return PQP_E_INVALID;

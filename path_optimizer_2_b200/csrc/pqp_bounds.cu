@@ -76,6 +76,45 @@ __global__ void __launch_bounds__(128) clearance_bounds_kernel(const BoundsArgs 
     }
 }
 
+struct StatesArgs {
+    int batch, n_max, k_max;
+    const double *spline;
+    const int32_t *k;
+    const double *max_s;
+    double ds_small, ds_large;
+    int dynamic;
+    double *states, *curvature, *knots;
+    int32_t *n, *total;
+};
+
+// one thread per path: the walk is sequential in s (each step depends on the curvature at the last)
+__global__ void __launch_bounds__(64) reference_states_kernel(const StatesArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    const double *sb = a.spline + (size_t)b * PQP_SPLINE_ROWS * a.k_max;
+    pqb::SplineView sp;
+    sp.sx = sb;
+    sp.xa = sb + 1 * (size_t)a.k_max; sp.xb = sb + 2 * (size_t)a.k_max; sp.xc = sb + 3 * (size_t)a.k_max; sp.xy = sb + 4 * (size_t)a.k_max;
+    sp.ya = sb + 5 * (size_t)a.k_max; sp.yb = sb + 6 * (size_t)a.k_max; sp.yc = sb + 7 * (size_t)a.k_max; sp.yy = sb + 8 * (size_t)a.k_max;
+    sp.k = a.k[b] > a.k_max ? a.k_max : a.k[b];
+    double *st = a.states + (size_t)b * PQP_STATE_ROWS * a.n_max;
+    double *cv = a.curvature + (size_t)b * a.n_max;
+    const int total = pqb::build_states(sp, a.max_s[b], a.ds_small, a.ds_large, a.dynamic != 0, a.n_max, st, cv);
+    const int nb = total < a.n_max ? total : a.n_max;
+    a.n[b] = nb;
+    if (a.total) a.total[b] = total;
+    if (a.knots) {
+        double *kb = a.knots + (size_t)b * PQP_NFIELDS * a.n_max;
+        for (int i = 0; i < nb; ++i) {
+            kb[(size_t)PQP_F_S * a.n_max + i] = st[i];
+            kb[(size_t)PQP_F_KREF * a.n_max + i] = cv[i];
+            kb[(size_t)PQP_F_L * a.n_max + i] = 0.0;
+            kb[(size_t)PQP_F_PSI * a.n_max + i] = 0.0;
+            kb[(size_t)PQP_F_K * a.n_max + i] = cv[i];
+        }
+    }
+}
+
 }  // namespace
 
 struct pqp_bounds_handle {
@@ -88,6 +127,9 @@ struct pqp_bounds_handle {
     // staging for the host-pointer call (grown on demand)
     double *d_states = nullptr, *d_spline = nullptr, *d_bounds = nullptr, *d_knots = nullptr;
     int32_t *d_n = nullptr, *d_k = nullptr, *d_nvalid = nullptr;
+    double *d_maxs = nullptr, *d_curv = nullptr;
+    int32_t *d_total = nullptr;
+    size_t cap_maxs = 0, cap_curv = 0, cap_total = 0;
     size_t cap_states = 0, cap_bounds = 0, cap_spline = 0, cap_knots = 0, cap_n = 0, cap_k = 0, cap_nvalid = 0;
     bool timed = false;
     std::string err;
@@ -229,6 +271,9 @@ void pqp_bounds_destroy(pqp_bounds_handle *h) {
     cudaFree(h->d_n);
     cudaFree(h->d_k);
     cudaFree(h->d_nvalid);
+    cudaFree(h->d_maxs);
+    cudaFree(h->d_curv);
+    cudaFree(h->d_total);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -274,6 +319,90 @@ int pqp_bounds_compute(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_
     if (rc != PQP_OK) return rc;
     PQB_CUDA(h, cudaMemcpyAsync(out->bounds, h->d_bounds, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
     PQB_CUDA(h, cudaMemcpyAsync(out->n_valid, h->d_nvalid, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (nk) PQB_CUDA(h, cudaMemcpyAsync(out->knots, h->d_knots, nk * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PQB_CUDA(h, cudaStreamSynchronize(s));
+    return PQP_OK;
+}
+
+static int validate_states(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out) {
+    if (!h) return PQP_E_INVALID;
+    if (!in || !out || in->batch <= 0 || in->n_max <= 0 || in->k_max < 3 || !in->spline || !in->k || !in->max_s ||
+        !out->states || !out->curvature || !out->n || !(in->delta_s_larger > 0.0) || !(in->delta_s_smaller > 0.0) ||
+        in->delta_s_smaller > in->delta_s_larger) {
+        h->err = "pqp_bounds_build_states: null pointer, non-positive size, or 0 < delta_s_smaller <= delta_s_larger violated";
+        return PQP_E_INVALID;
+    }
+    return PQP_OK;
+}
+
+static int launch_states(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out, cudaStream_t s) {
+    StatesArgs a;
+    a.batch = in->batch;
+    a.n_max = in->n_max;
+    a.k_max = in->k_max;
+    a.spline = in->spline;
+    a.k = in->k;
+    a.max_s = in->max_s;
+    a.ds_small = in->delta_s_smaller;
+    a.ds_large = in->delta_s_larger;
+    a.dynamic = in->dynamic_segmentation;
+    a.states = out->states;
+    a.curvature = out->curvature;
+    a.knots = out->knots;
+    a.n = out->n;
+    a.total = out->total;
+    PQB_CUDA(h, cudaEventRecord(h->ev0, s));
+    reference_states_kernel<<<(in->batch + 63) / 64, 64, 0, s>>>(a);
+    PQB_CUDA(h, cudaGetLastError());
+    PQB_CUDA(h, cudaEventRecord(h->ev1, s));
+    h->timed = true;
+    return PQP_OK;
+}
+
+int pqp_bounds_build_states_device(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out, void *stream) {
+    int rc = validate_states(h, in, out);
+    if (rc != PQP_OK) return rc;
+    PQB_CUDA(h, cudaSetDevice(h->device));
+    return launch_states(h, in, out, static_cast<cudaStream_t>(stream));
+}
+
+int pqp_bounds_build_states(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out) {
+    int rc = validate_states(h, in, out);
+    if (rc != PQP_OK) return rc;
+    PQB_CUDA(h, cudaSetDevice(h->device));
+    const size_t B = in->batch, ns = B * PQP_STATE_ROWS * in->n_max, nsp = B * PQP_SPLINE_ROWS * in->k_max;
+    const size_t nc = B * in->n_max, nk = out->knots ? B * PQP_NFIELDS * in->n_max : 0;
+    PQB_CUDA(h, grow(&h->d_states, &h->cap_states, ns));
+    PQB_CUDA(h, grow(&h->d_curv, &h->cap_curv, nc));
+    PQB_CUDA(h, grow(&h->d_spline, &h->cap_spline, nsp));
+    if (nk) PQB_CUDA(h, grow(&h->d_knots, &h->cap_knots, nk));
+    PQB_CUDA(h, grow(&h->d_n, &h->cap_n, B));
+    PQB_CUDA(h, grow(&h->d_k, &h->cap_k, B));
+    PQB_CUDA(h, grow(&h->d_total, &h->cap_total, B));
+    PQB_CUDA(h, grow(&h->d_maxs, &h->cap_maxs, B));
+    cudaStream_t s = h->stream;
+    PQB_CUDA(h, cudaMemcpyAsync(h->d_spline, in->spline, nsp * sizeof(double), cudaMemcpyHostToDevice, s));
+    PQB_CUDA(h, cudaMemcpyAsync(h->d_k, in->k, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    PQB_CUDA(h, cudaMemcpyAsync(h->d_maxs, in->max_s, B * sizeof(double), cudaMemcpyHostToDevice, s));
+    PQB_CUDA(h, cudaMemsetAsync(h->d_states, 0, ns * sizeof(double), s));
+    PQB_CUDA(h, cudaMemsetAsync(h->d_curv, 0, nc * sizeof(double), s));
+    if (nk) PQB_CUDA(h, cudaMemcpyAsync(h->d_knots, out->knots, nk * sizeof(double), cudaMemcpyHostToDevice, s));
+    pqp_states_in din = *in;
+    din.spline = h->d_spline;
+    din.k = h->d_k;
+    din.max_s = h->d_maxs;
+    pqp_states_out dout;
+    dout.states = h->d_states;
+    dout.curvature = h->d_curv;
+    dout.n = h->d_n;
+    dout.total = h->d_total;
+    dout.knots = nk ? h->d_knots : nullptr;
+    rc = launch_states(h, &din, &dout, s);
+    if (rc != PQP_OK) return rc;
+    PQB_CUDA(h, cudaMemcpyAsync(out->states, h->d_states, ns * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PQB_CUDA(h, cudaMemcpyAsync(out->curvature, h->d_curv, nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PQB_CUDA(h, cudaMemcpyAsync(out->n, h->d_n, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out->total) PQB_CUDA(h, cudaMemcpyAsync(out->total, h->d_total, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (nk) PQB_CUDA(h, cudaMemcpyAsync(out->knots, h->d_knots, nk * sizeof(double), cudaMemcpyDeviceToHost, s));
     PQB_CUDA(h, cudaStreamSynchronize(s));
     return PQP_OK;

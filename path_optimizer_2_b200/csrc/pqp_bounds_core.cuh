@@ -192,4 +192,38 @@ PQB_HD void anchor_bounds(const MapView &m, const Params &P, const SplineView &s
     ub += offset;
 }
 
+// ReferencePathImpl::buildReferenceFromSpline (reference_path_impl.cpp:314-338) for one path:
+// writes at most n_max states (rows s, x, y, heading with stride n_max, curvature separately) and
+// returns the number of states the reference would emit.
+PQB_HD int build_states(const SplineView &sp, double max_s, double ds_small, double ds_large, bool dynamic, int n_max,
+                        double *st, double *curv) {
+    const double large_k = 0.2, small_k = 0.08;
+    double tmp_s = 0.0;
+    int count = 0;
+    while (tmp_s <= max_s) {
+        double x, y, dx, dy, ddx, ddy;
+        spline_eval(sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, tmp_s, x, dx, ddx);
+        spline_eval(sp.sx, sp.ya, sp.yb, sp.yc, sp.yy, sp.k, tmp_s, y, dy, ddy);
+        const double h = atan2(dy, dx);                                             // tools.cpp:32-36
+        const double k = (dx * ddy - dy * ddx) / pow(pow(dx, 2) + pow(dy, 2), 1.5);  // tools.cpp:38-44
+        if (count < n_max) {
+            st[count] = tmp_s;
+            st[n_max + count] = x;
+            st[2 * n_max + count] = y;
+            st[3 * n_max + count] = h;
+            curv[count] = k;
+        }
+        ++count;
+        if (dynamic) {
+            const double ak = fabs(k);
+            const double k_share = ak > large_k ? 1.0 : (ak < small_k ? 0.0 : (ak - small_k) / (large_k - small_k));
+            tmp_s += ds_large - k_share * (ds_large - ds_small);
+        } else {
+            tmp_s += ds_large;
+        }
+        if (count > (1 << 24)) break;  // a non-positive step would never terminate
+    }
+    return count;
+}
+
 }  // namespace pqb

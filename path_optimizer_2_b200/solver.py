@@ -65,6 +65,7 @@ def load_library():
     L.pqp_resolve.argtypes = [vp, pin, pout]
     L.pqp_solve_device.argtypes = [vp, pin, pout, vp]
     L.pqp_resolve_device.argtypes = [vp, pin, pout, vp]
+    L.pqp_relinearise_device.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.pqp_advance_window_device.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     L.pqp_frenet_to_cartesian_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     L.pqp_frenet_to_cartesian.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
@@ -79,7 +80,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "pqp_version", "pqp_default_params", "pqp_create", "pqp_destroy", "pqp_solve", "pqp_resolve",
-    "pqp_solve_device", "pqp_resolve_device", "pqp_advance_window_device", "pqp_frenet_to_cartesian_device",
+    "pqp_solve_device", "pqp_resolve_device", "pqp_relinearise_device", "pqp_advance_window_device",
+    "pqp_frenet_to_cartesian_device",
     "pqp_frenet_to_cartesian", "pqp_last_kernel_ms", "pqp_launch_count", "pqp_kernel_info",
     "pqp_last_error",
 ]
@@ -143,6 +145,10 @@ class PathQpSolver:
         self._check(self.L.pqp_frenet_to_cartesian(self.h, len(n), n.ctypes.data, ref.ctypes.data,
                                                    sol.ctypes.data, out.ctypes.data))
         return out
+
+    def relinearise_device(self, batch, sol_ptr, knots_ptr, stream=0):
+        """sol -> linearisation fields of the knot block, on the device (pqp_relinearise_device)."""
+        self._check(self.L.pqp_relinearise_device(self.h, batch, sol_ptr, knots_ptr, C.c_void_p(stream)))
 
     def advance_window_device(self, batch, ext_len, tick, ext_ptr, sol_ptr, knots_ptr, inst_ptr, stream=0):
         """Receding-horizon tick bookkeeping on the device (pqp_advance_window_device)."""

@@ -25,6 +25,7 @@ def lib():
         _lib = C.CDLL(_LIB)
         _lib.pqb_emu_compute.argtypes = [C.POINTER(pb.BoundsMap), C.POINTER(pb.BoundsParams), C.POINTER(pb.BoundsIn),
                                          C.POINTER(pb.BoundsOut)]
+        _lib.pqb_emu_build_states.argtypes = [C.POINTER(pb.StatesIn), C.POINTER(pb.StatesOut)]
     return _lib
 
 
@@ -43,3 +44,17 @@ def compute(dist, res, states, n, spline, k, *, params=None, center=(0.0, 0.0), 
     bo = pb.BoundsOut(out.ctypes.data, n_valid.ctypes.data, knots.ctypes.data if knots is not None else None)
     assert lib().pqb_emu_compute(C.byref(m), C.byref(p), C.byref(bi), C.byref(bo)) == 0
     return out, n_valid
+
+
+def build_states(spline, k, max_s, n_max, *, ds_small=0.15, ds_large=0.3, dynamic=True):
+    spline = np.ascontiguousarray(spline, dtype=np.float64)
+    k = np.ascontiguousarray(k, dtype=np.int32)
+    max_s = np.ascontiguousarray(max_s, dtype=np.float64)
+    B = spline.shape[0]
+    states, curv = np.zeros((B, 4, n_max)), np.zeros((B, n_max))
+    n, total = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    si = pb.StatesIn(B, n_max, spline.shape[2], spline.ctypes.data, k.ctypes.data, max_s.ctypes.data, ds_small, ds_large,
+                     1 if dynamic else 0)
+    so = pb.StatesOut(states.ctypes.data, curv.ctypes.data, n.ctypes.data, total.ctypes.data, None)
+    assert lib().pqb_emu_build_states(C.byref(si), C.byref(so)) == 0
+    return states, curv, n, total

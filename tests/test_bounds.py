@@ -176,6 +176,26 @@ def test_ragged_batch_and_padding(dmap, lines):
     assert np.array_equal(eb[0, :, :37], full[0, :, :37]) and np.all(eb[0, :, 37:] == 0.0)
 
 
+def test_reference_states_from_spline(lines):
+    """buildReferenceFromSpline: the kernel's source on the host against the oracle
+    walk and against the workload generator's own states."""
+    max_s = np.array([lines.spline_rows(b)[0, -1] for b in range(lines.batch)])
+    st, cv, n, total = bounds_emu.build_states(lines.spline, lines.k, max_s, lines.n_max)
+    assert np.all(n == lines.n_max) and np.all(total > lines.n_max)
+    assert np.max(np.abs(st - lines.states)) < 1e-9 and np.max(np.abs(cv - lines.kref)) < 1e-9
+    for b in range(0, lines.batch, 5):
+        os_, ox, oy, oh, ok = bo.build_states(lines.spline_rows(b), max_s[b])
+        assert len(os_) == total[b]
+        m = lines.n_max
+        assert np.max(np.abs(np.stack((os_, ox, oy, oh))[:, :m] - st[b])) < 1e-9 and np.max(np.abs(ok[:m] - cv[b])) < 1e-9
+    # a short spline ends before n_max: n = total < n_max, the rest stays zero; fixed step without
+    # dynamic segmentation; a spline whose max_s is an exact multiple of the step includes s = max_s
+    short = np.array([7.5] * lines.batch)
+    st2, cv2, n2, total2 = bounds_emu.build_states(lines.spline, lines.k, short, lines.n_max, dynamic=False)
+    assert np.all(n2 == 26) and np.all(total2 == 26) and np.all(st2[:, :, 26:] == 0.0)
+    assert np.allclose(st2[0, 0, :26], 0.3 * np.arange(26), atol=1e-12)
+
+
 def test_lines_are_deterministic(dmap):
     a = sharedmap.make_lines(4, 60, dmap=dmap)
     b = sharedmap.make_lines(2, 60, first=2, dmap=dmap)
@@ -233,6 +253,30 @@ def test_gpu_bounds_match_oracle(dmap, lines):
 
 
 @pytest.mark.gpu
+def test_gpu_reference_states_match_oracle(dmap, lines):
+    from path_optimizer_2_b200 import bounds
+    pbn = bounds.PathBounds(dmap.dist, dmap.res)
+    max_s = np.array([lines.spline_rows(b)[0, -1] for b in range(lines.batch)])
+    knots = np.full((lines.batch, abi.NFIELDS, lines.n_max), 7.0)
+    st, cv, n, total = pbn.build_states(lines.spline, lines.k, max_s, lines.n_max, knots=knots)
+    est, ecv, en, etotal = bounds_emu.build_states(lines.spline, lines.k, max_s, lines.n_max)
+    assert np.array_equal(n, en) and np.array_equal(total, etotal)
+    assert np.max(np.abs(st - est)) < 1e-9 and np.max(np.abs(cv - ecv)) < 1e-9
+    for b in range(0, lines.batch, 5):
+        os_, ox, oy, oh, ok = bo.build_states(lines.spline_rows(b), max_s[b])
+        assert len(os_) == total[b]
+        assert np.max(np.abs(np.stack((os_, ox, oy, oh))[:, :lines.n_max] - st[b])) < 1e-9
+    assert np.array_equal(knots[:, abi.F_S], st[:, 0]) and np.array_equal(knots[:, abi.F_KREF], cv)
+    assert np.array_equal(knots[:, abi.F_K], cv) and np.all(knots[:, abi.F_L] == 0.0) and np.all(knots[:, abi.F_B0_LB] == 7.0)
+    st2, _, n2, total2 = pbn.build_states(lines.spline, lines.k, np.full(lines.batch, 7.5), lines.n_max, dynamic=False)
+    assert np.all(n2 == 26) and np.all(total2 == 26) and np.all(st2[:, :, 26:] == 0.0)
+    from path_optimizer_2_b200 import solver
+    with pytest.raises(solver.PqpError):
+        pbn.build_states(lines.spline, lines.k, max_s, lines.n_max, ds_small=0.4, ds_large=0.3)
+    pbn.close()
+
+
+@pytest.mark.gpu
 def test_gpu_blocked_path_and_errors():
     from path_optimizer_2_b200 import bounds, solver
     dm = pinch_map(gap=1.6)
@@ -252,35 +296,74 @@ def test_gpu_blocked_path_and_errors():
 
 @pytest.mark.gpu
 def test_gpu_map_to_path_pipeline(dmap):
-    """BASELINE configs[0] (one path) and a slice of configs[1]: map -> clearance bounds (device
-    pointers, written straight into the solver's knot block) -> solve, through the C ABI."""
+    """BASELINE configs[0] (one path) and a slice of configs[1], device-resident from the splines to
+    the second solve: buildReferenceFromSpline -> updateBoundsImproved -> BaseSolver::solve ->
+    re-linearise -> updateProblemFormulationAndSolve (path_optimizer.cpp:124-161), all through the
+    C ABI with device pointers; each stage is checked against its oracle."""
     import torch
     from path_optimizer_2_b200 import bounds, solver
     params = abi.default_params()
     pbn = bounds.PathBounds(dmap.dist, dmap.res)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
     for batch in (1, 48):
-        ln = sharedmap.make_lines(batch, 120, dmap=dmap)
-        hb0 = ln.to_host_batch(np.zeros((batch, 6, 120)))
-        dev = torch.device("cuda", 0)
-        d_states, d_spline = torch.from_numpy(ln.states).to(dev), torch.from_numpy(ln.spline).to(dev)
-        d_n, d_k = torch.from_numpy(ln.n).to(dev), torch.from_numpy(ln.k).to(dev)
-        d_knots = torch.from_numpy(hb0.knots).to(dev)
-        d_bounds = torch.zeros((batch, 6, 120), dtype=torch.float64, device=dev)
-        d_nv = torch.zeros(batch, dtype=torch.int32, device=dev)
-        bi = bounds.BoundsIn(batch, 120, ln.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
+        n = 120
+        ln = sharedmap.make_lines(batch, n, dmap=dmap)
+        max_s = np.array([ln.spline_rows(b)[0, -1] for b in range(batch)])
+        d_spline, d_k, d_maxs = (torch.from_numpy(v).to(dev) for v in (ln.spline, ln.k, max_s))
+        d_inst = torch.from_numpy(ln.inst).to(dev)
+        d_states = torch.zeros((batch, 4, n), dtype=torch.float64, device=dev)
+        d_curv = torch.zeros((batch, n), dtype=torch.float64, device=dev)
+        d_knots = torch.zeros((batch, abi.NFIELDS, n), dtype=torch.float64, device=dev)
+        d_bounds = torch.zeros((batch, 6, n), dtype=torch.float64, device=dev)
+        d_n, d_nv = (torch.zeros(batch, dtype=torch.int32, device=dev) for _ in range(2))
+        d_sol = torch.zeros((batch, 4, n), dtype=torch.float64, device=dev)
+        d_sol2 = torch.zeros((batch, 4, n), dtype=torch.float64, device=dev)
+        d_cost = torch.zeros(batch, dtype=torch.float64, device=dev)
+        d_status, d_iters, d_status2, d_iters2 = (torch.zeros(batch, dtype=torch.int32, device=dev) for _ in range(4))
+        sv = solver.PathQpSolver(params, n_max=n, batch_max=batch)
+        si = bounds.StatesIn(batch, n, ln.k_max, d_spline.data_ptr(), d_k.data_ptr(), d_maxs.data_ptr(), 0.15, 0.3, 1)
+        so = bounds.StatesOut(d_states.data_ptr(), d_curv.data_ptr(), d_n.data_ptr(), None, d_knots.data_ptr())
+        bi = bounds.BoundsIn(batch, n, ln.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
         bout = bounds.BoundsOut(d_bounds.data_ptr(), d_nv.data_ptr(), d_knots.data_ptr())
-        pbn.compute_device(bi, bout, stream=torch.cuda.current_stream().cuda_stream)
+        qi = abi.PqpBatchIn(batch, n, d_knots.data_ptr(), d_inst.data_ptr(), d_nv.data_ptr(), None)
+        qo = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(), None, None, None, None)
+        qo2 = abi.PqpBatchOut(d_sol2.data_ptr(), d_cost.data_ptr(), d_status2.data_ptr(), d_iters2.data_ptr(), None, None, None, None)
+        pbn.build_states_device(si, so, stream=stream)
+        pbn.compute_device(bi, bout, stream=stream)
+        sv.solve_device(qi, qo, stream=stream)
+        hb1 = None
         torch.cuda.synchronize()
-        hb = abi.HostBatch(d_knots.cpu().numpy(), ln.inst.copy(), d_nv.cpu().numpy())
-        assert np.array_equal(hb.n, ln.n)
-        sv = solver.PathQpSolver(params, n_max=120, batch_max=batch)
-        res = sv.solve(hb, full=True)
+        hb1 = abi.HostBatch(d_knots.cpu().numpy(), ln.inst.copy(), d_nv.cpu().numpy())
+        sv.relinearise_device(batch, d_sol.data_ptr(), d_knots.data_ptr(), stream=stream)
+        sv.solve_device(qi, qo2, stream=stream, warm=True)
+        torch.cuda.synchronize()
+        # stage oracles: states and bounds ...
+        assert np.array_equal(hb1.n, ln.n) and np.max(np.abs(d_states.cpu().numpy() - ln.states)) < 1e-9
+        gb = d_bounds.cpu().numpy()
+        for b in range(0, batch, 7):
+            ob, onv = bo.update_bounds(dmap.dist, dmap.res, ln.spline_rows(b), *ln.states[b])
+            assert onv == hb1.n[b]
+            _assert_bounds_close(gb[b], ob, "pipeline line %d" % b)
+        assert np.array_equal(hb1.knots[:, abi.F_B0_LB:abi.F_B1_UB + 1], gb[:, 0:4])
+        # ... first solve against the oracle, second solve against the oracle re-linearised about it
+        sol1, sol2 = d_sol.cpu().numpy(), d_sol2.cpu().numpy()
+        st1, st2 = d_status.cpu().numpy(), d_status2.cpu().numpy()
+        res_h = sv.solve(hb1, full=True)  # host API on the same inputs: full iterates for the parity check
+        assert np.array_equal(res_h.sol, sol1) and np.array_equal(res_h.status, st1)
+        hb2 = hb1.with_linearisation(sol1)
+        assert np.array_equal(d_knots.cpu().numpy(), hb2.knots)
+        res_h2 = sv.resolve(hb2, full=True)
+        assert np.array_equal(res_h2.sol, sol2) and np.array_equal(res_h2.status, st2)
         for b in range(0, batch, 3):
-            s = parity.oracle_reference(params, hb, b)
-            parity.check_instance(params, hb, res, b, oracle_solver=s, label="sharedmap gpu")
-        ok = res.status == abi.PQP_SOLVED
+            s = parity.oracle_reference(params, hb1, b)
+            parity.check_instance(params, hb1, res_h, b, oracle_solver=s, label="sharedmap gpu")
+            if s.status == abi.PQP_SOLVED and st1[b] == abi.PQP_SOLVED:
+                s2 = parity.oracle_reference(params, hb1, b, warm_from=sol1[b][:3, :int(hb1.n[b])])
+                parity.check_instance(params, hb2, res_h2, b, oracle_solver=s2, label="sharedmap gpu warm")
+        ok = st2 == abi.PQP_SOLVED
         assert ok.mean() > 0.9
-        xy = sv.frenet_to_cartesian(hb.n, ln.ref_xyh, res.sol)  # the optimised path stays in free space
+        xy = sv.frenet_to_cartesian(hb1.n, ln.ref_xyh, sol2)  # the optimised path stays in free space
         assert np.all(dmap.lookup(xy[ok, 0], xy[ok, 1]) > 0.5)
         sv.close()
     pbn.close()
