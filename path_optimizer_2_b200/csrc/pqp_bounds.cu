@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(64) reference_states_kernel(const StatesArgs a
     sp.k = a.k[b] > a.k_max ? a.k_max : a.k[b];
     double *st = a.states + (size_t)b * PQP_STATE_ROWS * a.n_max;
     double *cv = a.curvature + (size_t)b * a.n_max;
-    const int total = pqb::build_states(sp, a.max_s[b], a.ds_small, a.ds_large, a.dynamic != 0, a.n_max, st, cv);
+    const int total = pqb::build_states(sp, a.max_s[b], a.ds_small, a.ds_large, a.dynamic != 0, a.n_max, a.total != nullptr, st, cv);
     const int nb = total < a.n_max ? total : a.n_max;
     a.n[b] = nb;
     if (a.total) a.total[b] = total;

@@ -54,18 +54,35 @@ PQB_HD double map_distance(const MapView &m, double x, double y) {
     return d00 * (1.0 - ti) * (1.0 - tj) + d10 * ti * (1.0 - tj) + d01 * (1.0 - ti) * tj + d11 * ti * tj;
 }
 
-// tk::spline::operator() and deriv(1|2) in one pass (src/tools/spline.cpp:252-330): segment
-// index = lower_bound - 1 clamped at 0; quadratic extrapolation left and right with the
-// reference's own coefficients (incl. its left second derivative 2 b0 h).
-PQB_HD void spline_eval(const double *sx, const double *a, const double *b, const double *c, const double *y, int k,
-                        double s, double &v, double &d1, double &d2) {
+// Segment index of tk::spline::operator() / deriv (src/tools/spline.cpp:252-258): lower_bound - 1
+// clamped at 0, i.e. the last abscissa strictly below s (0 if there is none, also for NaN).
+PQB_HD int seg_index(const double *sx, int k, double s) {
     int lo = 0, hi = k;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (sx[mid] < s) lo = mid + 1;
         else hi = mid;
     }
-    const int idx = lo - 1 < 0 ? 0 : lo - 1;
+    return lo - 1 < 0 ? 0 : lo - 1;
+}
+
+// The same index reached by walking from a nearby one (the previous Newton iterate / the previous
+// state of the walk): one or two loads instead of a dependent binary-search chain.
+PQB_HD int seg_index_from(const double *sx, int k, double s, int hint) {
+    int j = hint < 0 ? 0 : (hint > k - 1 ? k - 1 : hint);
+    if (sx[j] < s) {
+        while (j + 1 < k && sx[j + 1] < s) ++j;
+    } else {
+        while (j > 0 && !(sx[j] < s)) --j;
+    }
+    return j;
+}
+
+// operator() and deriv(1|2) of one spline at s, given the segment index (spline.cpp:259-330):
+// quadratic extrapolation left and right with the reference's own coefficients (incl. its left
+// second derivative 2 b0 h).
+PQB_HD void spline_eval_at(int idx, const double *sx, const double *a, const double *b, const double *c, const double *y,
+                           int k, double s, double &v, double &d1, double &d2) {
     const double h = s - sx[idx];
     if (s < sx[0]) {
         const double b0 = b[0], c0 = c[0];
@@ -83,6 +100,13 @@ PQB_HD void spline_eval(const double *sx, const double *a, const double *b, cons
     }
 }
 
+// x(s), y(s) and their first two derivatives: the two splines share their abscissae, so one index
+PQB_HD void path_eval(const SplineView &sp, int idx, double s, double &x, double &dx, double &ddx, double &y, double &dy,
+                      double &ddy) {
+    spline_eval_at(idx, sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, s, x, dx, ddx);
+    spline_eval_at(idx, sp.sx, sp.ya, sp.yb, sp.yc, sp.yy, sp.k, s, y, dy, ddy);
+}
+
 PQB_HD double std_min(double a, double b) { return (b < a) ? b : a; }  // std::min, NaN behaviour included
 
 // getDirectionalProjectionByNewton (src/tools/tools.cpp:156-189): foot point of the line through
@@ -95,20 +119,21 @@ PQB_HD void directional_projection(const SplineView &sp, double tx, double ty, d
     sincos(angle, &sa, &ca);
     const double v1 = sa, v2 = -ca;
     double x, y, dx, dy, ddx, ddy;
+    int idx = seg_index(sp.sx, sp.k, cur_s);
     for (int i = 0; i < 20; ++i) {
-        spline_eval(sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, cur_s, x, dx, ddx);
-        spline_eval(sp.sx, sp.ya, sp.yb, sp.yc, sp.yy, sp.k, cur_s, y, dy, ddy);
+        path_eval(sp, idx, cur_s, x, dx, ddx, y, dy, ddy);
         const double p1 = v1 * (x - tx) + v2 * (y - ty);
         const double p2 = v1 * dx + v2 * dy;
         const double j = p1 * p2;
         const double h = p1 * (v1 * ddx + v2 * ddy) + p2 * p2;
         cur_s -= j / h;
+        idx = seg_index_from(sp.sx, sp.k, cur_s, idx);
         if (fabs(cur_s - prev_s) < 1e-5) break;
         prev_s = cur_s;
     }
     cur_s = std_min(cur_s, max_s);
-    spline_eval(sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, cur_s, px, dx, ddx);
-    spline_eval(sp.sx, sp.ya, sp.yb, sp.yc, sp.yy, sp.k, cur_s, py, dy, ddy);
+    idx = seg_index_from(sp.sx, sp.k, cur_s, idx);
+    path_eval(sp, idx, cur_s, px, dx, ddx, py, dy, ddy);
 }
 
 PQB_HD double constrain_angle(double a) {  // include/tools/tools.hpp:25-35 (recursion unrolled, bounded)
@@ -194,16 +219,17 @@ PQB_HD void anchor_bounds(const MapView &m, const Params &P, const SplineView &s
 
 // ReferencePathImpl::buildReferenceFromSpline (reference_path_impl.cpp:314-338) for one path:
 // writes at most n_max states (rows s, x, y, heading with stride n_max, curvature separately) and
-// returns the number of states the reference would emit.
+// returns the number of states the reference would emit (count_all) or min(that, n_max).
 PQB_HD int build_states(const SplineView &sp, double max_s, double ds_small, double ds_large, bool dynamic, int n_max,
-                        double *st, double *curv) {
+                        bool count_all, double *st, double *curv) {
     const double large_k = 0.2, small_k = 0.08;
     double tmp_s = 0.0;
-    int count = 0;
+    int count = 0, idx = 0;
     while (tmp_s <= max_s) {
+        if (count >= n_max && !count_all) break;
         double x, y, dx, dy, ddx, ddy;
-        spline_eval(sp.sx, sp.xa, sp.xb, sp.xc, sp.xy, sp.k, tmp_s, x, dx, ddx);
-        spline_eval(sp.sx, sp.ya, sp.yb, sp.yc, sp.yy, sp.k, tmp_s, y, dy, ddy);
+        idx = seg_index_from(sp.sx, sp.k, tmp_s, idx);
+        path_eval(sp, idx, tmp_s, x, dx, ddx, y, dy, ddy);
         const double h = atan2(dy, dx);                                             // tools.cpp:32-36
         const double k = (dx * ddy - dy * ddx) / pow(pow(dx, 2) + pow(dy, 2), 1.5);  // tools.cpp:38-44
         if (count < n_max) {

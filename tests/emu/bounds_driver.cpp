@@ -57,7 +57,7 @@ extern "C" int pqb_emu_build_states(const pqp_states_in *in, const pqp_states_ou
         pqb::SplineView sp{sb, sb + k_max, sb + 2 * k_max, sb + 3 * k_max, sb + 4 * k_max,
                            sb + 5 * k_max, sb + 6 * k_max, sb + 7 * k_max, sb + 8 * k_max, in->k[b]};
         const int total = pqb::build_states(sp, in->max_s[b], in->delta_s_smaller, in->delta_s_larger,
-                                            in->dynamic_segmentation != 0, n_max,
+                                            in->dynamic_segmentation != 0, n_max, out->total != nullptr,
                                             out->states + (size_t)b * PQP_STATE_ROWS * n_max, out->curvature + (size_t)b * n_max);
         out->n[b] = total < n_max ? total : n_max;
         if (out->total) out->total[b] = total;
