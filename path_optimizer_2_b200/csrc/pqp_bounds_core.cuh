@@ -224,14 +224,39 @@ PQB_HD int build_states(const SplineView &sp, double max_s, double ds_small, dou
                         bool count_all, double *st, double *curv) {
     const double large_k = 0.2, small_k = 0.08;
     double tmp_s = 0.0;
-    int count = 0, idx = 0;
+    int count = 0, idx = 0, cached = -1;
+    // coefficients of the current segment stay in registers: the walk crosses a segment border
+    // only every few steps, so most steps touch no memory
+    double x0 = 0.0, x1 = 0.0, xa = 0.0, xb = 0.0, xc = 0.0, xy = 0.0, ya = 0.0, yb = 0.0, yc = 0.0, yy = 0.0;
+    const double s_first = sp.sx[0], s_last = sp.sx[sp.k - 1];
     while (tmp_s <= max_s) {
         if (count >= n_max && !count_all) break;
         double x, y, dx, dy, ddx, ddy;
-        idx = seg_index_from(sp.sx, sp.k, tmp_s, idx);
-        path_eval(sp, idx, tmp_s, x, dx, ddx, y, dy, ddy);
+        // still strictly above the cached segment's start and not above its end: same index
+        if (!(cached >= 0 && x0 < tmp_s && !(x1 < tmp_s))) idx = seg_index_from(sp.sx, sp.k, tmp_s, idx);
+        if (tmp_s < s_first || tmp_s > s_last) {
+            path_eval(sp, idx, tmp_s, x, dx, ddx, y, dy, ddy);  // extrapolation (spline.cpp:262-268)
+        } else {
+            if (idx != cached) {
+                cached = idx;
+                x0 = sp.sx[idx];
+                x1 = idx + 1 < sp.k ? sp.sx[idx + 1] : HUGE_VAL;
+                xa = sp.xa[idx]; xb = sp.xb[idx]; xc = sp.xc[idx]; xy = sp.xy[idx];
+                ya = sp.ya[idx]; yb = sp.yb[idx]; yc = sp.yc[idx]; yy = sp.yy[idx];
+            }
+            const double h = tmp_s - x0;
+            x = ((xa * h + xb) * h + xc) * h + xy;
+            dx = (3.0 * xa * h + 2.0 * xb) * h + xc;
+            ddx = 6.0 * xa * h + 2.0 * xb;
+            y = ((ya * h + yb) * h + yc) * h + yy;
+            dy = (3.0 * ya * h + 2.0 * yb) * h + yc;
+            ddy = 6.0 * ya * h + 2.0 * yb;
+        }
         const double h = atan2(dy, dx);                                             // tools.cpp:32-36
-        const double k = (dx * ddy - dy * ddx) / pow(pow(dx, 2) + pow(dy, 2), 1.5);  // tools.cpp:38-44
+        // tools.cpp:38-44: pow(pow(dx, 2) + pow(dy, 2), 1.5), written with products and a square
+        // root (each within 1 ulp of the pow form; CUDA's pow itself is only 2-ulp accurate)
+        const double sq = dx * dx + dy * dy;
+        const double k = (dx * ddy - dy * ddx) / (sq * sqrt(sq));
         if (count < n_max) {
             st[count] = tmp_s;
             st[n_max + count] = x;
