@@ -112,6 +112,7 @@ def bounds_stage(args, dmap, lines, device):
         worst = max(worst, float(d[d < 0.04].max()))
         assert onv == nv[b], "bounds kernel and oracle cut path %d differently" % b
     cpu_s = time.perf_counter() - t0
+    plan = plan_pipeline(args, pbn, lines, d_spline, d_k, d_maxs, device)
     pbn.close()
     # algorithmic bytes per state: 32 B state + 48 B bounds + the path's share of its spline
     alg = B * n * 80 + lines.spline.nbytes + dmap.dist.nbytes
@@ -122,7 +123,56 @@ def bounds_stage(args, dmap, lines, device):
                               "gpu_launches_per_batch": 2, "max_abs_diff_vs_oracle": worst,
                               "cpu_oracle_states_per_s": sample * n / cpu_s, "cpu_oracle_sample": sample},
             "states_kernel": {"kernel": "reference_states_kernel", "ms_per_batch": ms["states"],
-                              "states_per_s": B * n / (ms["states"] * 1e-3)}}
+                              "states_per_s": B * n / (ms["states"] * 1e-3)},
+            "plan_pipeline": plan}
+
+
+def plan_pipeline(args, pbn, lines, d_spline, d_k, d_maxs, device):
+    """The reference's whole PathOptimizer::optimizePath sequence (path_optimizer.cpp:124-161) for the
+    batch, device-resident through the C ABI: reference states from the splines -> clearance bounds
+    -> BaseSolver::solve -> re-linearise -> updateProblemFormulationAndSolve. One plan = two solves."""
+    import torch
+    from path_optimizer_2_b200 import bounds, solver
+    dev = torch.device("cuda", device)
+    B, n = lines.batch, lines.n_max
+    f64 = dict(dtype=torch.float64, device=dev)
+    d_inst = torch.from_numpy(lines.inst).to(dev)
+    d_states, d_curv = torch.zeros((B, 4, n), **f64), torch.zeros((B, n), **f64)
+    d_knots, d_bounds = torch.zeros((B, abi.NFIELDS, n), **f64), torch.zeros((B, 6, n), **f64)
+    d_sol, d_cost = torch.zeros((B, 4, n), **f64), torch.zeros(B, **f64)
+    d_n, d_nv, d_status, d_iters = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(4))
+    sv = solver.PathQpSolver(abi.default_params(reserved=args.option_bits), n_max=n, batch_max=B, device=device)
+    si = bounds.StatesIn(B, n, lines.k_max, d_spline.data_ptr(), d_k.data_ptr(), d_maxs.data_ptr(), 0.15, 0.3, 1)
+    so = bounds.StatesOut(d_states.data_ptr(), d_curv.data_ptr(), d_n.data_ptr(), None, d_knots.data_ptr())
+    bi = bounds.BoundsIn(B, n, lines.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
+    bo = bounds.BoundsOut(d_bounds.data_ptr(), d_nv.data_ptr(), d_knots.data_ptr())
+    qi = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_nv.data_ptr(), None)
+    qo = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(), None, None, None, None)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def plan():
+        pbn.build_states_device(si, so, stream=stream)
+        pbn.compute_device(bi, bo, stream=stream)
+        sv.solve_device(qi, qo, stream=stream)
+        sv.relinearise_device(B, d_sol.data_ptr(), d_knots.data_ptr(), stream=stream)
+        sv.solve_device(qi, qo, stream=stream, warm=True)
+
+    for _ in range(3):
+        plan()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    status, iters2 = d_status.cpu().numpy(), d_iters.cpu().numpy()
+    sv.close()
+    return {"what": "states -> bounds -> solve -> relinearise -> warm re-solve, device-resident (PathOptimizer::optimizePath)",
+            "ms_per_batch": ms, "plans_per_s": B / (ms * 1e-3), "launches_per_plan": 8,
+            "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)), "mean_second_solve_iters": float(np.mean(iters2))}
 
 
 def algorithmic_bytes(n, warm=False):
