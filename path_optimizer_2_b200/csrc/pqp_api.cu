@@ -429,7 +429,15 @@ cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t
     switch (chunk) {
         case 1: return launch_tmem<1>(ka, s, sm_count);
         case 2: return launch_tmem<2>(ka, s, sm_count);
-        case 4: return launch_tmem<4>(ka, s, sm_count);
+        case 4:
+            if (getenv("PQP_TMEM_WT4")) {  // experiment: 4 instead of 8 warps per SM
+                int ctas = (ka.batch + 3) / 4;
+                if (ctas > sm_count) ctas = sm_count;
+                cudaFuncSetAttribute(pqp_admm_kernel_tmem<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+                pqp_admm_kernel_tmem<4, 4><<<ctas, 128, kTmemSmem, s>>>(ka);
+                return cudaGetLastError();
+            }
+            return launch_tmem<4>(ka, s, sm_count);
         default: return launch_tmem<8>(ka, s, sm_count);
     }
 }
@@ -837,6 +845,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->chunk = pqp::chunk_for(n_max);
     h->sm_count = prop.multiProcessorCount;
     h->smem_bytes = pqp::smem_floats(h->chunk) * sizeof(float) + 16;
+    if (const char *e = getenv("PQP_SMEM_PAD")) h->smem_bytes += (size_t)atoi(e);  // occupancy experiments only
 #define PQP_CREATE_CUDA(call)                                                     \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
