@@ -312,7 +312,7 @@ struct SmemStore {
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
 #ifndef PQP_CR_UNROLL
-#define PQP_CR_UNROLL _Pragma("unroll")
+#define PQP_CR_UNROLL _Pragma("unroll 1")
 #endif
 
 template <int C, typename real, typename Store = SmemStore<C, real> >
@@ -869,7 +869,8 @@ struct QpWarp {
             if (lane == 31) fr = real(0.0);
             bs[r] = bk[r] - fr;
         }
-        // cyclic reduction, forward (unrolled: lane masks become constants)
+        // cyclic reduction, forward (rolled: measured +4..10 % wherever more than one warp per
+        // scheduler is resident - smaller hot loop - and neutral at n = 240; profiles/r1/README.md)
         PQP_CR_UNROLL
         for (int t = 0; t < 5; ++t) {
             const int h = 1 << t;
