@@ -93,6 +93,46 @@ def test_config3_sampled(solver_mod):
     sv.close()
 
 
+def test_full_size_batch_properties(solver_mod):
+    """BASELINE configs[2] at full size (8192 x 240, ragged n) through size-independent properties:
+    the result of an instance does not depend on the batch around it - repeat runs, a permuted
+    batch and small sub-batches are bit-identical (each QP is one warp's private, deterministic
+    computation, whichever CTA picks it up) - and every solved instance's reported residuals pass
+    the termination test; the warm re-solve about the solution itself stops at its first check."""
+    params = abi.default_params()
+    B, n = 8192, 240
+    hb = synthetic.make_batch(3, B, n, ragged=True)
+    sv = solver_mod.PathQpSolver(params, n_max=n, batch_max=B)
+    a = sv.solve(hb)
+    # idempotence: re-linearised about its own solution, a solved instance is solved again within
+    # the first two checks of the warm run
+    w = sv.resolve(hb.with_linearisation(a.sol))
+    ok = a.status == abi.PQP_SOLVED
+    assert np.mean(w.status[ok] == abi.PQP_SOLVED) > 0.99
+    assert np.median(w.iters[ok]) <= 2 * params.check_termination
+    b = sv.solve(hb)
+    live = np.arange(n)[None, :] < hb.n[:, None]  # sol[b][:, i >= n[b]] is not written
+
+    def same(x, y, idx=slice(None)):
+        return (np.array_equal(x.status, y.status[idx]) and np.array_equal(x.iters, y.iters[idx]) and
+                np.array_equal(x.cost, y.cost[idx]) and
+                np.array_equal(np.where(live[idx][:, None, :], x.sol, 0.0), np.where(live[idx][:, None, :], y.sol[idx], 0.0)))
+
+    assert same(b, a)
+    perm = np.random.default_rng(0).permutation(B)
+    hp = abi.HostBatch(hb.knots[perm], hb.inst[perm], hb.n[perm])
+    c = sv.solve(hp)
+    assert same(c, a, perm)
+    sub = np.sort(perm[:24])
+    sv_small = solver_mod.PathQpSolver(params, n_max=n, batch_max=len(sub))  # plain launch instead of the streamed one
+    d = sv_small.solve(abi.HostBatch(hb.knots[sub], hb.inst[sub], hb.n[sub]))
+    assert same(d, a, sub)
+    sv_small.close()
+    assert np.all(a.status != abi.PQP_UNSOLVED) and np.mean(a.status == abi.PQP_SOLVED) > 0.95
+    assert np.all(a.iters[a.status == abi.PQP_SOLVED] % params.check_termination == 0)
+    sv.close()
+
+
 def test_frenet_to_cartesian(solver_mod):
     from oracle import oracle
     hb, ref = synthetic.make_batch(3, 4, 120, with_ref=True)
