@@ -543,7 +543,11 @@ cudaError_t dmalloc(T **p, size_t count) {
 int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int B) {
     std::vector<int> idx;
     for (int b = 0; b < B; ++b)
-        if (h->h_status[b] == PQP_MAX_ITER_REACHED && (h->h_flags[b] & 1)) idx.push_back(b);
+        // also an "inaccurate" certificate at the iteration cap: in FP32 the 10x-tolerance test can
+        // pass on rounding noise alone, the FP64 run decides (normally: PRIMAL_INFEASIBLE proper)
+        if ((h->h_status[b] == PQP_MAX_ITER_REACHED && (h->h_flags[b] & 1)) ||
+            h->h_status[b] == PQP_PRIMAL_INFEASIBLE_INACCURATE)
+            idx.push_back(b);
     if (idx.empty()) return PQP_OK;
     const int nmax = h->n_max;
     const size_t c = h->chunk;

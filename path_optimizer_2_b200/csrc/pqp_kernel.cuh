@@ -500,9 +500,12 @@ struct QpWarp {
                 rn[5] = ec1 * xmax(xmax(dk[0], h1 * dk[1]), dk[5]);
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    const real dnw = dk[j] * frsqrt(limit_scaling(cn[j]));
+                    // 1/sqrt as one MUFU.RSQ in FP32 (2 ulp): the Ruiz factors are only required to be
+                    // positive - any D, E give an equivalent problem - and 960 sqrt + divide pairs per
+                    // solve were 7 % of the kernel's stall samples; the FP64 instantiation stays exact
+                    const real dnw = dk[j] * xfast_rsqrt(limit_scaling(cn[j]));
                     S(FD1 + j, k) = dnw;
-                    S(FE1 + j, k) = ek[j] * frsqrt(limit_scaling(rn[j]));
+                    S(FE1 + j, k) = ek[j] * xfast_rsqrt(limit_scaling(rn[j]));
                     psum += dnw * dnw * pw[j];
                 }
             }

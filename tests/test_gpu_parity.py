@@ -202,7 +202,9 @@ def test_infeasible_instance_escalates_to_fp64(solver_mod):
     sv = solver_mod.PathQpSolver(abi.default_params(reserved=4), n_max=3, batch_max=6)  # escalation off
     res = sv.solve(hb)
     bad = exp == abi.PQP_PRIMAL_INFEASIBLE
-    assert np.all(np.isin(res.status[bad], [abi.PQP_PRIMAL_INFEASIBLE, abi.PQP_MAX_ITER_REACHED]))
+    # without the FP64 run the FP32 kernel reports the cap or a certificate (possibly the "inaccurate"
+    # one taken at the cap): all of them are `false` for the caller (base_solver.cpp:88)
+    assert np.all(np.isin(res.status[bad], parity.INFEASIBLE + (abi.PQP_MAX_ITER_REACHED,)))
     assert np.array_equal(res.status[~bad], exp[~bad])
     sv.close()
 
