@@ -138,6 +138,25 @@ def test_oracle_projection_and_states_on_a_circle():
     assert st is not None and np.allclose(np.diff(st[0]), 0.3)  # |k| = 0.05 < 0.08 -> 0.3 m spacing
 
 
+def test_bounds_golden_fixture(dmap):
+    """Frozen oracle outputs (tests/golden/make_bounds_golden.py): guards the bounds oracle, the map
+    loader and the spline rows against silent changes. Oracle-produced; parity unpinned."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bounds_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    ln = sharedmap.make_lines(3, 120, dmap=dmap)
+    for c in cases:
+        b = c["line"]
+        rows = np.array(c["spline"])
+        assert np.allclose(ln.spline_rows(b), rows, rtol=0, atol=1e-12)  # the workload generator is frozen too
+        bounds, n_valid = bo.update_bounds(dmap.dist, dmap.res, rows, *ln.states[b])
+        assert n_valid == c["n_valid"] and np.allclose(bounds[:, ::8], np.array(c["bounds_sampled"]), rtol=0, atol=1e-12)
+        st = bo.build_states(rows, float(rows[0, -1]))
+        assert len(st[0]) == c["total_states"]
+        assert np.allclose(np.stack(st)[:, ::16], np.array(c["states_sampled"]), rtol=0, atol=1e-12)
+
+
 # ------------------------------------------------------- the kernel's source on the host (CPU)
 def test_kernel_source_on_host_matches_oracle(dmap, lines):
     knots = np.zeros((lines.batch, abi.NFIELDS, lines.n_max))
