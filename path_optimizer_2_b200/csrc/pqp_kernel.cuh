@@ -311,6 +311,12 @@ struct SmemStore {
 #ifndef PQP_UPDATE_UNROLL
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
+// ADMM step in increment form (solve K dx = -(r_dual + A'R r_prim), x~ = x + dx) instead of the
+// textbook form (solve K x~ = S x + A'(R z - y)): algebraically the same iteration, but the rounding
+// error then scales with |dx| instead of |x| (profiles/r1/README.md, FP32 iteration-count gap).
+#ifndef PQP_INCREMENT
+#define PQP_INCREMENT 1
+#endif
 #ifndef PQP_CR_UNROLL
 #define PQP_CR_UNROLL _Pragma("unroll 1")
 #endif
@@ -1054,6 +1060,98 @@ struct QpWarp {
         fix_first_stage(wprev);
     }
 
+    // -------------------------------------------------------------- increment form
+    // A x of stage k's six rows at the stored iterate x (this stage) / xn (l, psi, kappa of the next
+    // stage), and the outgoing rows' residual A x - b with the large terms grouped first
+    // ((l - l') + (a00 - 1) l + ...) so that its rounding error is relative to the small terms.
+    PQP_DEV void stage_ax(const StageRO &q, const StagePred &sp, const real (&x)[6], const real (&xn)[3], real llo,
+                          real lnlo, real (&ax)[6], real (&req)[3]) {
+        const real one = real(1.0);
+        // l is carried as l + l_lo (the only state large enough for its FP32 quantum to matter)
+        const real g0 = ((x[0] + sp.gn * xn[0]) + (llo + sp.gn * lnlo)) + (q.a00 - one) * x[0] + q.a01 * x[1];
+        const real g1 = (x[1] + sp.gn * xn[1]) + q.a10 * x[0] + (q.a11 - one) * x[1] + q.a12 * x[2];
+        const real g2 = (sp.a22 * x[2] + sp.gn * xn[2]) + q.ds * x[3];
+        req[0] = g0 - q.ob[0]; req[1] = g1 - q.ob[1]; req[2] = g2 - q.ob[2];
+        ax[0] = g0; ax[1] = g1; ax[2] = g2;
+        ax[3] = sp.real ? x[2] : real(0.0);
+        ax[4] = sp.act0 ? (x[0] + sp.h0 * x[1] + x[4]) : real(0.0);
+        ax[5] = sp.act1 ? (x[0] + sp.h1 * x[1] + x[5]) : real(0.0);
+    }
+    // stage-local part of -(P x + A'(y + R (A x - z))) from the row vectors w' = R ((z - A x) - yhat)
+    PQP_DEV void local_rhs_incr(const StageRO &q, const StagePred &sp, const real (&x)[6], real (&wo)[3], real wk,
+                                real (&wc)[2], real (&bk)[3]) {
+        const real pl = sp.real ? w_l : real(0.0), pk = sp.real ? w_kappa : real(0.0), pu = sp.mid ? w_dkappa : real(0.0);
+        const real p0 = sp.act0 ? w_slack : real(0.0), p1 = sp.act1 ? w_slack : real(0.0);
+        const real rhs_u = q.ds * wo[2] - pu * x[3];
+        wo[2] -= (q.Ro[2] * q.ds * q.miu) * rhs_u;
+        const real rhs_s0 = wc[0] - p0 * x[4];
+        wc[0] -= (q.Rc[0] * q.mis0) * rhs_s0;
+        const real rhs_s1 = wc[1] - p1 * x[5];
+        wc[1] -= (q.Rc[1] * q.mis1) * rhs_s1;
+        bk[0] = q.a00 * wo[0] + q.a10 * wo[1] + wc[0] + wc[1] - pl * x[0];
+        bk[1] = q.a01 * wo[0] + q.a11 * wo[1] + sp.h0 * wc[0] + sp.h1 * wc[1];
+        bk[2] = q.a12 * wo[1] + sp.a22 * wo[2] + wk - pk * x[2];
+    }
+    // x (l, psi, kappa) of the right neighbour lane's first stage at the stored iterate
+    PQP_DEV void right_x(real (&xr)[3]) {
+        const Vec4 v = V(GX0, 0);
+        xr[0] = shfl_down(v.x, 1, lane);
+        xr[1] = shfl_down(v.y, 1, lane);
+        xr[2] = shfl_down(v.z, 1, lane);
+        if (lane == 31) { xr[0] = xr[1] = xr[2] = real(0.0); }
+    }
+    PQP_DEV void build_rhs_incr(bool initial, bool warm) {
+        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
+        real xr[3];
+        right_x(xr);
+        real lor = shfl_down((real)S(FB + 3, 0), 1, lane);
+        if (lane == 31) lor = real(0.0);
+        PQP_ROLL
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            StageRO q;
+            load_ro(k, q);
+            Vec4 x0, x1, oy, cz;
+            load_rw(k, x0, x1, oy, cz);
+            const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+            real xn[3];
+            if (k < C - 1) {
+                const Vec4 v = V(GX0, k < C - 1 ? k + 1 : k);
+                xn[0] = v.x; xn[1] = v.y; xn[2] = v.z;
+            } else {
+                xn[0] = xr[0]; xn[1] = xr[1]; xn[2] = xr[2];
+            }
+            real ax[6], req[3];
+            const real llo = initial ? real(0.0) : (real)S(FB + 3, k);
+            real lnlo;
+            if (k < C - 1) lnlo = initial ? real(0.0) : (real)S(FB + 3, k < C - 1 ? k + 1 : k);
+            else lnlo = initial ? real(0.0) : lor;
+            stage_ax(q, sp, x, xn, llo, lnlo, ax, req);
+            const real oyv[3] = {oy.x, oy.y, oy.z};
+            real wo[3], wk, wc[2], bk[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                real zmax;  // z - A x
+                if (sp.last && r < 2) zmax = zend[r] - ax[r];
+                else zmax = initial ? (z0_out(warm, r, k) - ax[r]) : -req[r];
+                wo[r] = q.Ro[r] * (zmax - oyv[r]);
+            }
+            wk = q.Rk * ((x1.z - ax[3]) - x1.w);
+            wc[0] = q.Rc[0] * ((cz.x - ax[4]) - cz.z);
+            wc[1] = q.Rc[1] * ((cz.y - ax[5]) - cz.w);
+            local_rhs_incr(q, sp, x, wo, wk, wc, bk);
+            Vec4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
+            bv.w = llo;
+            V(GBV, k) = bv;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
+        }
+        fix_first_stage(wprev);
+    }
+
     // -------------------------------------------------------------- infeasibility certificate terms
     // delta_y of one row (computed without cancellation as R (zt - z+)), projected onto the polar
     // of the recession cone of [lo, hi] (OSQP is_primal_infeasible); a bound counts as infinite
@@ -1209,6 +1307,165 @@ struct QpWarp {
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
             xv = xw;
+        }
+        fix_first_stage(wprev);
+    }
+
+    // -------------------------------------------------------------- one ADMM update, increment form
+    // in: GBV = dx (state part) of the solve K dx = -(P x + A'(y + R (A x - z))); dt / dn are dx of
+    // this / the next stage, xn the next stage's stored x. Same outputs as update_stage; the rhs
+    // produced is again the increment-form one.
+    template <bool kCheck>
+    PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
+                                   const real (&xn)[3], real &llo, real lnlo, real (&wo)[3], real (&bk)[3]) {
+        const real oma = real(1.0) - alpha;
+        const StagePred sp = pred(k);
+        StageRO q;
+        load_ro(k, q);
+        Vec4 x0, x1, oy, cz;
+        load_rw(k, x0, x1, oy, cz);
+        real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+        real ax[6], req[3];
+        stage_ax(q, sp, x, xn, llo, lnlo, ax, req);
+        const real oyv[3] = {oy.x, oy.y, oy.z};
+        // z - A x of the outgoing rows at the old iterate
+        real zo_old[3], zmax[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (sp.last && r < 2) { zo_old[r] = zend[r]; zmax[r] = zend[r] - ax[r]; }
+            else if (first) { zo_old[r] = z0_out(warm, r, k); zmax[r] = zo_old[r] - ax[r]; }
+            else { zo_old[r] = q.ob[r]; zmax[r] = -req[r]; }
+        }
+        // increments of the eliminated variables (their rhs recomputed from the old iterates)
+        const real pu = sp.mid ? w_dkappa : real(0.0);
+        const real p0 = sp.act0 ? w_slack : real(0.0), p1 = sp.act1 ? w_slack : real(0.0);
+        const real aux_u = q.ds * (q.Ro[2] * (zmax[2] - oyv[2])) - pu * x[3];
+        const real aux_s0 = q.Rc[0] * ((cz.x - ax[4]) - cz.z) - p0 * x[4];
+        const real aux_s1 = q.Rc[1] * ((cz.y - ax[5]) - cz.w) - p1 * x[5];
+        const real du = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * dt[2] + sp.gn * dn[2]));
+        const real ds0 = q.mis0 * (aux_s0 - q.Rc[0] * (dt[0] + sp.h0 * dt[1]));
+        const real ds1 = q.mis1 * (aux_s1 - q.Rc[1] * (dt[0] + sp.h1 * dt[1]));
+        // A dx
+        real dz[6];
+        dz[0] = q.a00 * dt[0] + q.a01 * dt[1] + sp.gn * dn[0];
+        dz[1] = q.a10 * dt[0] + q.a11 * dt[1] + q.a12 * dt[2] + sp.gn * dn[1];
+        dz[2] = sp.a22 * dt[2] + q.ds * du + sp.gn * dn[2];
+        dz[3] = sp.real ? dt[2] : real(0.0);
+        dz[4] = sp.act0 ? (dt[0] + sp.h0 * dt[1] + ds0) : real(0.0);
+        dz[5] = sp.act1 ? (dt[0] + sp.h1 * dt[1] + ds1) : real(0.0);
+        // x+ = x + alpha dx
+        {   // l + l_lo += alpha dl (fast two-sum: the increment is far below l)
+            const real t = llo + alpha * dt[0];
+            const real hi = x[0] + t;
+            llo = t - (hi - x[0]);
+            x[0] = hi;
+        }
+        x[1] += alpha * dt[1]; x[2] += alpha * dt[2];
+        x[3] += alpha * du; x[4] += alpha * ds0; x[5] += alpha * ds1;
+        x0.x = x[0]; x0.y = x[1]; x0.z = x[2]; x0.w = x[3]; x1.x = x[4]; x1.y = x[5];
+        // rows. zt - z_old = alpha (z~ - z_old) with z~ = A x + A dx; new (z - A x) = z+ - (A x + alpha A dx)
+        real wk, wc[2], oyn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const real bnd = q.ob[r];
+            // alpha (z~ - z_old) = alpha (A dx - (z_old - A x))
+            const real step = alpha * (dz[r] - zmax[r]);
+            real zn, dyr;
+            if (sp.last && r < 2) {
+                const real zh = (zo_old[r] + step) + oyv[r];
+                zn = clampf(zh, bnd, bnd + endw[r]);
+                zend[r] = zn;
+                oyn[r] = zh - zn;
+                dyr = (zo_old[r] + step) - zn;
+                wo[r] = q.Ro[r] * (((zn - ax[r]) - alpha * dz[r]) - oyn[r]);
+            } else {
+                // equality row: z+ = b; yhat+ = (z_old + step) + yhat - b, z_old - b = 0 unless `first`
+                zn = bnd;
+                const real off = first ? (zo_old[r] - bnd) : real(0.0);
+                dyr = step + off;
+                oyn[r] = oyv[r] + dyr;
+                // new z - A x = b - (A x + alpha A dx) = -(req + alpha A dx)
+                wo[r] = q.Ro[r] * (-(req[r] + alpha * dz[r]) - oyn[r]);
+            }
+            if (kCheck) cert_row(r, k, q.Ro[r] * dyr, bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
+        }
+        oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
+        {
+            const real zt = x1.z + alpha * (dz[3] - (x1.z - ax[3]));
+            const real zh = zt + x1.w;
+            const real zn = clampf(zh, -kmax, kmax);
+            x1.z = zn;
+            x1.w = zh - zn;
+            wk = q.Rk * (((zn - ax[3]) - alpha * dz[3]) - x1.w);
+            if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
+        }
+        {
+            const real zt = cz.x + alpha * (dz[4] - (cz.x - ax[4]));
+            const real zh = zt + cz.z;
+            const real zn = clampf(zh, q.clo[0], q.chi[0]);
+            cz.x = zn;
+            cz.z = zh - zn;
+            wc[0] = q.Rc[0] * (((zn - ax[4]) - alpha * dz[4]) - cz.z);
+            if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
+        }
+        {
+            const real zt = cz.y + alpha * (dz[5] - (cz.y - ax[5]));
+            const real zh = zt + cz.w;
+            const real zn = clampf(zh, q.clo[1], q.chi[1]);
+            cz.y = zn;
+            cz.w = zh - zn;
+            wc[1] = q.Rc[1] * (((zn - ax[5]) - alpha * dz[5]) - cz.w);
+            if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
+        }
+        V(GX0, k) = x0;
+        V(GX1, k) = x1;
+        V(GOY, k) = oy;
+        V(GCZ, k) = cz;
+        local_rhs_incr(q, sp, x, wo, wk, wc, bk);
+    }
+
+    template <bool kCheck>
+    PQP_DEV void admm_update_incr(bool first, bool warm) {
+        real dnb[3], xrb[3], lorb;
+        {
+            const Vec4 v = V(GBV, 0);
+            dnb[0] = shfl_down(v.x, 1, lane);
+            dnb[1] = shfl_down(v.y, 1, lane);
+            dnb[2] = shfl_down(v.z, 1, lane);
+            lorb = shfl_down(v.w, 1, lane);
+            if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = lorb = real(0.0); }
+        }
+        right_x(xrb);  // before any stage is advanced: the neighbour's stage 0 is updated in the first pass
+        if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
+        real wprev[3] = {real(0.0), real(0.0), real(0.0)};
+        Vec4 dv = V(GBV, 0);
+        PQP_UPDATE_UNROLL
+        for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            const int kn1 = k < C - 1 ? k + 1 : k;
+            const Vec4 dw = V(GBV, kn1);
+            const Vec4 xw = V(GX0, kn1);
+            const real dt[3] = {dv.x, dv.y, dv.z};
+            real dn[3], xn[3];
+            dn[0] = (k == C - 1) ? dnb[0] : dw.x;
+            dn[1] = (k == C - 1) ? dnb[1] : dw.y;
+            dn[2] = (k == C - 1) ? dnb[2] : dw.z;
+            xn[0] = (k == C - 1) ? xrb[0] : xw.x;
+            xn[1] = (k == C - 1) ? xrb[1] : xw.y;
+            xn[2] = (k == C - 1) ? xrb[2] : xw.z;
+            real wo[3], bk[3];
+            real llo = dv.w;
+            const real lnlo = (k == C - 1) ? lorb : dw.w;
+            update_stage_incr<kCheck>(k, first, warm, dt, dn, xn, llo, lnlo, wo, bk);
+            Vec4 bv;
+            bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
+            bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
+            bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
+            bv.w = llo;
+            V(GBV, k) = bv;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
+            dv = dw;
         }
         fix_first_stage(wprev);
     }
@@ -1465,7 +1722,11 @@ struct QpWarp {
                 store.fence();
                 sync_warp(lane);
                 if (!fok) { status = kNumerical; break; }
+#if PQP_INCREMENT
+                build_rhs_incr(initial, warm);
+#else
                 build_rhs(initial, warm);
+#endif
                 need_factor = false;
                 initial = false;
             }
@@ -1477,8 +1738,13 @@ struct QpWarp {
             const bool can_adapt = (--to_adapt == 0) && !last;
             if (to_check <= 0) to_check = P.check_every > 0 ? P.check_every : -1;
             if (to_adapt <= 0) to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
+#if PQP_INCREMENT
+            if (can_check) admm_update_incr<true>(iter == 1, warm);
+            else admm_update_incr<false>(iter == 1, warm);
+#else
             if (can_check) admm_update<true>(iter == 1, warm);
             else admm_update<false>(iter == 1, warm);
+#endif
             if (can_check || can_adapt) {
                 nr = residuals();
                 if (can_check) {
