@@ -980,6 +980,25 @@ struct QpWarp {
         q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
         q.Sw[2] = t[24]; q.Sw[3] = t[25]; q.Sw[4] = t[26]; q.Sw[5] = t[27];
     }
+    // the same without the proximal weights S (increment form: no S x term in the rhs)
+    PQP_DEV void load_ro6(int k, StageRO &q) {
+        real t[24];
+        store.template ld4n<6>(GA0, k, t);
+        q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
+        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
+        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
+        q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
+        q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
+        q.Rc[0] = t[20]; q.Rc[1] = t[21];
+    }
+    // GX1, GOY, GCZ of stage k (the caller carries GX0 over from the previous stage's look-ahead)
+    PQP_DEV void load_rw3(int k, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
+        real t[12];
+        store.template ld4n<3>(GX1, k, t);
+        x1.x = t[0]; x1.y = t[1]; x1.z = t[2]; x1.w = t[3];
+        oy.x = t[4]; oy.y = t[5]; oy.z = t[6]; oy.w = t[7];
+        cz.x = t[8]; cz.y = t[9]; cz.z = t[10]; cz.w = t[11];
+    }
     // the four read-write groups of stage k (x, s/kappa-row, yhat, clearance z/yhat)
     PQP_DEV void load_rw(int k, Vec4 &x0, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
         real t[16];
@@ -1316,14 +1335,13 @@ struct QpWarp {
     // this / the next stage, xn the next stage's stored x. Same outputs as update_stage; the rhs
     // produced is again the increment-form one.
     template <bool kCheck>
-    PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
+    PQP_DEV void update_stage_incr(int k, bool first, bool warm, Vec4 x0, const real (&dt)[3], const real (&dn)[3],
                                    const real (&xn)[3], real &llo, real lnlo, real (&wo)[3], real (&bk)[3]) {
-        const real oma = real(1.0) - alpha;
         const StagePred sp = pred(k);
         StageRO q;
-        load_ro(k, q);
-        Vec4 x0, x1, oy, cz;
-        load_rw(k, x0, x1, oy, cz);
+        load_ro6(k, q);
+        Vec4 x1, oy, cz;
+        load_rw3(k, x1, oy, cz);
         real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
         real ax[6], req[3];
         stage_ax(q, sp, x, xn, llo, lnlo, ax, req);
@@ -1439,12 +1457,13 @@ struct QpWarp {
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
         Vec4 dv = V(GBV, 0);
+        Vec4 xcur = V(GX0, 0);
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             const int kn1 = k < C - 1 ? k + 1 : k;
             const Vec4 dw = V(GBV, kn1);
-            const Vec4 xw = V(GX0, kn1);
+            const Vec4 xw = V(GX0, kn1);  // look-ahead: the next stage's stored x (still the old iterate)
             const real dt[3] = {dv.x, dv.y, dv.z};
             real dn[3], xn[3];
             dn[0] = (k == C - 1) ? dnb[0] : dw.x;
@@ -1456,7 +1475,8 @@ struct QpWarp {
             real wo[3], bk[3];
             real llo = dv.w;
             const real lnlo = (k == C - 1) ? lorb : dw.w;
-            update_stage_incr<kCheck>(k, first, warm, dt, dn, xn, llo, lnlo, wo, bk);
+            update_stage_incr<kCheck>(k, first, warm, xcur, dt, dn, xn, llo, lnlo, wo, bk);
+            xcur = xw;
             Vec4 bv;
             bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
