@@ -300,6 +300,11 @@ struct SmemStore {
             out[4 * g] = v.x; out[4 * g + 1] = v.y; out[4 * g + 2] = v.z; out[4 * g + 3] = v.w;
         }
     }
+    // two unrelated groups with one latency (tensor memory: one wait for both loads)
+    PQP_DEV void ld4x2(int ga, int ka, int gb, int kb, Vec4 &a, Vec4 &b) const {
+        a = ld4(ga, ka);
+        b = ld4(gb, kb);
+    }
     PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
 };
 
@@ -1462,8 +1467,8 @@ struct QpWarp {
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             const int kn1 = k < C - 1 ? k + 1 : k;
-            const Vec4 dw = V(GBV, kn1);
-            const Vec4 xw = V(GX0, kn1);  // look-ahead: the next stage's stored x (still the old iterate)
+            Vec4 dw, xw;  // look-ahead: the next stage's dx and stored x (still the old iterate)
+            store.ld4x2(GBV, kn1, GX0, kn1, dw, xw);
             const real dt[3] = {dv.x, dv.y, dv.z};
             real dn[3], xn[3];
             dn[0] = (k == C - 1) ? dnb[0] : dw.x;
