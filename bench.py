@@ -457,7 +457,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--option-bits", type=int, default=0,
                     help="pqp_params.reserved: 1 FP32 factorisation, 2 FP64 iterates, 4 no FP64 escalation, "
-                         "8 state in tensor memory")
+                         "8 state in tensor memory, 16 state in shared memory, 32 increment-form ADMM step, 64 textbook form")
     ap.add_argument("--workload", default="cold", choices=["cold", "receding", "sharedmap"],
                     help="cold: BASELINE configs[2]/[3] (default); receding: configs[4], warm re-solves with a "
                          "50-iteration cap on a window that advances one knot per step; sharedmap: configs[1], "

@@ -116,7 +116,11 @@ typedef struct pqp_params {
                                        2 = iterate in FP64 (whole kernel in double precision),
                                        4 = do not re-solve suspected-infeasible instances in FP64,
                                        8 = FP32 state in tensor memory (persistent CTAs, tcgen05.ld/st),
-                                       16 = FP32 state in shared memory even where tensor memory is the default */
+                                       16 = FP32 state in shared memory even where tensor memory is the default,
+                                       32 = ADMM step in increment form (dx solve, l carried as l + l_lo): the FP32
+                                            kernel then follows the FP64 iteration count for count; default only
+                                            where it is also faster (64 <= n_max <= 127, shared-memory policy),
+                                       64 = textbook form everywhere */
 } pqp_params;
 
 /* Batch input. All pointers are HOST pointers for pqp_solve/pqp_resolve and DEVICE

@@ -60,7 +60,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // ------------------------------------------------------------------ device: kernel entry
 // One CTA = one warp = one QP instance. Dynamic shared memory: NFIELD*C*32 floats of
 // solver state (the factor region doubles as the FP64 input staging buffer) + 1 mbarrier.
-template <int C, typename real>
+template <int C, typename real, bool Incr>
 __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pqp::KernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     real *smem = reinterpret_cast<real *>(smem_raw);
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pq
         mbar_wait(bar, 0);
         src = stage;
     }
-    pqp::QpWarp<C, real> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
+    pqp::QpWarp<C, real, pqp::SmemStore<C, real>, Incr> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
     w.run(src, ka.n_max);
 }
 
@@ -201,7 +201,7 @@ struct TmemStore {
 // A hybrid variant that added shared-memory-backed warps to the same CTA was measured slower
 // (instruction-fetch bound either as two instantiations or as one with run-time backend
 // selection): profiles/r1/README.md.
-template <int C, int WT>
+template <int C, int WT, bool Incr>
 __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_constant__ pqp::KernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t tbase_s;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
             }
         }
         const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
-        pqp::QpWarp<C, float, Store> w(ka, Store(tb, spill, lane), lane, qp);
+        pqp::QpWarp<C, float, Store, Incr> w(ka, Store(tb, spill, lane), lane, qp);
         w.run(src, ka.n_max);
         if (ka.done) {
             __syncwarp();
@@ -356,6 +356,7 @@ struct pqp_handle {
     int *d_counters = nullptr;
     unsigned counter_next = 0;
     bool use_tmem = false;         // params.reserved bit 3: state in tensor memory (FP32 kernel)
+    bool incr = false;             // ADMM step in increment form (FP32 kernels)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
     size_t smem_bytes64 = 0;
@@ -394,33 +395,44 @@ int cuda_fail(pqp_handle *h, cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call);  \
     } while (0)
 
-template <int C, typename real>
+// the increment form is only instantiated for FP32 (the FP64 kernel is exact in either form)
+template <int C, typename real, bool Incr>
 cudaError_t launch(const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
-    pqp_admm_kernel<C, real><<<ka.batch, 32, smem, s>>>(ka);
+    pqp_admm_kernel<C, real, Incr><<<ka.batch, 32, smem, s>>>(ka);
     return cudaGetLastError();
 }
+template <int C, typename real>
+cudaError_t launch_form(const pqp::KernelArgs &ka, size_t smem, cudaStream_t s, bool incr) {
+    if (incr && sizeof(real) == 4) return launch<C, float, true>(ka, smem, s);
+    return launch<C, real, false>(ka, smem, s);
+}
 template <typename real>
-cudaError_t launch_chunk(int chunk, const pqp::KernelArgs &ka, size_t smem, cudaStream_t s) {
+cudaError_t launch_chunk(int chunk, const pqp::KernelArgs &ka, size_t smem, cudaStream_t s, bool incr = false) {
     switch (chunk) {
-        case 1: return launch<1, real>(ka, smem, s);
-        case 2: return launch<2, real>(ka, smem, s);
-        case 4: return launch<4, real>(ka, smem, s);
-        default: return launch<8, real>(ka, smem, s);
+        case 1: return launch_form<1, real>(ka, smem, s, incr);
+        case 2: return launch_form<2, real>(ka, smem, s, incr);
+        case 4: return launch_form<4, real>(ka, smem, s, incr);
+        default: return launch_form<8, real>(ka, smem, s, incr);
     }
 }
-template <int C, typename real>
+template <int C, typename real, bool Incr>
 cudaError_t prepare(size_t smem, int *blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel<C, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel<C, real, Incr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, pqp_admm_kernel<C, real>, 32, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, pqp_admm_kernel<C, real, Incr>, 32, smem);
+}
+template <int C, typename real>
+cudaError_t prepare_form(size_t smem, int *bps, bool incr) {
+    if (incr && sizeof(real) == 4) return prepare<C, float, true>(smem, bps);
+    return prepare<C, real, false>(smem, bps);
 }
 template <typename real>
-cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
+cudaError_t prepare_chunk(int chunk, size_t smem, int *bps, bool incr = false) {
     switch (chunk) {
-        case 1: return prepare<1, real>(smem, bps);
-        case 2: return prepare<2, real>(smem, bps);
-        case 4: return prepare<4, real>(smem, bps);
-        default: return prepare<8, real>(smem, bps);
+        case 1: return prepare_form<1, real>(smem, bps, incr);
+        case 2: return prepare_form<2, real>(smem, bps, incr);
+        case 4: return prepare_form<4, real>(smem, bps, incr);
+        default: return prepare_form<8, real>(smem, bps, incr);
     }
 }
 
@@ -428,33 +440,39 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps) {
 // so that a second CTA cannot be resident and spin on tcgen05.alloc)
 template <int C> struct TmemCfg { static constexpr int WT = (C == 4) ? 8 : 4; };
 constexpr size_t kTmemSmem = 120 * 1024;
-template <int C>
+template <int C, bool Incr>
 cudaError_t launch_tmem(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
     constexpr int W = TmemCfg<C>::WT;
     int ctas = (ka.batch + W - 1) / W;
     if (ctas > sm_count) ctas = sm_count;
-    pqp_admm_kernel_tmem<C, W><<<ctas, 32 * W, kTmemSmem, s>>>(ka);
+    pqp_admm_kernel_tmem<C, W, Incr><<<ctas, 32 * W, kTmemSmem, s>>>(ka);
     return cudaGetLastError();
 }
-cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
+template <int C>
+cudaError_t launch_tmem_form(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count, bool incr) {
+    return incr ? launch_tmem<C, true>(ka, s, sm_count) : launch_tmem<C, false>(ka, s, sm_count);
+}
+cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count, bool incr) {
     switch (chunk) {
-        case 1: return launch_tmem<1>(ka, s, sm_count);
-        case 2: return launch_tmem<2>(ka, s, sm_count);
+        case 1: return launch_tmem_form<1>(ka, s, sm_count, incr);
+        case 2: return launch_tmem_form<2>(ka, s, sm_count, incr);
         case 4:
-            if (getenv("PQP_TMEM_WT4")) {  // experiment: 4 instead of 8 warps per SM
+            if (getenv("PQP_TMEM_WT4")) {  // experiment: 4 instead of 8 warps per SM (textbook form)
                 int ctas = (ka.batch + 3) / 4;
                 if (ctas > sm_count) ctas = sm_count;
-                cudaFuncSetAttribute(pqp_admm_kernel_tmem<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
-                pqp_admm_kernel_tmem<4, 4><<<ctas, 128, kTmemSmem, s>>>(ka);
+                cudaFuncSetAttribute(pqp_admm_kernel_tmem<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+                pqp_admm_kernel_tmem<4, 4, false><<<ctas, 128, kTmemSmem, s>>>(ka);
                 return cudaGetLastError();
             }
-            return launch_tmem<4>(ka, s, sm_count);
-        default: return launch_tmem<8>(ka, s, sm_count);
+            return launch_tmem_form<4>(ka, s, sm_count, incr);
+        default: return launch_tmem_form<8>(ka, s, sm_count, incr);
     }
 }
 template <int C>
 cudaError_t prepare_tmem() {
-    return cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
 }
 cudaError_t prepare_tmem_chunk(int chunk) {
     switch (chunk) {
@@ -528,9 +546,9 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
         PQP_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), s));
         ka.work_counter = ctr;
-        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count));
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count, h->incr));
     } else {
-        PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s));
+        PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s, h->incr));
     }
     if (timed) PQP_CUDA(h, cudaEventRecord(h->ev1, s));
     h->launches++;
@@ -881,6 +899,11 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     // instances. Bits 8 / 16 force one or the other.
     const bool auto_tmem = h->chunk == 8 || (h->chunk == 4 && batch_max <= 4096);
     h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (auto_tmem && (params->reserved & 16) == 0));
+    // form of the ADMM step (FP32 kernels): the increment form follows the FP64 oracle's rho schedule
+    // (same iteration count in 98-99 % of instances, ~6 % fewer iterations) for ~8 % more instructions
+    // per iteration - a net win only where spare issue slots absorb them: 64 <= n_max <= 127 under the
+    // shared-memory policy (+4 %; -4 % at n = 240, -7 % at n = 60). Bits 32 / 64 force one or the other.
+    h->incr = !h->fp64 && ((params->reserved & 32) != 0 || ((params->reserved & 64) == 0 && h->chunk == 4 && !h->use_tmem));
     if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
@@ -888,7 +911,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
         PQP_CREATE_CUDA(prepare_chunk<double>(h->chunk, h->smem_bytes64, &bps));
         h->prepared64 = true;
     } else {
-        PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps));
+        PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps, h->incr));
     }
     h->warps_per_sm = h->use_tmem ? tmem_warps(h->chunk) : bps;
     for (int i = 0; i < pqp_handle::kStreams; ++i) {

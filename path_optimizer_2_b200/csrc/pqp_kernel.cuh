@@ -316,17 +316,17 @@ struct SmemStore {
 #ifndef PQP_UPDATE_UNROLL
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
-// ADMM step in increment form (solve K dx = -(r_dual + A'R r_prim), x~ = x + dx) instead of the
-// textbook form (solve K x~ = S x + A'(R z - y)): algebraically the same iteration, but the rounding
-// error then scales with |dx| instead of |x| (profiles/r1/README.md, FP32 iteration-count gap).
-#ifndef PQP_INCREMENT
-#define PQP_INCREMENT 1
-#endif
+// QpWarp's last template argument selects the ADMM step in increment form (solve
+// K dx = -(r_dual + A'R r_prim), x~ = x + dx, with l carried as l + l_lo) instead of the textbook
+// form (solve K x~ = S x + A'(R z - y)): algebraically the same iteration, but its rounding error
+// scales with |dx| instead of |x|, so the FP32 kernel follows the FP64 oracle's rho schedule
+// (same iteration count in 98-99 % of instances instead of 85 %, ~6 % fewer iterations) at ~8 % more
+// instructions per iteration (profiles/r1/README.md).
 #ifndef PQP_CR_UNROLL
 #define PQP_CR_UNROLL _Pragma("unroll 1")
 #endif
 
-template <int C, typename real, typename Store = SmemStore<C, real> >
+template <int C, typename real, typename Store = SmemStore<C, real>, bool Incr = false>
 struct QpWarp {
     typedef typename Vec4T<real>::type Vec4;
     const KernelArgs &ka;
@@ -1747,11 +1747,8 @@ struct QpWarp {
                 store.fence();
                 sync_warp(lane);
                 if (!fok) { status = kNumerical; break; }
-#if PQP_INCREMENT
-                build_rhs_incr(initial, warm);
-#else
-                build_rhs(initial, warm);
-#endif
+                if (Incr) build_rhs_incr(initial, warm);
+                else build_rhs(initial, warm);
                 need_factor = false;
                 initial = false;
             }
@@ -1763,13 +1760,13 @@ struct QpWarp {
             const bool can_adapt = (--to_adapt == 0) && !last;
             if (to_check <= 0) to_check = P.check_every > 0 ? P.check_every : -1;
             if (to_adapt <= 0) to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
-#if PQP_INCREMENT
-            if (can_check) admm_update_incr<true>(iter == 1, warm);
-            else admm_update_incr<false>(iter == 1, warm);
-#else
-            if (can_check) admm_update<true>(iter == 1, warm);
-            else admm_update<false>(iter == 1, warm);
-#endif
+            if (Incr) {
+                if (can_check) admm_update_incr<true>(iter == 1, warm);
+                else admm_update_incr<false>(iter == 1, warm);
+            } else {
+                if (can_check) admm_update<true>(iter == 1, warm);
+                else admm_update<false>(iter == 1, warm);
+            }
             if (can_check || can_adapt) {
                 nr = residuals();
                 if (can_check) {

@@ -14,22 +14,30 @@ struct EmuHandle {
     pqp_params prm;
     int n_max, batch_max, chunk;
     bool fp64 = false;  // params.reserved bit 1: run the FP64 instantiation
+    bool incr = false;  // increment form of the ADMM step (bit 32; bit 64 forces the textbook form; default C == 4)
     std::vector<double> warm, scal, dy, rho;   // sized for the wider scalar type
     std::vector<double> smem;
     bool solved = false;
 };
 
-template <int C, typename real>
-void run_one(const pqp::KernelArgs &ka, int qp, real *smem) {
+template <int C, typename real, bool Incr>
+void run_form(const pqp::KernelArgs &ka, int qp, real *smem) {
     warp_emu::Warp warp;
     warp_emu::current() = &warp;
     const double *src = ka.knots + (size_t)qp * 9 * ka.n_max;
     const int stride = ka.n_max;
     warp.run([&](int lane) {
-        pqp::QpWarp<C, real> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
+        pqp::QpWarp<C, real, pqp::SmemStore<C, real>, Incr> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
         w.run(src, stride);
     });
     warp_emu::current() = nullptr;
+}
+// both forms of the ADMM step are instantiated for both scalar types (the library only builds the
+// increment form in FP32); `incr` as the library decides it: reserved bit 32 / 64, default C == 4
+template <int C, typename real>
+void run_one(const pqp::KernelArgs &ka, int qp, real *smem, bool incr) {
+    if (incr) run_form<C, real, true>(ka, qp, smem);
+    else run_form<C, real, false>(ka, qp, smem);
 }
 
 int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode) {
@@ -72,18 +80,18 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         if (h->fp64) {
             double *sm = h->smem.data();
             switch (h->chunk) {
-                case 1: run_one<1, double>(ka, b, sm); break;
-                case 2: run_one<2, double>(ka, b, sm); break;
-                case 4: run_one<4, double>(ka, b, sm); break;
-                default: run_one<8, double>(ka, b, sm); break;
+                case 1: run_one<1, double>(ka, b, sm, h->incr); break;
+                case 2: run_one<2, double>(ka, b, sm, h->incr); break;
+                case 4: run_one<4, double>(ka, b, sm, h->incr); break;
+                default: run_one<8, double>(ka, b, sm, h->incr); break;
             }
         } else {
             float *sm = reinterpret_cast<float *>(h->smem.data());
             switch (h->chunk) {
-                case 1: run_one<1, float>(ka, b, sm); break;
-                case 2: run_one<2, float>(ka, b, sm); break;
-                case 4: run_one<4, float>(ka, b, sm); break;
-                default: run_one<8, float>(ka, b, sm); break;
+                case 1: run_one<1, float>(ka, b, sm, h->incr); break;
+                case 2: run_one<2, float>(ka, b, sm, h->incr); break;
+                case 4: run_one<4, float>(ka, b, sm, h->incr); break;
+                default: run_one<8, float>(ka, b, sm, h->incr); break;
             }
         }
     }
@@ -104,6 +112,7 @@ void *emu_create(const pqp_params *prm, int n_max, int batch_max) {
     h->chunk = pqp::chunk_for(n_max);
     const int c = h->chunk;
     h->fp64 = (prm->reserved & 2) != 0;
+    h->incr = (prm->reserved & 32) != 0 || ((prm->reserved & 64) == 0 && !h->fp64 && h->chunk == 4);
     h->warm.assign((size_t)batch_max * pqp::warm_floats(c), 0.0);
     h->scal.assign((size_t)batch_max * pqp::scal_floats(c), 0.0);
     h->dy.assign((size_t)batch_max * pqp::dy_floats(c), 0.0);

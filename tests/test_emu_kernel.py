@@ -59,8 +59,9 @@ def test_emulated_fp64_instantiation_reproduces_oracle_iterates():
     schedule as the oracle -> same iteration counts, rho, statuses (incl. PRIMAL_INFEASIBLE)
     and iterates to ~1e-7, cold and warm."""
     from oracle import oracle
-    p32, p64 = abi.default_params(), abi.default_params(reserved=2)
-    for cfg, batch, n in ((103, 6, 3), (3, 4, 60), (3, 2, 240)):
+    p32 = abi.default_params()
+    for cfg, batch, n, bits in ((103, 6, 3, 2), (3, 4, 60, 2), (3, 2, 240, 2), (103, 6, 3, 2 | 32), (3, 2, 120, 2 | 32)):
+        p64 = abi.default_params(reserved=bits)  # bit 32: the increment form is the same iteration in exact arithmetic
         hb = synthetic.make_batch(cfg, batch, n)
         es = emu.EmuSolver(p64, n, batch)
         res = es.solve(hb)
@@ -110,11 +111,11 @@ def test_emulated_fp32_tracks_the_oracle_iteration_for_iteration():
     rho schedule and termination follow the FP64 oracle - same iteration count in >= 90 % of instances
     (measured 98-99 %), never more than one check interval apart, mean within 2 %."""
     from oracle import oracle
-    params = abi.default_params()
-    for n, batch in ((120, 48), (240, 24)):
+    params = abi.default_params(reserved=32)  # increment form at every size (default only for 64 <= n <= 127)
+    for n, batch in ((120, 48), (240, 24), (40, 24)):
         hb = synthetic.make_batch(3, batch, n)
         g = emu.EmuSolver(params, n, batch).solve(hb)
-        o, _ = oracle.solve_batch(params, hb, nthreads=2, full=True)
+        o, _ = oracle.solve_batch(abi.default_params(), hb, nthreads=2, full=True)
         assert np.array_equal(g.status, o.status)
         ok = o.status == abi.PQP_SOLVED
         d = g.iters[ok].astype(np.int64) - o.iters[ok]
