@@ -622,6 +622,17 @@ struct QpWarp {
         }
     }
 
+    // proximal weight S_j of stage k. The increment form keeps the carried row values A x in the
+    // FS slots during the iteration (it has no S x term), so S is recomputed from the Ruiz D in
+    // global scratch where it is needed (factorisation, checks).
+    template <typename T>
+    PQP_DEV T s_weight(int j, int k, const StagePred &sp) {
+        if (!Incr) return T(S(FS + j, k));
+        const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
+        const T d = T(G(gscal, GD + j, k));
+        return exists ? T(sigma) / (T(cscale) * d * d) : T(1.0);
+    }
+
     // z of outgoing row r at the start of a (warm) solve, before the first iteration
     PQP_DEV real z0_out(bool warm, int r, int k) {
         return warm ? G(gwarm, WOZ + r, k) / G(gscal, GE + r, k) : real(0.0);
@@ -636,7 +647,7 @@ struct QpWarp {
         const T ds = S(FA + 5, k);
         const T R2 = S(FOR_ + 2, k);
         const T pu = sp.mid ? T(w_dkappa) : T(0);
-        const T mu = pu + T(S(FS + 3, k)) + R2 * ds * ds;
+        const T mu = pu + s_weight<T>(3, k, sp) + R2 * ds * ds;
         const T miu = T(1) / mu;
         if (store) S(FE + 0, k) = (real)miu;
         Rt[0] = S(FOR_ + 0, k);
@@ -655,7 +666,7 @@ struct QpWarp {
             const bool act = j == 0 ? sp.act0 : sp.act1;
             const T ps = act ? T(w_slack) : T(0);
             const T Rcj = S(FCR + j, k);
-            const T ms = ps + T(S(FS + 4 + j, k)) + Rcj;
+            const T ms = ps + s_weight<T>(4 + j, k, sp) + Rcj;
             const T mis = T(1) / ms;
             S(FE + 1 + j, k) = (real)mis;
             Rc[j] = Rcj - (Rcj * mis) * Rcj;
@@ -663,12 +674,12 @@ struct QpWarp {
         const T h0 = sp.h0, h1 = sp.h1;
         const T pk = sp.real ? T(w_kappa) : T(0), pl = sp.real ? T(w_l) : T(0);
         const T hasL = sp.real ? T(1) : T(0);
-        D[0] = T(S(FS + 0, k)) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
+        D[0] = s_weight<T>(0, k, sp) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
         D[1] = Rt[0] * a00 * a01 + Rt[1] * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
         D[2] = Rt[1] * a10 * a12;
-        D[3] = T(S(FS + 1, k)) + Rt[0] * a01 * a01 + Rt[1] * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1 + hasL * RtL[1];
+        D[3] = s_weight<T>(1, k, sp) + Rt[0] * a01 * a01 + Rt[1] * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1 + hasL * RtL[1];
         D[4] = Rt[1] * a11 * a12;
-        D[5] = T(S(FS + 2, k)) + pk + Rt[1] * a12 * a12 + Rt[2] * a22 * a22 + T(S(FKR, k)) + hasL * RtL[2];
+        D[5] = s_weight<T>(2, k, sp) + pk + Rt[1] * a12 * a12 + Rt[2] * a22 * a22 + T(S(FKR, k)) + hasL * RtL[2];
     }
     // coupling block between stage k and k+1: O[r][c] = gn * Rt_r * Ahat[r][c]
     template <typename T>
@@ -1088,14 +1099,11 @@ struct QpWarp {
     // A x of stage k's six rows at the stored iterate x (this stage) / xn (l, psi, kappa of the next
     // stage), and the outgoing rows' residual A x - b with the large terms grouped first
     // ((l - l') + (a00 - 1) l + ...) so that its rounding error is relative to the small terms.
-    PQP_DEV void stage_ax(const StageRO &q, const StagePred &sp, const real (&x)[6], const real (&xn)[3], real llo,
-                          real lnlo, real (&ax)[6], real (&req)[3]) {
+    PQP_DEV void stage_ax(const StageRO &q, const StagePred &sp, const real (&x)[6], const real (&xn)[3], real (&ax)[6]) {
         const real one = real(1.0);
-        // l is carried as l + l_lo (the only state large enough for its FP32 quantum to matter)
-        const real g0 = ((x[0] + sp.gn * xn[0]) + (llo + sp.gn * lnlo)) + (q.a00 - one) * x[0] + q.a01 * x[1];
+        const real g0 = (x[0] + sp.gn * xn[0]) + (q.a00 - one) * x[0] + q.a01 * x[1];
         const real g1 = (x[1] + sp.gn * xn[1]) + q.a10 * x[0] + (q.a11 - one) * x[1] + q.a12 * x[2];
         const real g2 = (sp.a22 * x[2] + sp.gn * xn[2]) + q.ds * x[3];
-        req[0] = g0 - q.ob[0]; req[1] = g1 - q.ob[1]; req[2] = g2 - q.ob[2];
         ax[0] = g0; ax[1] = g1; ax[2] = g2;
         ax[3] = sp.real ? x[2] : real(0.0);
         ax[4] = sp.act0 ? (x[0] + sp.h0 * x[1] + x[4]) : real(0.0);
@@ -1124,12 +1132,13 @@ struct QpWarp {
         xr[2] = shfl_down(v.z, 1, lane);
         if (lane == 31) { xr[0] = xr[1] = xr[2] = real(0.0); }
     }
+    // rhs of the increment solve from the stored iterates. `initial` (start of a solve): the row
+    // values A x are evaluated from x (large terms grouped first) and written to the FS slots; later
+    // rebuilds (after a rho update) reuse the carried values.
     PQP_DEV void build_rhs_incr(bool initial, bool warm) {
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
-        real xr[3];
-        right_x(xr);
-        real lor = shfl_down((real)S(FB + 3, 0), 1, lane);
-        if (lane == 31) lor = real(0.0);
+        real xr[3] = {real(0.0), real(0.0), real(0.0)};
+        if (initial) right_x(xr);
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
@@ -1138,26 +1147,32 @@ struct QpWarp {
             Vec4 x0, x1, oy, cz;
             load_rw(k, x0, x1, oy, cz);
             const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-            real xn[3];
-            if (k < C - 1) {
-                const Vec4 v = V(GX0, k < C - 1 ? k + 1 : k);
-                xn[0] = v.x; xn[1] = v.y; xn[2] = v.z;
+            real ax[6];
+            if (initial) {
+                real xn[3];
+                if (k < C - 1) {
+                    const Vec4 v = V(GX0, k < C - 1 ? k + 1 : k);
+                    xn[0] = v.x; xn[1] = v.y; xn[2] = v.z;
+                } else {
+                    xn[0] = xr[0]; xn[1] = xr[1]; xn[2] = xr[2];
+                }
+                stage_ax(q, sp, x, xn, ax);
+                Vec4 g5, g6;
+                g5.x = q.Rc[0]; g5.y = q.Rc[1]; g5.z = ax[0]; g5.w = ax[1];
+                g6.x = ax[2]; g6.y = ax[3]; g6.z = ax[4]; g6.w = ax[5];
+                V(GR5, k) = g5;
+                V(GS6, k) = g6;
             } else {
-                xn[0] = xr[0]; xn[1] = xr[1]; xn[2] = xr[2];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ax[j] = q.Sw[j];
             }
-            real ax[6], req[3];
-            const real llo = initial ? real(0.0) : (real)S(FB + 3, k);
-            real lnlo;
-            if (k < C - 1) lnlo = initial ? real(0.0) : (real)S(FB + 3, k < C - 1 ? k + 1 : k);
-            else lnlo = initial ? real(0.0) : lor;
-            stage_ax(q, sp, x, xn, llo, lnlo, ax, req);
             const real oyv[3] = {oy.x, oy.y, oy.z};
             real wo[3], wk, wc[2], bk[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 real zmax;  // z - A x
                 if (sp.last && r < 2) zmax = zend[r] - ax[r];
-                else zmax = initial ? (z0_out(warm, r, k) - ax[r]) : -req[r];
+                else zmax = (initial ? z0_out(warm, r, k) : q.ob[r]) - ax[r];
                 wo[r] = q.Ro[r] * (zmax - oyv[r]);
             }
             wk = q.Rk * ((x1.z - ax[3]) - x1.w);
@@ -1168,7 +1183,7 @@ struct QpWarp {
             bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
             bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
-            bv.w = llo;
+            bv.w = real(0.0);
             V(GBV, k) = bv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
@@ -1337,27 +1352,29 @@ struct QpWarp {
 
     // -------------------------------------------------------------- one ADMM update, increment form
     // in: GBV = dx (state part) of the solve K dx = -(P x + A'(y + R (A x - z))); dt / dn are dx of
-    // this / the next stage, xn the next stage's stored x. Same outputs as update_stage; the rhs
-    // produced is again the increment-form one.
+    // this / the next stage. The row values A x are carried in the FS slots (q.Sw) and advanced by
+    // alpha A dx - never re-evaluated from the rounded x - so their error scales with |dx|.
+    // Same outputs as update_stage; the rhs produced is again the increment-form one.
     template <bool kCheck>
-    PQP_DEV void update_stage_incr(int k, bool first, bool warm, Vec4 x0, const real (&dt)[3], const real (&dn)[3],
-                                   const real (&xn)[3], real &llo, real lnlo, real (&wo)[3], real (&bk)[3]) {
+    PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
+                                   real (&wo)[3], real (&bk)[3]) {
         const StagePred sp = pred(k);
         StageRO q;
-        load_ro6(k, q);
-        Vec4 x1, oy, cz;
-        load_rw3(k, x1, oy, cz);
+        load_ro(k, q);
+        Vec4 x0, x1, oy, cz;
+        load_rw(k, x0, x1, oy, cz);
         real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
-        real ax[6], req[3];
-        stage_ax(q, sp, x, xn, llo, lnlo, ax, req);
+        real ax[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ax[j] = q.Sw[j];
         const real oyv[3] = {oy.x, oy.y, oy.z};
         // z - A x of the outgoing rows at the old iterate
         real zo_old[3], zmax[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            if (sp.last && r < 2) { zo_old[r] = zend[r]; zmax[r] = zend[r] - ax[r]; }
-            else if (first) { zo_old[r] = z0_out(warm, r, k); zmax[r] = zo_old[r] - ax[r]; }
-            else { zo_old[r] = q.ob[r]; zmax[r] = -req[r]; }
+            if (sp.last && r < 2) zo_old[r] = zend[r];
+            else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
+            zmax[r] = zo_old[r] - ax[r];
         }
         // increments of the eliminated variables (their rhs recomputed from the old iterates)
         const real pu = sp.mid ? w_dkappa : real(0.0);
@@ -1368,125 +1385,118 @@ struct QpWarp {
         const real du = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * dt[2] + sp.gn * dn[2]));
         const real ds0 = q.mis0 * (aux_s0 - q.Rc[0] * (dt[0] + sp.h0 * dt[1]));
         const real ds1 = q.mis1 * (aux_s1 - q.Rc[1] * (dt[0] + sp.h1 * dt[1]));
-        // A dx
+        // alpha A dx
         real dz[6];
-        dz[0] = q.a00 * dt[0] + q.a01 * dt[1] + sp.gn * dn[0];
-        dz[1] = q.a10 * dt[0] + q.a11 * dt[1] + q.a12 * dt[2] + sp.gn * dn[1];
-        dz[2] = sp.a22 * dt[2] + q.ds * du + sp.gn * dn[2];
-        dz[3] = sp.real ? dt[2] : real(0.0);
-        dz[4] = sp.act0 ? (dt[0] + sp.h0 * dt[1] + ds0) : real(0.0);
-        dz[5] = sp.act1 ? (dt[0] + sp.h1 * dt[1] + ds1) : real(0.0);
+        dz[0] = alpha * (q.a00 * dt[0] + q.a01 * dt[1] + sp.gn * dn[0]);
+        dz[1] = alpha * (q.a10 * dt[0] + q.a11 * dt[1] + q.a12 * dt[2] + sp.gn * dn[1]);
+        dz[2] = alpha * (sp.a22 * dt[2] + q.ds * du + sp.gn * dn[2]);
+        dz[3] = sp.real ? alpha * dt[2] : real(0.0);
+        dz[4] = sp.act0 ? alpha * (dt[0] + sp.h0 * dt[1] + ds0) : real(0.0);
+        dz[5] = sp.act1 ? alpha * (dt[0] + sp.h1 * dt[1] + ds1) : real(0.0);
         // x+ = x + alpha dx
-        {   // l + l_lo += alpha dl (fast two-sum: the increment is far below l)
-            const real t = llo + alpha * dt[0];
-            const real hi = x[0] + t;
-            llo = t - (hi - x[0]);
-            x[0] = hi;
-        }
-        x[1] += alpha * dt[1]; x[2] += alpha * dt[2];
+        x[0] += alpha * dt[0]; x[1] += alpha * dt[1]; x[2] += alpha * dt[2];
         x[3] += alpha * du; x[4] += alpha * ds0; x[5] += alpha * ds1;
         x0.x = x[0]; x0.y = x[1]; x0.z = x[2]; x0.w = x[3]; x1.x = x[4]; x1.y = x[5];
-        // rows. zt - z_old = alpha (z~ - z_old) with z~ = A x + A dx; new (z - A x) = z+ - (A x + alpha A dx)
+        // rows: zt = z_old + alpha (z~ - z_old) = z_old + (alpha A dx - alpha (z_old - A x));
+        // afterwards A x+ = A x + alpha A dx
         real wk, wc[2], oyn[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const real bnd = q.ob[r];
-            // alpha (z~ - z_old) = alpha (A dx - (z_old - A x))
-            const real step = alpha * (dz[r] - zmax[r]);
+            const real step = dz[r] - alpha * zmax[r];
+            const real axn = ax[r] + dz[r];
             real zn, dyr;
             if (sp.last && r < 2) {
-                const real zh = (zo_old[r] + step) + oyv[r];
+                const real zt = zo_old[r] + step;
+                const real zh = zt + oyv[r];
                 zn = clampf(zh, bnd, bnd + endw[r]);
                 zend[r] = zn;
                 oyn[r] = zh - zn;
-                dyr = (zo_old[r] + step) - zn;
-                wo[r] = q.Ro[r] * (((zn - ax[r]) - alpha * dz[r]) - oyn[r]);
+                dyr = zt - zn;
             } else {
-                // equality row: z+ = b; yhat+ = (z_old + step) + yhat - b, z_old - b = 0 unless `first`
+                // equality row: z+ = b, yhat+ = yhat + (z_old + step - b); z_old = b unless `first`
                 zn = bnd;
-                const real off = first ? (zo_old[r] - bnd) : real(0.0);
-                dyr = step + off;
+                dyr = step + (zo_old[r] - bnd);
                 oyn[r] = oyv[r] + dyr;
-                // new z - A x = b - (A x + alpha A dx) = -(req + alpha A dx)
-                wo[r] = q.Ro[r] * (-(req[r] + alpha * dz[r]) - oyn[r]);
             }
+            wo[r] = q.Ro[r] * ((zn - axn) - oyn[r]);
+            ax[r] = axn;
             if (kCheck) cert_row(r, k, q.Ro[r] * dyr, bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
         }
         oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
         {
-            const real zt = x1.z + alpha * (dz[3] - (x1.z - ax[3]));
+            const real zt = x1.z + (dz[3] - alpha * (x1.z - ax[3]));
             const real zh = zt + x1.w;
             const real zn = clampf(zh, -kmax, kmax);
+            ax[3] += dz[3];
             x1.z = zn;
             x1.w = zh - zn;
-            wk = q.Rk * (((zn - ax[3]) - alpha * dz[3]) - x1.w);
+            wk = q.Rk * ((zn - ax[3]) - x1.w);
             if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
         }
         {
-            const real zt = cz.x + alpha * (dz[4] - (cz.x - ax[4]));
+            const real zt = cz.x + (dz[4] - alpha * (cz.x - ax[4]));
             const real zh = zt + cz.z;
             const real zn = clampf(zh, q.clo[0], q.chi[0]);
+            ax[4] += dz[4];
             cz.x = zn;
             cz.z = zh - zn;
-            wc[0] = q.Rc[0] * (((zn - ax[4]) - alpha * dz[4]) - cz.z);
+            wc[0] = q.Rc[0] * ((zn - ax[4]) - cz.z);
             if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
         }
         {
-            const real zt = cz.y + alpha * (dz[5] - (cz.y - ax[5]));
+            const real zt = cz.y + (dz[5] - alpha * (cz.y - ax[5]));
             const real zh = zt + cz.w;
             const real zn = clampf(zh, q.clo[1], q.chi[1]);
+            ax[5] += dz[5];
             cz.y = zn;
             cz.w = zh - zn;
-            wc[1] = q.Rc[1] * (((zn - ax[5]) - alpha * dz[5]) - cz.w);
+            wc[1] = q.Rc[1] * ((zn - ax[5]) - cz.w);
             if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
         }
         V(GX0, k) = x0;
         V(GX1, k) = x1;
         V(GOY, k) = oy;
         V(GCZ, k) = cz;
+        {
+            Vec4 g5, g6;
+            g5.x = q.Rc[0]; g5.y = q.Rc[1]; g5.z = ax[0]; g5.w = ax[1];
+            g6.x = ax[2]; g6.y = ax[3]; g6.z = ax[4]; g6.w = ax[5];
+            V(GR5, k) = g5;
+            V(GS6, k) = g6;
+        }
         local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
 
     template <bool kCheck>
     PQP_DEV void admm_update_incr(bool first, bool warm) {
-        real dnb[3], xrb[3], lorb;
+        real dnb[3];
         {
             const Vec4 v = V(GBV, 0);
             dnb[0] = shfl_down(v.x, 1, lane);
             dnb[1] = shfl_down(v.y, 1, lane);
             dnb[2] = shfl_down(v.z, 1, lane);
-            lorb = shfl_down(v.w, 1, lane);
-            if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = lorb = real(0.0); }
+            if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = real(0.0); }
         }
-        right_x(xrb);  // before any stage is advanced: the neighbour's stage 0 is updated in the first pass
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
         Vec4 dv = V(GBV, 0);
-        Vec4 xcur = V(GX0, 0);
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            const int kn1 = k < C - 1 ? k + 1 : k;
-            Vec4 dw, xw;  // look-ahead: the next stage's dx and stored x (still the old iterate)
-            store.ld4x2(GBV, kn1, GX0, kn1, dw, xw);
+            const Vec4 dw = V(GBV, k < C - 1 ? k + 1 : k);
             const real dt[3] = {dv.x, dv.y, dv.z};
-            real dn[3], xn[3];
+            real dn[3];
             dn[0] = (k == C - 1) ? dnb[0] : dw.x;
             dn[1] = (k == C - 1) ? dnb[1] : dw.y;
             dn[2] = (k == C - 1) ? dnb[2] : dw.z;
-            xn[0] = (k == C - 1) ? xrb[0] : xw.x;
-            xn[1] = (k == C - 1) ? xrb[1] : xw.y;
-            xn[2] = (k == C - 1) ? xrb[2] : xw.z;
             real wo[3], bk[3];
-            real llo = dv.w;
-            const real lnlo = (k == C - 1) ? lorb : dw.w;
-            update_stage_incr<kCheck>(k, first, warm, xcur, dt, dn, xn, llo, lnlo, wo, bk);
-            xcur = xw;
+            update_stage_incr<kCheck>(k, first, warm, dt, dn, wo, bk);
             Vec4 bv;
             bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
             bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
-            bv.w = llo;
+            bv.w = real(0.0);
             V(GBV, k) = bv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
@@ -1536,7 +1546,7 @@ struct QpWarp {
                     ev[r] = (cl == 3 || !(Rr > real(0.0))) ? real(0.0) : Rr * xfast_rsqrt(Rr) * kc;
                 }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(S(FS + j, k));
+                for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(s_weight<real>(j, k, sp));
             }
             const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
