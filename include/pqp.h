@@ -117,9 +117,9 @@ typedef struct pqp_params {
                                        4 = do not re-solve suspected-infeasible instances in FP64,
                                        8 = FP32 state in tensor memory (persistent CTAs, tcgen05.ld/st),
                                        16 = FP32 state in shared memory even where tensor memory is the default,
-                                       32 = ADMM step in increment form (dx solve, l carried as l + l_lo): the FP32
-                                            kernel then follows the FP64 iteration count for count; default only
-                                            where it is also faster (64 <= n_max <= 127, shared-memory policy),
+                                       32 = ADMM step in increment form (dx solve, carried row values): the FP32
+                                            kernel then follows an FP64 OSQP iteration count for count; the
+                                            default for n_max >= 64 (bit 32 forces it below as well),
                                        64 = textbook form everywhere */
 } pqp_params;
 

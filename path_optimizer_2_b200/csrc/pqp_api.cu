@@ -899,11 +899,13 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     // instances. Bits 8 / 16 force one or the other.
     const bool auto_tmem = h->chunk == 8 || (h->chunk == 4 && batch_max <= 4096);
     h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (auto_tmem && (params->reserved & 16) == 0));
-    // form of the ADMM step (FP32 kernels): the increment form follows the FP64 oracle's rho schedule
-    // (same iteration count in 98-99 % of instances, ~6 % fewer iterations) for ~8 % more instructions
-    // per iteration - a net win only where spare issue slots absorb them: 64 <= n_max <= 127 under the
-    // shared-memory policy (+4 %; -4 % at n = 240, -7 % at n = 60). Bits 32 / 64 force one or the other.
-    h->incr = !h->fp64 && ((params->reserved & 32) != 0 || ((params->reserved & 64) == 0 && h->chunk == 4 && !h->use_tmem));
+    // form of the ADMM step (FP32 kernels): the increment form (dx solve, row values A x carried and
+    // advanced by alpha A dx) follows the FP64 oracle's rho schedule - same iteration count in ~99-100 %
+    // of instances, ~6 % fewer iterations - for ~6 % more work per iteration. Measured against the
+    // textbook form: n = 240 equal (892 k solves/s), n = 120 +5 %, the 1024 x 120 shared-map batch
+    // +15 % (one wave: its slowest instances need fewer iterations), n = 60 -3.5 %. Default: increment
+    // form for n_max >= 64, textbook form below; bits 32 / 64 force one or the other.
+    h->incr = !h->fp64 && ((params->reserved & 32) != 0 || ((params->reserved & 64) == 0 && h->chunk >= 4));
     if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;

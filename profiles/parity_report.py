@@ -52,8 +52,8 @@ if __name__ == "__main__":
     report("BASELINE configs[2] slice (per-instance bounds)", synthetic.make_batch(3, 2048, 240))
     report("ragged n", synthetic.make_batch(7, 1024, 240, ragged=True))
     report("n = 120", synthetic.make_batch(3, 2048, 120))
-    report("n = 240, increment form of the ADMM step (option bit 32)", synthetic.make_batch(3, 2048, 240), bits=32)
-    report("n = 120, increment form (option bit 32; the default there under the shared-memory policy)", synthetic.make_batch(3, 2048, 120), bits=32)
+    report("n = 240, textbook form of the ADMM step (option bit 64; the default is the increment form)", synthetic.make_batch(3, 2048, 240), bits=64)
+    report("n = 120, textbook form (option bit 64)", synthetic.make_batch(3, 2048, 120), bits=64)
     report("n = 60, increment form (option bit 32)", synthetic.make_batch(3, 2048, 60), bits=32)
     report("FP64 instantiation (must reproduce the oracle)", synthetic.make_batch(3, 512, 240), bits=2)
     try:

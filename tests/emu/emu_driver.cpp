@@ -14,7 +14,7 @@ struct EmuHandle {
     pqp_params prm;
     int n_max, batch_max, chunk;
     bool fp64 = false;  // params.reserved bit 1: run the FP64 instantiation
-    bool incr = false;  // increment form of the ADMM step (bit 32; bit 64 forces the textbook form; default C == 4)
+    bool incr = false;  // increment form of the ADMM step (bit 32; bit 64 forces the textbook form; default C >= 4)
     std::vector<double> warm, scal, dy, rho;   // sized for the wider scalar type
     std::vector<double> smem;
     bool solved = false;
@@ -33,7 +33,7 @@ void run_form(const pqp::KernelArgs &ka, int qp, real *smem) {
     warp_emu::current() = nullptr;
 }
 // both forms of the ADMM step are instantiated for both scalar types (the library only builds the
-// increment form in FP32); `incr` as the library decides it: reserved bit 32 / 64, default C == 4
+// increment form in FP32); `incr` as the library decides it: reserved bit 32 / 64, default C >= 4
 template <int C, typename real>
 void run_one(const pqp::KernelArgs &ka, int qp, real *smem, bool incr) {
     if (incr) run_form<C, real, true>(ka, qp, smem);
@@ -112,7 +112,7 @@ void *emu_create(const pqp_params *prm, int n_max, int batch_max) {
     h->chunk = pqp::chunk_for(n_max);
     const int c = h->chunk;
     h->fp64 = (prm->reserved & 2) != 0;
-    h->incr = (prm->reserved & 32) != 0 || ((prm->reserved & 64) == 0 && !h->fp64 && h->chunk == 4);
+    h->incr = (prm->reserved & 32) != 0 || ((prm->reserved & 64) == 0 && !h->fp64 && h->chunk >= 4);
     h->warm.assign((size_t)batch_max * pqp::warm_floats(c), 0.0);
     h->scal.assign((size_t)batch_max * pqp::scal_floats(c), 0.0);
     h->dy.assign((size_t)batch_max * pqp::dy_floats(c), 0.0);

@@ -278,10 +278,10 @@ def test_advance_window_on_device_matches_host_bookkeeping(solver_mod):
 
 @pytest.mark.parametrize("n", [60, 120, 240])
 def test_increment_form_tracks_the_oracle_iteration_counts(solver_mod, n):
-    """params.reserved bit 32: ADMM step in increment form (dx solve, l carried as l + l_lo). Same
-    iteration in exact arithmetic; in FP32 its rounding error scales with |dx|, so the kernel follows
-    the FP64 oracle's rho schedule: identical iteration count in >= 95 % of instances (measured
-    98.9-99.3 % over 2048; the textbook form reaches 85 %), never further than 4 check intervals."""
+    """params.reserved bit 32 (the default for n_max >= 64): ADMM step in increment form (dx solve, row
+    values A x carried). Same iteration in exact arithmetic; in FP32 its rounding error scales with
+    |dx|, so the kernel follows the FP64 oracle's rho schedule: identical iteration count in >= 95 %
+    of instances (the textbook form reaches 85 %), never further than 4 check intervals."""
     from oracle import oracle
     hb = synthetic.make_batch(3, 256, n)
     sv = solver_mod.PathQpSolver(abi.default_params(reserved=32), n_max=n, batch_max=hb.batch)
