@@ -179,17 +179,6 @@ struct TmemStore {
         }
         tmem_wait_ld();
     }
-    __device__ void ld4x2(int ga, int ka, int gb, int kb, float4 &a, float4 &b) const {
-        float oa[4], ob[4];
-        const bool sa = spilled(ga), sb = spilled(gb);
-        if (sa) { const float4 v = *sp(ga, ka); oa[0] = v.x; oa[1] = v.y; oa[2] = v.z; oa[3] = v.w; }
-        else tmem_ld4_nowait(col(ga, ka), oa);
-        if (sb) { const float4 v = *sp(gb, kb); ob[0] = v.x; ob[1] = v.y; ob[2] = v.z; ob[3] = v.w; }
-        else tmem_ld4_nowait(col(gb, kb), ob);
-        if (!sa || !sb) tmem_wait_ld();
-        a = make_float4(oa[0], oa[1], oa[2], oa[3]);
-        b = make_float4(ob[0], ob[1], ob[2], ob[3]);
-    }
     __device__ void fence() { tmem_wait_st(); }
 };
 

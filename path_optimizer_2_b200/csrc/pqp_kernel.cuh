@@ -300,11 +300,6 @@ struct SmemStore {
             out[4 * g] = v.x; out[4 * g + 1] = v.y; out[4 * g + 2] = v.z; out[4 * g + 3] = v.w;
         }
     }
-    // two unrelated groups with one latency (tensor memory: one wait for both loads)
-    PQP_DEV void ld4x2(int ga, int ka, int gb, int kb, Vec4 &a, Vec4 &b) const {
-        a = ld4(ga, ka);
-        b = ld4(gb, kb);
-    }
     PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
 };
 
@@ -995,25 +990,6 @@ struct QpWarp {
         q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
         q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
         q.Sw[2] = t[24]; q.Sw[3] = t[25]; q.Sw[4] = t[26]; q.Sw[5] = t[27];
-    }
-    // the same without the proximal weights S (increment form: no S x term in the rhs)
-    PQP_DEV void load_ro6(int k, StageRO &q) {
-        real t[24];
-        store.template ld4n<6>(GA0, k, t);
-        q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
-        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
-        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
-        q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
-        q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
-        q.Rc[0] = t[20]; q.Rc[1] = t[21];
-    }
-    // GX1, GOY, GCZ of stage k (the caller carries GX0 over from the previous stage's look-ahead)
-    PQP_DEV void load_rw3(int k, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
-        real t[12];
-        store.template ld4n<3>(GX1, k, t);
-        x1.x = t[0]; x1.y = t[1]; x1.z = t[2]; x1.w = t[3];
-        oy.x = t[4]; oy.y = t[5]; oy.z = t[6]; oy.w = t[7];
-        cz.x = t[8]; cz.y = t[9]; cz.z = t[10]; cz.w = t[11];
     }
     // the four read-write groups of stage k (x, s/kappa-row, yhat, clearance z/yhat)
     PQP_DEV void load_rw(int k, Vec4 &x0, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
