@@ -61,7 +61,8 @@ constexpr int kSolved = 0, kMaxIter = 1, kPrimInf = 2, kDualInf = 3, kSolvedInac
 // Per-stage data is stored as 18 float4 groups; element (group g, local stage k, lane) is the
 // float4 at index (g*C + k)*32 + lane, so a warp's access to one group of one stage is one
 // conflict-free 512-byte LDS.128/STS.128. The logical field number f = 4*g + component.
-// Groups 0-6 are read-only inside the ADMM loop, 7-11 are read-write, 12-17 are the factor.
+// Groups 0-6 are read-only inside the ADMM loop (in the increment form the FS slots of groups 5-6
+// are rewritten every iteration), 7-11 are read-write, 12-17 are the factor.
 enum : int {
     FA = 0,     // 6: a00 a01 a10 a11 | a12 ds        (stage transition coefficients)
     FE = 6,     // 3: 1/m_u 1/m_s0 | 1/m_s1            (closed-form elimination constants)
@@ -70,7 +71,8 @@ enum : int {
     FKR = 15,   //    kappa-row weight R
     FCLO = 16, FCHI = 18,  // clearance-row bounds (2 each)
     FCR = 20,   // 2: clearance-row weights R
-    FS = 22,    // 6: S_j = sigma / (c d_j^2)          (proximal weights)
+    FS = 22,    // 6: S_j = sigma / (c d_j^2) (proximal weights) in the textbook form; in the
+                //    increment form the carried row values A x of the stage's six rows
     FX = 28,    // 6: l, psi, kappa, u | s0, s1        (primal iterate x)
     FKZ = 34, FKY = 35,    // kappa box row: z, yhat
     FOY = 36,   // 3: outgoing-row scaled dual yhat    (+1 pad)
