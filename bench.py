@@ -609,6 +609,9 @@ def main():
                 "mean_admm_iters": float(np.mean(iters)),
                 "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
                 "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
+                "admm_step": ("increment form (dx solve, carried row values)"
+                              if (args.option_bits & 32) or (not (args.option_bits & (64 | 2)) and n >= 64)
+                              else "textbook form"),
                 "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if info["smem_per_warp"] < 72 * 128 else "shared memory",
             },
             "clocks": clocks,
