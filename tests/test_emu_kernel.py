@@ -124,3 +124,19 @@ def test_emulated_fp32_tracks_the_oracle_iteration_for_iteration():
         nv = 6 * hb.n - 1
         dx = np.array([np.max(np.abs(g.x_full[b, :nv[b]] - o.x_full[b, :nv[b]])) for b in np.nonzero(ok)[0]])
         assert np.median(dx) < 1e-4
+
+
+def test_emulated_fp32_increment_form_certifies_infeasibility_like_the_oracle():
+    """With the increment form the FP32 iterates resolve OSQP's primal-infeasibility certificate
+    (|A'dy| < 1e-4 |dy|) themselves: same status and iteration count as the FP64 oracle without the
+    FP64 escalation; the textbook form runs to the cap on the same instance."""
+    from oracle import oracle
+    hb = synthetic.make_batch(103, 6, 3)
+    ref = [oracle.OracleSolver(abi.default_params(), hb.knots[b], hb.inst[b], 3) for b in range(6)]
+    exp = [(s.solve(), s.iters) for s in ref]
+    assert (abi.PQP_PRIMAL_INFEASIBLE, 125) in exp
+    r = emu.EmuSolver(abi.default_params(reserved=4 | 32), 3, 6).solve(hb)
+    assert list(zip(r.status.tolist(), r.iters.tolist())) == exp
+    t = emu.EmuSolver(abi.default_params(reserved=4 | 64), 3, 6).solve(hb)
+    bad = [i for i, e in enumerate(exp) if e[0] == abi.PQP_PRIMAL_INFEASIBLE]
+    assert all(t.iters[i] == 4000 for i in bad)
