@@ -120,7 +120,11 @@ typedef struct pqp_params {
                                        32 = ADMM step in increment form (dx solve, carried row values): the FP32
                                             kernel then follows an FP64 OSQP iteration count for count; the
                                             default for n_max >= 64 (bit 32 forces it below as well),
-                                       64 = textbook form everywhere */
+                                       64 = textbook form everywhere,
+                                       128 = cold-only handle: no warm state is kept or written back
+                                             (pqp_resolve* returns PQP_E_STATE); for batches that are only
+                                             ever solved once (BASELINE configs[2]/[3]) this removes 18 KB
+                                             per instance of HBM write traffic */
 } pqp_params;
 
 /* Batch input. All pointers are HOST pointers for pqp_solve/pqp_resolve and DEVICE
@@ -168,7 +172,7 @@ typedef struct pqp_handle pqp_handle;
 int pqp_default_params(pqp_params *params);
 
 /* Create a solver bound to CUDA device `device` able to hold `batch_max` instances of up
- * to `n_max` knots (2 <= n_max <= 255). Owns device buffers for inputs, outputs and the
+ * to `n_max` knots (2 <= n_max <= 511; the reference itself has no cap). Owns device buffers for inputs, outputs and the
  * per-instance warm state (scaled x, z, y and rho; the OSQP workspace of
  * base_solver.hpp:62). */
 int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32_t device,
@@ -185,7 +189,14 @@ int pqp_solve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out);
 int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out);
 
 /* Same, with DEVICE pointers and the caller's stream (a cudaStream_t passed as void*,
- * NULL = default stream). Asynchronous: no host synchronisation inside. */
+ * NULL = default stream). Asynchronous: no host synchronisation inside. Two differences from the
+ * host-pointer calls follow from that: (1) n[] and p[] cannot be validated on the host - an instance
+ * whose n is outside [2, n_max] is skipped by the kernel with status PQP_NUMERICAL_ERROR; (2) there
+ * is no FP64 re-solve of suspected-infeasible instances (that needs the statuses on the host): an
+ * infeasible instance the FP32 certificate cannot resolve ends as PQP_MAX_ITER_REACHED here and as
+ * PQP_PRIMAL_INFEASIBLE through pqp_solve. Both mean `false` to the reference's caller
+ * (base_solver.cpp:88). After a host-pointer call escalated an instance, its warm slot is reset to
+ * the cold state (zero iterates, rho = params.rho). */
 int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
                      void *stream);
 int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
@@ -221,6 +232,23 @@ int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n,
  * number of kernel launches the handle has issued so far. */
 int pqp_last_kernel_ms(pqp_handle *h, float *ms);
 int pqp_launch_count(pqp_handle *h, int64_t *count);
+
+/* Per-stage device times (ms, CUDA events) of the last host-pointer solve/resolve: the counterpart of
+ * the TimeRecorder stages BaseSolver::solve logs (base_solver.cpp:57-93: "Set cost", "Set
+ * constraints", "Set solver", "OSQP Solve", "Retrive path"). Cost, constraints, solver set-up and
+ * the ADMM loop are ONE kernel here, so the stages are: host-to-device copy, kernel, device-to-host
+ * copy, FP64 re-solve of suspected-infeasible instances, whole call. ms[PQP_NSTAGES]. The three
+ * pipeline stages are only defined for single-stream calls (batches below the chunking threshold,
+ * i.e. the B = 1 drop-in); chunked / streamed calls overlap them and report -1 there. */
+enum {
+    PQP_STAGE_H2D = 0,
+    PQP_STAGE_KERNEL = 1,
+    PQP_STAGE_D2H = 2,
+    PQP_STAGE_ESCALATION = 3,
+    PQP_STAGE_TOTAL = 4,
+    PQP_NSTAGES = 5
+};
+int pqp_last_stage_ms(pqp_handle *h, float *ms);
 
 /* Device-side properties, for occupancy reporting: SM count, resident warps per SM of
  * the solve kernel, dynamic shared memory per warp in bytes (the whole per-QP state under the

@@ -59,6 +59,15 @@ def lib():
         L.pqo_solve_batch.argtypes = [C.POINTER(abi.PqpParams), C.POINTER(abi.PqpBatchIn),
                                       C.POINTER(abi.PqpBatchOut), C.c_int, C.c_int, C.c_int]
         L.pqo_max_threads.restype = C.c_int
+        L.pqo_omp_probe.argtypes = [C.c_int]
+        L.pqo_omp_probe.restype = C.c_int
+        L.pqo_termination_batch.argtypes = [C.POINTER(abi.PqpParams), C.POINTER(abi.PqpBatchIn), vp, vp, vp, vp, C.c_int]
+        L.pqo_batch_setup.restype = vp
+        L.pqo_batch_setup.argtypes = [C.POINTER(abi.PqpParams), C.POINTER(abi.PqpBatchIn), C.c_int]
+        L.pqo_batch_update_full.argtypes = [vp, C.POINTER(abi.PqpBatchIn), C.c_int]
+        L.pqo_batch_solve.restype = C.c_double
+        L.pqo_batch_solve.argtypes = [vp, C.POINTER(abi.PqpBatchOut), C.c_int]
+        L.pqo_batch_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -183,6 +192,53 @@ def solve_batch(params, hb: abi.HostBatch, *, nthreads=1, mode=0, dense_assembly
 
 def max_threads():
     return lib().pqo_max_threads()
+
+
+def termination_batch(params, hb: abi.HostBatch, x_full, y_full, z_full, *, nthreads=None):
+    """OSQP's unscaled termination test of the given points, FP64, on the oracle-assembled problems
+    (linearisation fields of `hb` included). Returns dict of per-instance arrays."""
+    x, y, z = (np.ascontiguousarray(v, dtype=np.float64) for v in (x_full, y_full, z_full))
+    rep = np.zeros((hb.batch, 6))
+    bi = hb.as_struct()
+    rc = lib().pqo_termination_batch(C.byref(params), C.byref(bi), x.ctypes.data, y.ctypes.data, z.ctypes.data,
+                                     rep.ctypes.data, int(nthreads or max_threads()))
+    if rc:
+        raise RuntimeError("pqo_termination_batch failed")
+    return dict(pri_res=rep[:, 0], eps_pri=rep[:, 1], dua_res=rep[:, 2], eps_dua=rep[:, 3], z_violation=rep[:, 4],
+                cost=rep[:, 5])
+
+
+class OracleBatch:
+    """One persistent OSQP-style workspace per path (the reference's solver object), for warm
+    re-solve sequences: solve() / update_full(hb) / solve() ..."""
+
+    def __init__(self, params, hb: abi.HostBatch, nthreads=None):
+        self.L, self.params = lib(), params
+        self.nthreads = int(nthreads or max_threads())
+        self.batch, self.n_max = hb.batch, hb.n_max
+        bi = hb.as_struct()
+        self.pb = self.L.pqo_batch_setup(C.byref(params), C.byref(bi), self.nthreads)
+        if not self.pb:
+            raise RuntimeError("pqo_batch_setup failed")
+
+    def solve(self, full=False):
+        res = abi.HostResult(self.batch, self.n_max, full=full)
+        bo = res.as_struct()
+        if self.L.pqo_batch_solve(self.pb, C.byref(bo), self.nthreads) < 0:
+            raise RuntimeError("pqo_batch_solve failed")
+        return res
+
+    def update_full(self, hb: abi.HostBatch):
+        bi = hb.as_struct()
+        if self.L.pqo_batch_update_full(self.pb, C.byref(bi), self.nthreads):
+            raise RuntimeError("pqo_batch_update_full failed")
+
+    def close(self):
+        if getattr(self, "pb", None):
+            self.L.pqo_batch_free(self.pb)
+            self.pb = None
+
+    __del__ = close
 
 
 def frenet_to_cartesian(ref_xyh, l, psi):

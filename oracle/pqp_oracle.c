@@ -1049,3 +1049,149 @@ int pqo_omp_probe(int nthreads) {
 #endif
     return cnt;
 }
+
+/* ------------------------------------------------------------------ batch checkers (tests only)
+ * OSQP's own unscaled termination test of a GIVEN point (x, y, z) - e.g. the
+ * CUDA library's x_full / y_full / z_full outputs, reference index order - evaluated in FP64 on the
+ * (P, A, l, u) this oracle assembles from the same inputs (linearisation fields included), for every
+ * instance of a batch. rep[b*6] = {pri_res, eps_pri, dua_res, eps_dua, worst violation of l <= z <= u
+ * on finite bounds, 0.5 x'Px}. Returns 0, or -1 if an instance could not be set up. */
+int pqo_termination_batch(const pqp_params *prm, const pqp_batch_in *in, const double *x_full,
+                          const double *y_full, const double *z_full, double *rep, int nthreads) {
+    if (!prm || !in || !x_full || !y_full || !z_full || !rep) return -1;
+    const int B = in->batch, nmax = in->n_max;
+    const int nvmax = 6 * nmax - 1, mmax = 6 * nmax + 2;
+    int err = 0;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+    for (int b = 0; b < B; ++b) {
+        const int n = in->n[b];
+        const int p = in->p ? in->p[b] : n;
+        pqo_ws *w = pqo_setup(prm, n, p, in->knots + (size_t)b * PQP_NFIELDS * nmax, nmax,
+                              in->inst + (size_t)b * PQP_NINST);
+        if (!w) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            err = 1;
+            continue;
+        }
+        const double *x = x_full + (size_t)b * nvmax, *y = y_full + (size_t)b * mmax, *z = z_full + (size_t)b * mmax;
+        double *Ax = (double *)calloc((size_t)w->m, sizeof(double));
+        double nAx = 0.0, nz = 0.0, pri = 0.0, viol = 0.0, dua = 0.0, nPx = 0.0, nAty = 0.0, cost = 0.0;
+        for (int j = 0; j < w->nv; ++j)
+            for (int e = w->Ap[j]; e < w->Ap[j + 1]; ++e) Ax[w->Ai[e]] += w->Ax0[e] * x[j];
+        for (int i = 0; i < w->m; ++i) {
+            pri = dmax(pri, fabs(Ax[i] - z[i]));
+            nAx = dmax(nAx, fabs(Ax[i]));
+            nz = dmax(nz, fabs(z[i]));
+            if (w->l0[i] > -1e29) viol = dmax(viol, w->l0[i] - z[i]);
+            if (w->u0[i] < 1e29) viol = dmax(viol, z[i] - w->u0[i]);
+        }
+        for (int j = 0; j < w->nv; ++j) {
+            double aty = 0.0;
+            for (int e = w->Ap[j]; e < w->Ap[j + 1]; ++e) aty += w->Ax0[e] * y[w->Ai[e]];
+            const double px = w->Pd0[j] * x[j];
+            dua = dmax(dua, fabs(px + aty));
+            nPx = dmax(nPx, fabs(px));
+            nAty = dmax(nAty, fabs(aty));
+            cost += 0.5 * px * x[j];
+        }
+        double *r = rep + (size_t)b * 6;
+        r[0] = pri;
+        r[1] = prm->eps_abs + prm->eps_rel * dmax(nAx, nz);
+        r[2] = dua;
+        r[3] = prm->eps_abs + prm->eps_rel * dmax(nPx, nAty);  /* q = 0 */
+        r[4] = viol;
+        r[5] = cost;
+        free(Ax);
+        pqo_free(w);
+    }
+    return err ? -1 : 0;
+}
+
+/* A batch of persistent workspaces: the reference's solver object per path, kept across the warm
+ * re-solves of a receding-horizon run (BASELINE configs[4]). */
+struct pqo_batch {
+    int B, nmax;
+    pqo_ws **w;
+};
+
+void pqo_batch_free(pqo_batch *pb) {
+    if (!pb) return;
+    for (int b = 0; b < pb->B; ++b) pqo_free(pb->w[b]);
+    free(pb->w);
+    free(pb);
+}
+pqo_batch *pqo_batch_setup(const pqp_params *prm, const pqp_batch_in *in, int nthreads) {
+    if (!prm || !in) return NULL;
+    pqo_batch *pb = (pqo_batch *)calloc(1, sizeof(pqo_batch));
+    pb->B = in->batch;
+    pb->nmax = in->n_max;
+    pb->w = (pqo_ws **)calloc((size_t)in->batch, sizeof(pqo_ws *));
+    int err = 0;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+    for (int b = 0; b < in->batch; ++b) {
+        pb->w[b] = pqo_setup(prm, in->n[b], in->p ? in->p[b] : in->n[b], in->knots + (size_t)b * PQP_NFIELDS * in->n_max,
+                             in->n_max, in->inst + (size_t)b * PQP_NINST);
+        if (!pb->w[b]) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            err = 1;
+        }
+    }
+    if (err) { pqo_batch_free(pb); return NULL; }
+    return pb;
+}
+/* osqp_update_bounds + osqp_update_A of every instance from a new knot/inst block (pqo_update_full) */
+int pqo_batch_update_full(pqo_batch *pb, const pqp_batch_in *in, int nthreads) {
+    if (!pb || !in || in->batch != pb->B || in->n_max != pb->nmax) return -1;
+    int err = 0;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+    for (int b = 0; b < pb->B; ++b)
+        if (pqo_update_full(pb->w[b], in->knots + (size_t)b * PQP_NFIELDS * pb->nmax, pb->nmax, in->inst + (size_t)b * PQP_NINST)) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            err = 1;
+        }
+    return err ? -1 : 0;
+}
+/* solve every instance (warm after the first call) and write the batch outputs */
+double pqo_batch_solve(pqo_batch *pb, const pqp_batch_out *out, int nthreads) {
+    if (!pb || !out || !out->sol) return -1.0;
+    const int nmax = pb->nmax, nvmax = 6 * nmax - 1, mmax = 6 * nmax + 2;
+    if (nthreads < 1) nthreads = 1;
+    const double t0 = now_s();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (int b = 0; b < pb->B; ++b) {
+        pqo_ws *w = pb->w[b];
+        const int st = pqo_solve(w);
+        pqo_get_sol(w, out->sol + (size_t)b * 4 * nmax, nmax);
+        if (out->cost) out->cost[b] = w->obj_val;
+        if (out->status) out->status[b] = st;
+        if (out->iters) out->iters[b] = w->iter;
+        if (out->x_full) pqo_get_x(w, out->x_full + (size_t)b * nvmax);
+        if (out->y_full) pqo_get_y(w, out->y_full + (size_t)b * mmax);
+        if (out->z_full) pqo_get_z(w, out->z_full + (size_t)b * mmax);
+        if (out->info) {
+            double *inf = out->info + (size_t)b * PQP_NINFO;
+            inf[PQP_INFO_PRI_RES] = w->pri_res;
+            inf[PQP_INFO_DUA_RES] = w->dua_res;
+            inf[PQP_INFO_RHO] = w->rho;
+            inf[PQP_INFO_RHO_UPDATES] = w->rho_updates;
+        }
+    }
+    return now_s() - t0;
+}

@@ -84,6 +84,19 @@ void pqo_frenet_to_cartesian(int n, const double *ref_x, const double *ref_y,
 double pqo_solve_batch(const pqp_params *prm, const pqp_batch_in *in, const pqp_batch_out *out,
                        int nthreads, int mode, int dense_assembly);
 int pqo_max_threads(void);
+int pqo_omp_probe(int nthreads);
+
+/* OSQP's unscaled termination test of a given (x, y, z) per instance, in FP64, on the (P, A, l, u)
+ * assembled here; rep[b*6] = {pri_res, eps_pri, dua_res, eps_dua, worst bound violation of z, 0.5 x'Px}. */
+int pqo_termination_batch(const pqp_params *prm, const pqp_batch_in *in, const double *x_full,
+                          const double *y_full, const double *z_full, double *rep, int nthreads);
+
+/* Persistent per-path workspaces for warm re-solve sequences (receding horizon, configs[4]). */
+typedef struct pqo_batch pqo_batch;
+pqo_batch *pqo_batch_setup(const pqp_params *prm, const pqp_batch_in *in, int nthreads);
+int pqo_batch_update_full(pqo_batch *pb, const pqp_batch_in *in, int nthreads);
+double pqo_batch_solve(pqo_batch *pb, const pqp_batch_out *out, int nthreads);
+void pqo_batch_free(pqo_batch *pb);
 
 #ifdef __cplusplus
 }

@@ -164,6 +164,16 @@ class HostResult:
                            _ptr(self.x_full), _ptr(self.y_full), _ptr(self.z_full),
                            _ptr(self.info))
 
+    def take(self, idx) -> "HostResult":
+        """The instances `idx` as a new (contiguous) result."""
+        idx = np.asarray(idx)
+        r = HostResult.__new__(HostResult)
+        r.batch, r.n_max = int(len(idx)), self.n_max
+        for name in ("sol", "cost", "status", "iters", "x_full", "y_full", "z_full", "info"):
+            v = getattr(self, name)
+            setattr(r, name, None if v is None else np.ascontiguousarray(v[idx]))
+        return r
+
 
 def sizes(n, p=None):
     """(nv, m) of one instance — base_solver.cpp:22-37."""

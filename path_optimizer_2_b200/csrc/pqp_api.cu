@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "pqp_device_guard.h"
 #include "pqp_host_common.h"
 
 namespace {
@@ -85,9 +86,25 @@ __global__ void __launch_bounds__(32) pqp_admm_kernel(const __grid_constant__ pq
         src = stage;
     }
     pqp::QpWarp<C, real, pqp::SmemStore<C, real>, Incr> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
-    w.run(src, ka.n_max);
+    w.run(src, ka.n_max, (size_t)(qp + ka.qp0));
 }
 
+
+// FP64 instantiation at C = 16 (256 <= n_max <= 511): its state (72 x 16 x 32 doubles = 288 KB per QP)
+// exceeds shared memory, so the same storage policy is pointed at a per-CTA block of global memory
+// (it lives in L1/L2; only the owning lane ever touches an element). This is the parity / escalation
+// path, not the throughput path: a few resident CTAs loop over the instances.
+template <int C, typename real, bool Incr>
+__global__ void __launch_bounds__(32) pqp_admm_kernel_gmem(const __grid_constant__ pqp::KernelArgs ka, real *state) {
+    const int lane = threadIdx.x;
+    real *st = state + (size_t)blockIdx.x * pqp::NFIELD * C * 32;
+    for (int qp = blockIdx.x; qp < ka.batch; qp += gridDim.x) {
+        const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
+        pqp::QpWarp<C, real, pqp::SmemStore<C, real>, Incr> w(ka, pqp::SmemStore<C, real>(st, lane), lane, qp);
+        w.run(src, ka.n_max, (size_t)(qp + ka.qp0));
+        __syncwarp();
+    }
+}
 
 // ------------------------------------------------------------------ device: tensor-memory storage policy
 // The solver keeps a QP's per-stage state as [group][stage][lane] float4. Tensor memory is 128
@@ -133,16 +150,31 @@ struct TmemStore {
     static constexpr int kAll = pqp::NFIELD / 4;                       // 18 groups
     static constexpr int kFit = COLS / (4 * C);                        // groups that fit in this warp's columns
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
-    static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8, else 0
+    static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8 (512 columns) and at C = 4 with 256 columns, 10 at C = 16, else 0
     uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
     float *sm;    // spill area (shared memory) of this warp: [spill slot][k][lane] float4
     int lane;
     __device__ TmemStore(uint32_t t, float *s, int l) : tb(t), sm(s), lane(l) {}
-    // groups GR5 (5) and GS6 (6) spill first; everything else keeps its relative order
-    __device__ static constexpr bool spilled(int g) { return kSpill > 0 && (g == pqp::GR5 || g == pqp::GS6) && (g - pqp::GR5) < kSpill; }
-    __device__ static constexpr int slot(int g) { return (kSpill > 0 && g > pqp::GS6) ? g - kSpill : g; }
+    // Which groups leave tensor memory first when the warp's columns do not hold all 18: the
+    // clearance / proximal weights GR5, GS6 (least frequently read), then the other read-only groups
+    // (4, 3, 2, 1, 0), then the factor from its end (17 .. 12), the read-write groups last.
+    __host__ __device__ static constexpr int spill_rank(int g) {
+        return g == pqp::GR5 ? 0 : g == pqp::GS6 ? 1 : g <= 4 ? 6 - g : g >= pqp::GF0 ? 7 + (17 - g) : 13 + (11 - g);
+    }
+    __host__ __device__ static constexpr bool spilled(int g) { return spill_rank(g) < kSpill; }
+    // position among the groups kept in tensor memory / among the spilled ones (ascending group order)
+    __host__ __device__ static constexpr int slot(int g) {
+        int s = 0;
+        for (int j = 0; j < g; ++j) s += spilled(j) ? 0 : 1;
+        return s;
+    }
+    __host__ __device__ static constexpr int spslot(int g) {
+        int s = 0;
+        for (int j = 0; j < g; ++j) s += spilled(j) ? 1 : 0;
+        return s;
+    }
     __device__ uint32_t col(int g, int k) const { return tb + (uint32_t)((k * kGroups + slot(g)) * 4); }
-    __device__ float4 *sp(int g, int k) const { return reinterpret_cast<float4 *>(sm) + (((g - pqp::GR5) * C + k) * 32 + lane); }
+    __device__ float4 *sp(int g, int k) const { return reinterpret_cast<float4 *>(sm) + ((spslot(g) * C + k) * 32 + lane); }
     __device__ float ld(int f, int k) const {
         const int g = f >> 2;
         if (spilled(g)) return reinterpret_cast<const float *>(sp(g, k))[f & 3];
@@ -194,10 +226,11 @@ template <int C, int WT, bool Incr>
 __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_constant__ pqp::KernelArgs ka) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t tbase_s;
-    constexpr int kCols = 512 / (WT / 4);
+    constexpr int kShare = WT > 4 ? WT / 4 : 1;  // warps per tensor-memory sub-partition
+    constexpr int kCols = 512 / kShare;
     typedef TmemStore<C, kCols> Store;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t need = (uint32_t)(Store::kGroups * 4 * C) * (WT / 4);
+    constexpr uint32_t need = (uint32_t)(Store::kGroups * 4 * C) * kShare;
     constexpr uint32_t ncols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     constexpr size_t kSpillFloats = (size_t)(Store::kSpill > 0 ? Store::kSpill : 0) * C * 32 * 4;
     if (warp == 0) tmem_alloc(&tbase_s, ncols);
@@ -238,7 +271,7 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
         }
         const double *src = ka.knots + (size_t)qp * PQP_NFIELDS * ka.n_max;
         pqp::QpWarp<C, float, Store, Incr> w(ka, Store(tb, spill, lane), lane, qp);
-        w.run(src, ka.n_max);
+        w.run(src, ka.n_max, (size_t)(blockIdx.x * WT + warp));
         if (ka.done) {
             __syncwarp();
             if (lane == 0) {
@@ -339,6 +372,7 @@ struct pqp_handle {
     double *d_xf = nullptr, *d_yf = nullptr, *d_zf = nullptr, *d_ref = nullptr, *d_xy = nullptr;
     int *d_n = nullptr, *d_p = nullptr, *d_status = nullptr, *d_iters = nullptr;
     void *d_warm = nullptr, *d_scal = nullptr, *d_dy = nullptr, *d_rho = nullptr;
+    double *d_state64 = nullptr;   // per-CTA state of the FP64 kernel at C = 16 (global memory)
     int *d_ready = nullptr, *d_done = nullptr;      // per-chunk flags of the streamed launch
     int *h_done = nullptr, *d_hdone = nullptr;     // mapped pinned host memory + its device alias
     static const int kCounters = 64;
@@ -348,6 +382,10 @@ struct pqp_handle {
     bool incr = false;             // ADMM step in increment form (FP32 kernels)
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
+    bool cold_only = false;        // params.reserved bit 128: no warm state is kept (pqp_resolve* is refused)
+    float stage_ms[PQP_NSTAGES] = {0, 0, 0, 0, 0};
+    float rho0_f = 0.1f;           // source of the async "slot is cold again" copy after an escalation
+    cudaEvent_t ev_st[4] = {};     // stage boundaries of the single-stream host call
     size_t smem_bytes64 = 0;
     bool prepared64 = false;
     int *d_flags = nullptr;
@@ -369,6 +407,8 @@ struct pqp_handle {
 };
 
 namespace {
+
+using pqp::DeviceGuard;
 
 int fail(pqp_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg;
@@ -395,13 +435,19 @@ cudaError_t launch_form(const pqp::KernelArgs &ka, size_t smem, cudaStream_t s, 
     if (incr && sizeof(real) == 4) return launch<C, float, true>(ka, smem, s);
     return launch<C, real, false>(ka, smem, s);
 }
+// C = 16 exists for FP32 only under the shared-memory policy (144 KB per QP); FP64 uses the
+// global-memory kernel above
+template <typename real> struct Has16 { static constexpr bool value = sizeof(real) == 4; };
 template <typename real>
 cudaError_t launch_chunk(int chunk, const pqp::KernelArgs &ka, size_t smem, cudaStream_t s, bool incr = false) {
     switch (chunk) {
         case 1: return launch_form<1, real>(ka, smem, s, incr);
         case 2: return launch_form<2, real>(ka, smem, s, incr);
         case 4: return launch_form<4, real>(ka, smem, s, incr);
-        default: return launch_form<8, real>(ka, smem, s, incr);
+        case 8: return launch_form<8, real>(ka, smem, s, incr);
+        default:
+            if constexpr (Has16<real>::value) return launch_form<16, real>(ka, smem, s, incr);
+            else return cudaErrorInvalidConfiguration;
     }
 }
 template <int C, typename real, bool Incr>
@@ -421,20 +467,31 @@ cudaError_t prepare_chunk(int chunk, size_t smem, int *bps, bool incr = false) {
         case 1: return prepare_form<1, real>(smem, bps, incr);
         case 2: return prepare_form<2, real>(smem, bps, incr);
         case 4: return prepare_form<4, real>(smem, bps, incr);
-        default: return prepare_form<8, real>(smem, bps, incr);
+        case 8: return prepare_form<8, real>(smem, bps, incr);
+        default:
+            if constexpr (Has16<real>::value) return prepare_form<16, real>(smem, bps, incr);
+            else { *bps = 2; return cudaSuccess; }  // global-memory kernel: nothing to prepare
     }
 }
 
 // tensor-memory persistent variant: one CTA per SM (the dynamic shared-memory request is padded
 // so that a second CTA cannot be resident and spin on tcgen05.alloc)
-template <int C> struct TmemCfg { static constexpr int WT = (C == 4) ? 8 : 4; };
-constexpr size_t kTmemSmem = 120 * 1024;
+// Warps (= QPs) per CTA: 8 at C = 4 (two warps share a sub-partition, 256 columns each), 4 at
+// C <= 8, 2 at C = 16 (n <= 511: 8 groups in the warp's 512 columns + 10 groups = 80 KB of shared
+// memory per warp; a shared-memory-only layout would hold one QP per SM).
+template <int C> struct TmemCfg {
+    static constexpr int WT = (C == 4) ? 8 : (C == 16 ? 2 : 4);
+    typedef TmemStore<C, (WT > 4 ? 512 / (WT / 4) : 512)> Store;
+    static constexpr size_t kSpillBytes = (size_t)WT * Store::kSpill * C * 32 * 4 * sizeof(float);
+    // at least 120 KB so that a second CTA cannot become resident
+    static constexpr size_t kSmem = kSpillBytes > 120 * 1024 ? kSpillBytes : 120 * 1024;
+};
 template <int C, bool Incr>
 cudaError_t launch_tmem(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
     constexpr int W = TmemCfg<C>::WT;
     int ctas = (ka.batch + W - 1) / W;
     if (ctas > sm_count) ctas = sm_count;
-    pqp_admm_kernel_tmem<C, W, Incr><<<ctas, 32 * W, kTmemSmem, s>>>(ka);
+    pqp_admm_kernel_tmem<C, W, Incr><<<ctas, 32 * W, TmemCfg<C>::kSmem, s>>>(ka);
     return cudaGetLastError();
 }
 template <int C>
@@ -445,33 +502,36 @@ cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t
     switch (chunk) {
         case 1: return launch_tmem_form<1>(ka, s, sm_count, incr);
         case 2: return launch_tmem_form<2>(ka, s, sm_count, incr);
-        case 4:
-            if (getenv("PQP_TMEM_WT4")) {  // experiment: 4 instead of 8 warps per SM (textbook form)
-                int ctas = (ka.batch + 3) / 4;
-                if (ctas > sm_count) ctas = sm_count;
-                cudaFuncSetAttribute(pqp_admm_kernel_tmem<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
-                pqp_admm_kernel_tmem<4, 4, false><<<ctas, 128, kTmemSmem, s>>>(ka);
-                return cudaGetLastError();
-            }
-            return launch_tmem_form<4>(ka, s, sm_count, incr);
-        default: return launch_tmem_form<8>(ka, s, sm_count, incr);
+        case 4: return launch_tmem_form<4>(ka, s, sm_count, incr);
+        case 8: return launch_tmem_form<8>(ka, s, sm_count, incr);
+        default: return launch_tmem_form<16>(ka, s, sm_count, incr);
     }
 }
 template <int C>
 cudaError_t prepare_tmem() {
-    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+    cudaError_t e = cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmemCfg<C>::kSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmemSmem);
+    return cudaFuncSetAttribute(pqp_admm_kernel_tmem<C, TmemCfg<C>::WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmemCfg<C>::kSmem);
 }
 cudaError_t prepare_tmem_chunk(int chunk) {
     switch (chunk) {
         case 1: return prepare_tmem<1>();
         case 2: return prepare_tmem<2>();
         case 4: return prepare_tmem<4>();
-        default: return prepare_tmem<8>();
+        case 8: return prepare_tmem<8>();
+        default: return prepare_tmem<16>();
     }
 }
-int tmem_warps(int chunk) { return chunk == 4 ? 8 : 4; }
+int tmem_warps(int chunk) { return chunk == 4 ? 8 : (chunk == 16 ? 2 : 4); }
+size_t tmem_spill_bytes(int chunk) {  // per warp
+    switch (chunk) {
+        case 1: return TmemCfg<1>::kSpillBytes / TmemCfg<1>::WT;
+        case 2: return TmemCfg<2>::kSpillBytes / TmemCfg<2>::WT;
+        case 4: return TmemCfg<4>::kSpillBytes / TmemCfg<4>::WT;
+        case 8: return TmemCfg<8>::kSpillBytes / TmemCfg<8>::WT;
+        default: return TmemCfg<16>::kSpillBytes / TmemCfg<16>::WT;
+    }
+}
 
 int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out) {
     if (!h) return PQP_E_INVALID;
@@ -480,6 +540,11 @@ int validate_batch(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *o
     if (in->batch < 1 || in->batch > h->batch_max) return fail(h, PQP_E_INVALID, "batch out of range");
     if (in->n_max != h->n_max) return fail(h, PQP_E_INVALID, "n_max differs from the handle's");
     return PQP_OK;
+}
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
 }
 
 // device pointers in `in`/`out`; asynchronous
@@ -496,7 +561,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     ka.prm = pqp::make_dev_params(h->prm);
     ka.batch = in->batch;
     ka.n_max = in->n_max;
-    ka.mode = mode;
+    ka.mode = mode | ((h->cold_only && !esc) ? 2 : 0);
     ka.qp0 = qp0;
     const size_t block_bytes = (size_t)PQP_NFIELDS * in->n_max * sizeof(double);
     ka.use_tma = ((block_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in->knots) % 16) == 0) ? 1 : 0;
@@ -529,7 +594,14 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
             PQP_CUDA(h, prepare_chunk<double>(h->chunk, h->smem_bytes64, &bps));
             h->prepared64 = true;
         }
-        PQP_CUDA(h, launch_chunk<double>(h->chunk, ka, h->smem_bytes64, s));
+        if (h->chunk == 16) {
+            const int ctas = std::min(ka.batch, 2 * h->sm_count);
+            if (!h->d_state64) PQP_CUDA(h, dmalloc(&h->d_state64, (size_t)2 * h->sm_count * pqp::smem_floats(16)));
+            pqp_admm_kernel_gmem<16, double, false><<<ctas, 32, 0, s>>>(ka, h->d_state64);
+            PQP_CUDA(h, cudaGetLastError());
+        } else {
+            PQP_CUDA(h, launch_chunk<double>(h->chunk, ka, h->smem_bytes64, s));
+        }
     } else if (h->use_tmem) {
         // one work counter per concurrently running launch (pipeline chunk); counters rotate
         int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
@@ -546,11 +618,6 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         if (qp0 == 0) h->last_batch = in->batch;
     }
     return PQP_OK;
-}
-
-template <typename T>
-cudaError_t dmalloc(T **p, size_t count) {
-    return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
 }
 
 // Instances the FP32 kernel could neither solve nor certify (iteration cap reached while the
@@ -622,6 +689,13 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
             // keep the device-resident results coherent too (resolve(NULL) linearises about d_sol)
             PQP_CUDA(h, cudaMemcpyAsync(h->d_sol + (size_t)b * 4 * nmax, h->e_sol + (size_t)j * 4 * nmax, 4 * (size_t)nmax * sizeof(double), cudaMemcpyDeviceToDevice, s));
             PQP_CUDA(h, cudaMemcpyAsync(h->d_status + b, h->e_status + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
+            // the FP32 warm state of this slot belongs to the failed run: make the slot cold again (zero
+            // iterates, rho0) so that a later pqp_resolve does not warm-start from it
+            if (!h->cold_only) {
+                const size_t wf = pqp::warm_floats(c);
+                PQP_CUDA(h, cudaMemsetAsync(static_cast<float *>(h->d_warm) + (size_t)b * wf, 0, wf * sizeof(float), s));
+                PQP_CUDA(h, cudaMemcpyAsync(static_cast<float *>(h->d_rho) + b, &h->rho0_f, sizeof(float), cudaMemcpyHostToDevice, s));
+            }
         }
         PQP_CUDA(h, cudaStreamSynchronize(s));
         h->escalated += E;
@@ -641,11 +715,7 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     const size_t nvm = 6 * (size_t)nmax - 1, mm = 6 * (size_t)nmax + 2;
     // up to kStreams chunks of >= 256 instances: small batches (configs[1]: 1024) still overlap
     // their copies with the solve, large ones (8192) move 1024 instances per chunk
-    static const int min_chunk = [] {
-        const char *e = getenv("PQP_STREAM_MIN_CHUNK");  // tuning knob, not part of the ABI
-        const int v = e ? atoi(e) : 0;
-        return v > 0 ? v : 256;
-    }();
+    const int min_chunk = 256;  // profiles/chunk_sweep.sh
     int nchunks = (B + min_chunk - 1) / min_chunk;
     if (nchunks > pqp_handle::kStreams) nchunks = pqp_handle::kStreams;
     const int per = (B + nchunks - 1) / nchunks;
@@ -710,6 +780,8 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     PQP_CUDA(h, cudaEventRecord(h->ev1, sd));
     PQP_CUDA(h, cudaStreamSynchronize(sd));
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    for (int i = 0; i < PQP_NSTAGES; ++i) h->stage_ms[i] = -1.0f;  // copies and kernel overlap: only the total is defined
+    h->stage_ms[PQP_STAGE_TOTAL] = h->last_ms;
     if (!h->fp64 && h->escalate) return escalate_fp64(h, in, out, B);
     return PQP_OK;
 }
@@ -718,7 +790,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     int rc;
     const int nmax = h->n_max;
     cudaStream_t s = h->stream;
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     int B;
     if (in) {
         rc = validate_batch(h, in, out);
@@ -728,6 +800,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
             if (in->n[b] < 2 || in->n[b] > nmax) return fail(h, PQP_E_INVALID, "n[b] must be in [2, n_max]");
             if (in->p && (in->p[b] < 0 || in->p[b] > in->n[b])) return fail(h, PQP_E_INVALID, "p[b] must be in [0, n[b]]");
         }
+        if (mode == 1 && h->cold_only) return fail(h, PQP_E_STATE, "cold-only handle (option bit 128) keeps no warm state");
         if (mode == 1 && (!h->solved || B != h->last_batch)) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
         h->host_inputs_resident = true;
         h->d_p_valid = in->p != nullptr;
@@ -740,6 +813,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         }
     } else {
         if (mode != 1) return fail(h, PQP_E_INVALID, "null batch");
+        if (h->cold_only) return fail(h, PQP_E_STATE, "cold-only handle (option bit 128) keeps no warm state");
         if (!out || !out->sol) return fail(h, PQP_E_INVALID, "null output");
         if (!h->solved || !h->host_inputs_resident) return fail(h, PQP_E_STATE, "resolve(NULL) needs a previous host-API solve");
         B = h->last_batch;
@@ -784,6 +858,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         if (out->x_full) PQP_CUDA(h, cudaMemsetAsync(h->d_xf + lo * nvm, 0, nb * nvm * sizeof(double), s));
         if (out->y_full) PQP_CUDA(h, cudaMemsetAsync(h->d_yf + lo * mm, 0, nb * mm * sizeof(double), s));
         if (out->z_full) PQP_CUDA(h, cudaMemsetAsync(h->d_zf + lo * mm, 0, nb * mm * sizeof(double), s));
+        if (nchunks == 1) PQP_CUDA(h, cudaEventRecord(h->ev_st[0], s));
         pqp_batch_in din;
         din.batch = (int32_t)nb;
         din.n_max = nmax;
@@ -802,6 +877,7 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
         dout.info = h->d_info + (size_t)lo * PQP_NINFO;
         rc = run_device(h, &din, &dout, mode, s, false, lo, false, h->d_flags + lo);
         if (rc) return rc;
+        if (nchunks == 1) PQP_CUDA(h, cudaEventRecord(h->ev_st[1], s));
         PQP_CUDA(h, cudaMemcpyAsync(h->h_status + lo, dout.status, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         PQP_CUDA(h, cudaMemcpyAsync(h->h_flags + lo, h->d_flags + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, s));
         PQP_CUDA(h, cudaMemcpyAsync(out->sol + (size_t)lo * 4 * nmax, dout.sol, nb * 4 * nmax * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -822,7 +898,24 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     PQP_CUDA(h, cudaEventRecord(h->ev1, streams[0]));
     PQP_CUDA(h, cudaStreamSynchronize(streams[0]));
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    if (!h->fp64 && h->escalate) return escalate_fp64(h, in, out, B);
+    // per-stage device times of a single-stream call (the reference's TimeRecorder stages of
+    // BaseSolver::solve, base_solver.cpp:57-93; here cost / constraints / solver set-up / ADMM are one kernel)
+    for (int i = 0; i < PQP_NSTAGES; ++i) h->stage_ms[i] = -1.0f;
+    if (nchunks == 1) {
+        PQP_CUDA(h, cudaEventElapsedTime(&h->stage_ms[PQP_STAGE_H2D], h->ev0, h->ev_st[0]));
+        PQP_CUDA(h, cudaEventElapsedTime(&h->stage_ms[PQP_STAGE_KERNEL], h->ev_st[0], h->ev_st[1]));
+        PQP_CUDA(h, cudaEventElapsedTime(&h->stage_ms[PQP_STAGE_D2H], h->ev_st[1], h->ev1));
+    }
+    h->stage_ms[PQP_STAGE_TOTAL] = h->last_ms;
+    h->stage_ms[PQP_STAGE_ESCALATION] = 0.0f;
+    if (!h->fp64 && h->escalate) {
+        PQP_CUDA(h, cudaEventRecord(h->ev_st[2], streams[0]));
+        rc = escalate_fp64(h, in, out, B);
+        if (rc) return rc;
+        PQP_CUDA(h, cudaEventRecord(h->ev_st[3], streams[0]));
+        PQP_CUDA(h, cudaEventSynchronize(h->ev_st[3]));
+        PQP_CUDA(h, cudaEventElapsedTime(&h->stage_ms[PQP_STAGE_ESCALATION], h->ev_st[2], h->ev_st[3]));
+    }
     return PQP_OK;
 }
 
@@ -846,7 +939,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     if (!out) return fail(nullptr, PQP_E_INVALID, "out is null");
     *out = nullptr;
     if (!params || !pqp::params_valid(*params)) return fail(nullptr, PQP_E_INVALID, "invalid params");
-    if (n_max < 2 || n_max > 32 * pqp::kMaxChunk - 1) return fail(nullptr, PQP_E_INVALID, "n_max must be in [2, 255]");
+    if (n_max < 2 || n_max > 32 * pqp::kMaxChunk - 1) return fail(nullptr, PQP_E_INVALID, "n_max must be in [2, 511]");
     if (batch_max < 1) return fail(nullptr, PQP_E_INVALID, "batch_max must be >= 1");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -867,7 +960,6 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->chunk = pqp::chunk_for(n_max);
     h->sm_count = prop.multiProcessorCount;
     h->smem_bytes = pqp::smem_floats(h->chunk) * sizeof(float) + 16;
-    if (const char *e = getenv("PQP_SMEM_PAD")) h->smem_bytes += (size_t)atoi(e);  // occupancy experiments only
 #define PQP_CREATE_CUDA(call)                                                     \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \
@@ -877,16 +969,17 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
             return PQP_E_CUDA;                                                    \
         }                                                                         \
     } while (0)
-    PQP_CREATE_CUDA(cudaSetDevice(device));
+    DeviceGuard guard_(device);
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
+    h->cold_only = (params->reserved & 128) != 0;
     // storage policy of the FP32 kernel: tensor memory where shared memory limits residency to
     // 3 QPs per SM (n_max >= 128: 819 k vs 628 k solves/s at n = 240), shared memory otherwise
     // (1.5x better at n = 60). At 64 <= n_max <= 127 tensor memory holds 8 QPs per SM against 6:
     // one wave instead of two for batches around 1024 (1.09 M vs 0.91 M solves/s at B = 1024,
     // 1.37 vs 1.29 at 2048, 1.48 vs 1.52 at 8192), so it is chosen for handles of <= 4096
     // instances. Bits 8 / 16 force one or the other.
-    const bool auto_tmem = h->chunk == 8 || (h->chunk == 4 && batch_max <= 4096);
+    const bool auto_tmem = h->chunk >= 8 || (h->chunk == 4 && batch_max <= 4096);
     h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (auto_tmem && (params->reserved & 16) == 0));
     // form of the ADMM step (FP32 kernels): the increment form (dx solve, row values A x carried and
     // advanced by alpha A dx) follows the FP64 oracle's rho schedule - same iteration count in ~99-100 %
@@ -923,11 +1016,20 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     PQP_CREATE_CUDA(dmalloc(&h->d_iters, B));
     PQP_CREATE_CUDA(dmalloc(&h->d_info, B * PQP_NINFO));
     const size_t esz = h->fp64 ? sizeof(double) : sizeof(float);
-    PQP_CREATE_CUDA(cudaMalloc(&h->d_warm, B * pqp::warm_floats(c) * esz));
-    PQP_CREATE_CUDA(cudaMalloc(&h->d_scal, B * pqp::scal_floats(c) * esz));
-    PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, B * pqp::dy_floats(c) * esz));
-    PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
-    PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
+    // Warm state (scaled x, z, y and rho: the OSQP workspace that persists between solve and
+    // updateProblemFormulationAndSolve) is per instance; a cold-only handle keeps none. The Ruiz
+    // factors and delta_y are scratch of one solve: per instance under the one-CTA-per-instance
+    // launch, per resident warp under the persistent launch (592 blocks that live in L2).
+    if (!h->cold_only) {
+        PQP_CREATE_CUDA(cudaMalloc(&h->d_warm, B * pqp::warm_floats(c) * esz));
+        PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
+        PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
+    }
+    const size_t slots = h->use_tmem ? (size_t)h->sm_count * tmem_warps(h->chunk) : B;
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_scal, slots * pqp::scal_floats(c) * esz));
+    PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, slots * pqp::dy_floats(c) * esz));
+    h->rho0_f = (float)params->rho;
+    for (int i = 0; i < 4; ++i) PQP_CREATE_CUDA(cudaEventCreate(&h->ev_st[i]));
     PQP_CREATE_CUDA(dmalloc(&h->d_counters, (size_t)pqp_handle::kCounters));
     PQP_CREATE_CUDA(dmalloc(&h->d_ready, (size_t)pqp_handle::kStreams));
     PQP_CREATE_CUDA(dmalloc(&h->d_done, (size_t)pqp_handle::kStreams));
@@ -945,7 +1047,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
 
 int pqp_destroy(pqp_handle *h) {
     if (!h) return PQP_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     for (int i = 0; i < pqp_handle::kStreams; ++i) if (h->streams[i]) cudaStreamSynchronize(h->streams[i]);
     cudaFree(h->d_knots); cudaFree(h->d_inst); cudaFree(h->d_n); cudaFree(h->d_p);
     cudaFree(h->d_sol); cudaFree(h->d_cost); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -953,6 +1055,7 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->d_ref); cudaFree(h->d_xy); cudaFree(h->d_sol2); cudaFree(h->d_n2);
     cudaFree(h->d_warm); cudaFree(h->d_scal); cudaFree(h->d_dy); cudaFree(h->d_rho);
     cudaFree(h->d_flags);
+    cudaFree(h->d_state64);
     cudaFree(h->d_counters);
     cudaFree(h->d_ready);
     cudaFree(h->d_done);
@@ -964,6 +1067,7 @@ int pqp_destroy(pqp_handle *h) {
     cudaFree(h->e_status); cudaFree(h->e_iters); cudaFree(h->e_warm); cudaFree(h->e_scal); cudaFree(h->e_dy); cudaFree(h->e_rho);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 4; ++i) if (h->ev_st[i]) cudaEventDestroy(h->ev_st[i]);
     for (int i = 0; i < pqp_handle::kStreams; ++i) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->evs[i]) cudaEventDestroy(h->evs[i]);
@@ -986,7 +1090,7 @@ int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out)
 int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, void *stream) {
     int rc = validate_batch(h, in, out);
     if (rc) return rc;
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     h->host_inputs_resident = false;
     return run_device(h, in, out, 0, static_cast<cudaStream_t>(stream), false);
 }
@@ -994,8 +1098,9 @@ int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out 
 int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, void *stream) {
     int rc = validate_batch(h, in, out);
     if (rc) return rc;
+    if (h->cold_only) return fail(h, PQP_E_STATE, "cold-only handle (option bit 128) keeps no warm state");
     if (!h->solved || in->batch != h->last_batch) return fail(h, PQP_E_STATE, "resolve needs a previous solve of the same batch");
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     return run_device(h, in, out, 1, static_cast<cudaStream_t>(stream), false);
 }
 
@@ -1003,7 +1108,7 @@ int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *
                                    const double *sol, double *out_xyh, void *stream) {
     if (!h) return PQP_E_INVALID;
     if (!n || !ref_xyh || !sol || !out_xyh || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
     frenet_to_cartesian_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, n, ref_xyh, sol, out_xyh);
     PQP_CUDA(h, cudaGetLastError());
@@ -1014,7 +1119,7 @@ int pqp_frenet_to_cartesian_device(pqp_handle *h, int32_t batch, const int32_t *
 int pqp_relinearise_device(pqp_handle *h, int32_t batch, const double *sol, double *knots, void *stream) {
     if (!h) return PQP_E_INVALID;
     if (!sol || !knots || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
     relinearise_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, sol, knots);
     PQP_CUDA(h, cudaGetLastError());
@@ -1027,7 +1132,7 @@ int pqp_advance_window_device(pqp_handle *h, int32_t batch, int32_t ext_len, int
     if (!h) return PQP_E_INVALID;
     if (!ext_knots || !sol || !knots || !inst || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
     if (tick < 0 || tick + h->n_max > ext_len) return fail(h, PQP_E_INVALID, "window [tick, tick + n_max) leaves the extended reference");
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     const int threads = 256, blocks = (batch * h->n_max + threads - 1) / threads;
     advance_window_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(batch, h->n_max, ext_len, tick, ext_knots, sol,
                                                                                    knots, inst);
@@ -1040,7 +1145,7 @@ int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n, cons
                             const double *sol, double *out_xyh) {
     if (!h) return PQP_E_INVALID;
     if (!n || !ref_xyh || !sol || !out_xyh || batch < 1 || batch > h->batch_max) return fail(h, PQP_E_INVALID, "bad arguments");
-    PQP_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     const size_t B = batch, nm = h->n_max;
     if (!h->d_ref) PQP_CUDA(h, dmalloc(&h->d_ref, (size_t)h->batch_max * 3 * nm));
     if (!h->d_xy) PQP_CUDA(h, dmalloc(&h->d_xy, (size_t)h->batch_max * 3 * nm));
@@ -1064,6 +1169,12 @@ int pqp_last_kernel_ms(pqp_handle *h, float *ms) {
     return PQP_OK;
 }
 
+int pqp_last_stage_ms(pqp_handle *h, float *ms) {
+    if (!h || !ms) return PQP_E_INVALID;
+    for (int i = 0; i < PQP_NSTAGES; ++i) ms[i] = h->stage_ms[i];
+    return PQP_OK;
+}
+
 int pqp_launch_count(pqp_handle *h, int64_t *count) {
     if (!h || !count) return PQP_E_INVALID;
     *count = h->launches;
@@ -1074,9 +1185,9 @@ int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm, int
     if (!h) return PQP_E_INVALID;
     if (sm_count) *sm_count = h->sm_count;
     if (warps_per_sm) *warps_per_sm = h->warps_per_sm;
-    // tensor-memory policy: only the two spilled groups (C = 8) live in shared memory
+    // tensor-memory policy: only the groups that do not fit the warp's columns live in shared memory
     if (smem_per_warp)
-        *smem_per_warp = h->use_tmem ? (int32_t)(h->chunk == 8 ? 2 * 8 * 32 * 4 * sizeof(float) : 0) : (int32_t)h->smem_bytes;
+        *smem_per_warp = h->use_tmem ? (int32_t)tmem_spill_bytes(h->chunk) : (int32_t)h->smem_bytes;
     return PQP_OK;
 }
 

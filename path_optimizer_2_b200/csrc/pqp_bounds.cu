@@ -14,6 +14,7 @@
 
 #include "../../include/pqp_bounds.h"
 #include "pqp_bounds_core.cuh"
+#include "pqp_device_guard.h"
 
 namespace {
 
@@ -236,7 +237,8 @@ int pqp_bounds_create(const pqp_bounds_map *map, const pqp_bounds_params *params
     h->prm.safety_margin = p.safety_margin;
     h->prm.epsilon = p.epsilon;
     const size_t cells = (size_t)map->rows * map->cols;
-    cudaError_t e = cudaSetDevice(device);
+    pqp::DeviceGuard guard_(device);
+    cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_dist), cells * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_dist, map->distance, cells * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -262,7 +264,7 @@ int pqp_bounds_create(const pqp_bounds_map *map, const pqp_bounds_params *params
 
 void pqp_bounds_destroy(pqp_bounds_handle *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    pqp::DeviceGuard guard_(h->device);
     cudaFree(h->d_dist);
     cudaFree(h->d_states);
     cudaFree(h->d_spline);
@@ -283,14 +285,14 @@ void pqp_bounds_destroy(pqp_bounds_handle *h) {
 int pqp_bounds_compute_device(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_bounds_out *out, void *stream) {
     int rc = validate(h, in, out);
     if (rc != PQP_OK) return rc;
-    PQB_CUDA(h, cudaSetDevice(h->device));
+    pqp::DeviceGuard guard_(h->device);
     return launch(h, in, out, static_cast<cudaStream_t>(stream));
 }
 
 int pqp_bounds_compute(pqp_bounds_handle *h, const pqp_bounds_in *in, const pqp_bounds_out *out) {
     int rc = validate(h, in, out);
     if (rc != PQP_OK) return rc;
-    PQB_CUDA(h, cudaSetDevice(h->device));
+    pqp::DeviceGuard guard_(h->device);
     const size_t B = in->batch, ns = B * PQP_STATE_ROWS * in->n_max, nsp = B * PQP_SPLINE_ROWS * in->k_max;
     const size_t nb = B * PQP_BOUND_ROWS * in->n_max, nk = out->knots ? B * PQP_NFIELDS * in->n_max : 0;
     PQB_CUDA(h, grow(&h->d_states, &h->cap_states, ns));
@@ -362,14 +364,14 @@ static int launch_states(pqp_bounds_handle *h, const pqp_states_in *in, const pq
 int pqp_bounds_build_states_device(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out, void *stream) {
     int rc = validate_states(h, in, out);
     if (rc != PQP_OK) return rc;
-    PQB_CUDA(h, cudaSetDevice(h->device));
+    pqp::DeviceGuard guard_(h->device);
     return launch_states(h, in, out, static_cast<cudaStream_t>(stream));
 }
 
 int pqp_bounds_build_states(pqp_bounds_handle *h, const pqp_states_in *in, const pqp_states_out *out) {
     int rc = validate_states(h, in, out);
     if (rc != PQP_OK) return rc;
-    PQB_CUDA(h, cudaSetDevice(h->device));
+    pqp::DeviceGuard guard_(h->device);
     const size_t B = in->batch, ns = B * PQP_STATE_ROWS * in->n_max, nsp = B * PQP_SPLINE_ROWS * in->k_max;
     const size_t nc = B * in->n_max, nk = out->knots ? B * PQP_NFIELDS * in->n_max : 0;
     PQB_CUDA(h, grow(&h->d_states, &h->cap_states, ns));

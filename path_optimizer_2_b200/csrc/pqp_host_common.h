@@ -73,7 +73,7 @@ inline int chunk_for(int n_max) {
     while (32 * c < n_max + 1) c *= 2;
     return c;
 }
-constexpr int kMaxChunk = 8;            // n_max <= 255
+constexpr int kMaxChunk = 16;           // n_max <= 511
 inline size_t smem_floats(int c) { return (size_t)NFIELD * c * 32; }
 inline size_t warm_floats(int c) { return (size_t)NWARM * c * 32; }
 inline size_t scal_floats(int c) { return (size_t)NSCAL * c * 32; }

@@ -109,7 +109,7 @@ struct DevParams {
 
 struct KernelArgs {
     DevParams prm;
-    int batch, n_max, mode, use_tma;  // mode 0 cold, 1 warm
+    int batch, n_max, mode, use_tma;  // mode bit 0: warm start; bit 1: cold-only handle (no warm state is written back)
     int qp0;                          // index of this launch's first instance in the handle's scratch
     const double *knots, *inst;
     const int *n, *p;
@@ -1686,9 +1686,23 @@ struct QpWarp {
     }
 
     // -------------------------------------------------------------- whole solve
-    PQP_DEV void run(const double *src, int stride) {
+    // `scratch`: index of the intra-solve scratch block (Ruiz D/E, delta_y): the instance's slot in the
+    // handle for one-CTA-per-instance launches, the resident warp's slot for persistent launches
+    // (592 blocks that stay in L2 instead of one per instance streaming out to HBM)
+    PQP_DEV void run(const double *src, int stride, size_t scratch) {
         const DevParams &P = ka.prm;
         n = ka.n[qp];
+        // the device-pointer entry points cannot inspect n[] on the host: an out-of-range size must not
+        // read past the knot block or write past sol[] (the host-pointer calls reject it up front)
+        if (n < 2 || n > ka.n_max || n > 32 * C - 1) {
+            if (lane == 0) {
+                if (ka.status) ka.status[qp] = kNumerical;
+                if (ka.iters) ka.iters[qp] = 0;
+                if (ka.cost) ka.cost[qp] = 0.0;
+                if (ka.flags) ka.flags[qp] = 0;
+            }
+            return;
+        }
         p = ka.p ? ka.p[qp] : n;
         p = p < 0 ? 0 : (p > n ? n : p);
         lf = (real)P.front_length;
@@ -1697,8 +1711,8 @@ struct QpWarp {
         const size_t plane = (size_t)C * 32;
         const size_t slot = (size_t)(qp + ka.qp0);  // per-instance scratch slot in the handle
         gwarm = static_cast<real *>(ka.warm) + slot * NWARM * plane;
-        gscal = static_cast<real *>(ka.scal) + slot * NSCAL * plane;
-        gdy = static_cast<real *>(ka.dy) + slot * NDY * plane;
+        gscal = static_cast<real *>(ka.scal) + scratch * NSCAL * plane;
+        gdy = static_cast<real *>(ka.dy) + scratch * NDY * plane;
         w_l = (real)P.w_l; w_kappa = (real)P.w_kappa; w_dkappa = (real)P.w_dkappa; w_slack = (real)P.w_slack;
         sigma = (real)P.sigma; alpha = (real)P.alpha; eps_abs = (real)P.eps_abs; eps_rel = (real)P.eps_rel;
         eps_pinf = (real)P.eps_pinf; rho_tol = (real)P.rho_tol;
@@ -1838,7 +1852,8 @@ struct QpWarp {
                     }
                 }
             }
-            // warm state: scaled iterates (x/d, e z, c y / e)
+            // warm state: scaled iterates (x/d, e z, c y / e); a cold-only handle keeps none
+            if (ka.mode & 2) continue;
             const real x6[6] = {l, ps, kp, u, s0, s1};
 #pragma unroll
             for (int j = 0; j < 6; ++j) G(gwarm, WX + j, k) = x6[j] / G(gscal, GD + j, k);
@@ -1871,7 +1886,7 @@ struct QpWarp {
                 double *inf = ka.info + (size_t)qp * 4;
                 inf[0] = nr.pri; inf[1] = nr.dua; inf[2] = rho; inf[3] = rho_updates;
             }
-            static_cast<real *>(ka.rho_state)[qp + ka.qp0] = rho;
+            if (!(ka.mode & 2)) static_cast<real *>(ka.rho_state)[qp + ka.qp0] = rho;
         }
     }
 };

@@ -35,7 +35,7 @@ def build_library(force=False, verbose=False):
     """nvcc-compile the CUDA library in-tree for sm_100a (no GPU needed to compile)."""
     root = os.path.dirname(_PKG)
     cu = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_bounds.cu")]
-    deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh")]
+    deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh", "pqp_device_guard.h")]
     deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h")]
     stale = not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in deps)
@@ -71,6 +71,7 @@ def load_library():
     L.pqp_frenet_to_cartesian.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.pqp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.pqp_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.pqp_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.pqp_kernel_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.pqp_last_error.argtypes = [vp]
     L.pqp_last_error.restype = C.c_char_p
@@ -82,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "pqp_version", "pqp_default_params", "pqp_create", "pqp_destroy", "pqp_solve", "pqp_resolve",
     "pqp_solve_device", "pqp_resolve_device", "pqp_relinearise_device", "pqp_advance_window_device",
     "pqp_frenet_to_cartesian_device",
-    "pqp_frenet_to_cartesian", "pqp_last_kernel_ms", "pqp_launch_count", "pqp_kernel_info",
+    "pqp_frenet_to_cartesian", "pqp_last_kernel_ms", "pqp_last_stage_ms", "pqp_launch_count", "pqp_kernel_info",
     "pqp_last_error",
 ]
 
@@ -164,6 +165,16 @@ class PathQpSolver:
         ms = C.c_float(0)
         self._check(self.L.pqp_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    STAGES = ("h2d", "kernel", "d2h", "escalation", "total")
+
+    @property
+    def last_stage_ms(self):
+        """Per-stage device times of the last host-pointer call (pqp_last_stage_ms): the counterpart of
+        the TimeRecorder stages of BaseSolver::solve (base_solver.cpp:57-93)."""
+        ms = (C.c_float * len(self.STAGES))()
+        self._check(self.L.pqp_last_stage_ms(self.h, ms))
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
 
     @property
     def launch_count(self):

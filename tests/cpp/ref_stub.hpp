@@ -30,6 +30,9 @@ class ReferencePath {
 };
 class VehicleState {
  public:
+    VehicleState() = default;
+    VehicleState(const State &start_state, const State &end_state, double offset = 0.0, double heading_error = 0.0)
+        : start_(start_state), target_(end_state), offset_(offset), heading_error_(heading_error) {}
     const State &getStartState() const { return start_; }
     const State &getTargetState() const { return target_; }
     std::vector<double> getInitError() const { return {offset_, heading_error_}; }

@@ -28,7 +28,7 @@ void run_form(const pqp::KernelArgs &ka, int qp, real *smem) {
     const int stride = ka.n_max;
     warp.run([&](int lane) {
         pqp::QpWarp<C, real, pqp::SmemStore<C, real>, Incr> w(ka, pqp::SmemStore<C, real>(smem, lane), lane, qp);
-        w.run(src, stride);
+        w.run(src, stride, (size_t)(qp + ka.qp0));
     });
     warp_emu::current() = nullptr;
 }
@@ -83,7 +83,8 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
                 case 1: run_one<1, double>(ka, b, sm, h->incr); break;
                 case 2: run_one<2, double>(ka, b, sm, h->incr); break;
                 case 4: run_one<4, double>(ka, b, sm, h->incr); break;
-                default: run_one<8, double>(ka, b, sm, h->incr); break;
+                case 8: run_one<8, double>(ka, b, sm, h->incr); break;
+                default: run_one<16, double>(ka, b, sm, h->incr); break;
             }
         } else {
             float *sm = reinterpret_cast<float *>(h->smem.data());
@@ -91,7 +92,8 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
                 case 1: run_one<1, float>(ka, b, sm, h->incr); break;
                 case 2: run_one<2, float>(ka, b, sm, h->incr); break;
                 case 4: run_one<4, float>(ka, b, sm, h->incr); break;
-                default: run_one<8, float>(ka, b, sm, h->incr); break;
+                case 8: run_one<8, float>(ka, b, sm, h->incr); break;
+                default: run_one<16, float>(ka, b, sm, h->incr); break;
             }
         }
     }
@@ -104,7 +106,7 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
 extern "C" {
 
 void *emu_create(const pqp_params *prm, int n_max, int batch_max) {
-    if (!prm || n_max < 2 || n_max > 255 || batch_max < 1 || !pqp::params_valid(*prm)) return nullptr;
+    if (!prm || n_max < 2 || n_max > 32 * pqp::kMaxChunk - 1 || batch_max < 1 || !pqp::params_valid(*prm)) return nullptr;
     EmuHandle *h = new EmuHandle;
     h->prm = *prm;
     h->n_max = n_max;

@@ -5,7 +5,8 @@ the converged point is): for every instance
   (1) status equals the oracle's status;
   (2) when solved, the returned (x, y, z) passes OSQP's own unscaled termination test with
       the reference's eps_abs = eps_rel = 2e-3 (base_solver.cpp:61-62), evaluated in FP64 on
-      the ORACLE-assembled (P, A, l, u), with a 1.25x allowance for the kernel's FP32 norms;
+      the ORACLE-assembled (P, A, l, u) at 1.00x: residual <= tolerance * (1 + 1e-4), the 1e-4
+      being the rounding of the FP32 norms the kernel's own check compared (measured worst: 1.000);
   (3) the objective lies within the envelope an eps=2e-3 OSQP solution itself exhibits around
       the eps=1e-9 optimum: |f - f*| <= max(1 % f* + 1e-3, 2 |f_oracle - f*|)
       + |y*|_1 r_prim + |x - x*|_1 r_dual (the duality slack the measured residuals allow);
@@ -37,6 +38,9 @@ def oracle_reference(params, hb, b, warm_from=None):
 
 
 INFEASIBLE = (abi.PQP_PRIMAL_INFEASIBLE, abi.PQP_PRIMAL_INFEASIBLE_INACCURATE)
+# OSQP's termination test re-evaluated in FP64 must hold at 1.00x; 1e-4 relative covers the rounding of
+# the FP32 norms that the kernel's own (strict) comparison used
+TERMINATION_SLACK = 1.0 + 1e-4
 
 
 def hi_params(params):
@@ -88,8 +92,8 @@ def check_instance(params, hb, res, b, *, oracle_solver, x_star=None, cost_star=
     Pd, A, l, u = s.problem()
     x, y, z = res.x_full[b, :nv], res.y_full[b, :m], res.z_full[b, :m]
     rep = oracle.osqp_termination_report(Pd, A, l, u, x, y, z, params.eps_abs, params.eps_rel)
-    assert rep["pri_res"] < 1.25 * rep["eps_pri"], "%s: primal residual %g > %g" % (tag, rep["pri_res"], rep["eps_pri"])
-    assert rep["dua_res"] < 1.25 * rep["eps_dua"], "%s: dual residual %g > %g" % (tag, rep["dua_res"], rep["eps_dua"])
+    assert rep["pri_res"] <= TERMINATION_SLACK * rep["eps_pri"], "%s: primal residual %g > %g" % (tag, rep["pri_res"], rep["eps_pri"])
+    assert rep["dua_res"] <= TERMINATION_SLACK * rep["eps_dua"], "%s: dual residual %g > %g" % (tag, rep["dua_res"], rep["eps_dua"])
     span = np.maximum(1.0, np.maximum(np.abs(l), np.abs(u)))
     finite = (np.abs(l) < 1e29) & (np.abs(u) < 1e29)
     assert np.all((z >= l - 1e-5 * span)[finite]) and np.all((z <= u + 1e-5 * span)[finite]), tag + ": z outside [l, u]"
@@ -111,10 +115,12 @@ def check_instance(params, hb, res, b, *, oracle_solver, x_star=None, cost_star=
     assert abs(cost_gpu - cost_star) <= env_f, "%s: cost %g vs f* %g (oracle %g, envelope %g)" % (
         tag, cost_gpu, cost_star, s.cost, env_f)
     dx = float(np.max(np.abs(x - s.x())))
+    widened = False
     if x_star is not None:
         env = max(1e-2, 2.0 * float(np.max(np.abs(s.x() - x_star))))
         d_star = float(np.max(np.abs(x - x_star)))
         if d_star > env:
+            widened = True
             env = max(env, 2.0 * schedule_spread(params, hb, b, x_star, getattr(s, "lin", None)))
         assert d_star <= env, "%s: |x - x*| = %g > envelope %g" % (tag, d_star, env)
     # sol block vs x_full
@@ -123,7 +129,8 @@ def check_instance(params, hb, res, b, *, oracle_solver, x_star=None, cost_star=
     assert np.allclose(sol[1, :n], x[1:3 * n:3], atol=1e-12)
     assert np.allclose(sol[2, :n], x[2:3 * n:3], atol=1e-12)
     assert np.allclose(sol[3, :n - 1], x[3 * n:4 * n - 1], atol=1e-12)
-    return dict(iters=int(res.iters[b]), oracle_iters=s.iters, dx=dx, pri=rep["pri_res"], dua=rep["dua_res"])
+    return dict(iters=int(res.iters[b]), oracle_iters=s.iters, dx=dx, pri=rep["pri_res"], dua=rep["dua_res"],
+                pri_ratio=rep["pri_res"] / rep["eps_pri"], dua_ratio=rep["dua_res"] / rep["eps_dua"], widened=widened)
 
 
 def high_accuracy_x(params_hi, hb, b):

@@ -17,14 +17,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "dropin_test")
 
 
-def _build():
+BIN_REAL = BIN + "_real"
+REF = "/root/reference"
+
+
+def _build(real=False):
+    """real=True: bind the drop-in to the reference's OWN boundary types (data_struct.hpp,
+    vehicle_state_frenet.{hpp,cpp} compile standalone). Only possible where
+    /root/reference exists (the CPU box); the binary is git-ignored but travels to the GPU box."""
     solver.build_library()
+    out = BIN_REAL if real else BIN
     src = os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp")
-    deps = [src, os.path.join(ROOT, "include", "pqp_base_solver.hpp"), solver.LIB_PATH]
-    if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
-        subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-o", BIN, src, solver.LIB_PATH,
-                               "-Wl,-rpath," + os.path.dirname(solver.LIB_PATH)])
-    return BIN
+    deps = [src, os.path.join(ROOT, "include", "pqp_base_solver.hpp"), os.path.join(ROOT, "tests", "cpp", "ref_stub.hpp"),
+            solver.LIB_PATH]
+    if real and not os.path.isdir(REF):
+        return out if os.path.exists(out) else None
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        extra = ["-DPQP_TEST_REAL_TYPES", "-I", os.path.join(REF, "include"), "-w",
+                 os.path.join(REF, "src", "data_struct", "vehicle_state_frenet.cpp")] if real else ["-Wall"]
+        subprocess.check_call(["g++", "-std=c++11", "-O1", "-o", out, src] + extra + [
+            solver.LIB_PATH, "-Wl,-rpath," + os.path.dirname(solver.LIB_PATH)])
+    return out
 
 
 def _write_instance(path, knots, inst, n, ref, target_heading, constraint_end_heading=1):
@@ -38,8 +51,11 @@ def _write_instance(path, knots, inst, n, ref, target_heading, constraint_end_he
                                                    target_heading, constraint_end_heading))
 
 
-def test_dropin_compiles_and_fails_loudly_without_gpu(tmp_path):
-    exe = _build()
+@pytest.mark.parametrize("real", [False, True])
+def test_dropin_compiles_and_fails_loudly_without_gpu(tmp_path, real):
+    exe = _build(real)
+    if exe is None:
+        pytest.skip("the reference tree is not present on this box")
     try:
         import torch
         if torch.cuda.is_available():
@@ -54,9 +70,12 @@ def test_dropin_compiles_and_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_dropin_matches_python_binding(tmp_path):
+@pytest.mark.parametrize("real", [False, True])
+def test_dropin_matches_python_binding(tmp_path, real):
     from oracle import oracle
-    exe = _build()
+    exe = _build(real)
+    if exe is None:
+        pytest.skip("dropin_test_real was not built on the CPU box")
     params = abi.default_params()
     for idx in range(3):
         knots, inst, n, ref = synthetic.make_instance(3, idx, 120)
@@ -82,3 +101,32 @@ def test_dropin_matches_python_binding(tmp_path):
         assert np.array_equal(got[:, 3], r2.sol[0, 2, :n]) and np.array_equal(got[:-1, 4], r2.sol[0, 3, :n - 1])
         xyh = oracle.frenet_to_cartesian(ref[:, :n], r2.sol[0, 0, :n], r2.sol[0, 1, :n])
         assert np.allclose(got[:, 0:3].T, xyh, atol=1e-12, rtol=0)
+
+
+@pytest.mark.gpu
+def test_dropin_long_path_and_handle_pool(tmp_path):
+    """A 100 m plan (n = 400 > 255 knots: the reference sizes everything from input_path.size(),
+    base_solver.cpp:15-39) through the drop-in, constructed per plan like the reference's caller
+    (path_optimizer.cpp:138): the handle pool creates one handle and re-uses it for every later plan."""
+    exe = _build(False)
+    params = abi.default_params()
+    knots, inst, n, ref = synthetic.make_instance(3, 1, 400)
+    assert n == 400 and knots[abi.F_S, n - 1] > 60.0
+    p = str(tmp_path / "long.txt")
+    _write_instance(p, knots, inst, n, ref, 0.0, constraint_end_heading=0)
+    lines = subprocess.run([exe, p, "20"], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert lines[0].startswith("plans 21 "), lines[0]
+    tok = lines[0].split()
+    stats = {tok[i]: float(tok[i + 1]) for i in range(0, 12, 2)}
+    assert stats["creates"] == 1 and stats["hits"] >= 20
+    assert stats["later_ms"] < stats["first_ms"]
+    assert lines[1].startswith("solve 1 status 0"), lines[1]
+    assert lines[2].startswith("resolve 1 status 0"), lines[2]
+    got = np.array([[float(v) for v in ln.split()] for ln in lines[3:]])
+    hb = abi.HostBatch(knots[None], inst[None], np.array([n], dtype=np.int32))
+    sv = solver.PathQpSolver(params, n_max=n, batch_max=1)
+    r1 = sv.solve(hb)
+    r2 = sv.resolve(hb.with_linearisation(r1.sol))
+    sv.close()
+    assert np.array_equal(got[:, 5], r2.sol[0, 0, :n]) and np.array_equal(got[:, 3], r2.sol[0, 2, :n])
+    print("drop-in plan loop:", lines[0])

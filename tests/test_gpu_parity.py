@@ -38,7 +38,7 @@ def _run_and_check(solver_mod, hb, params, label, warm=True, check_all=True, max
     return stats
 
 
-@pytest.mark.parametrize("n", [2, 3, 20, 31, 32, 63, 64, 120, 127, 128, 240, 255])
+@pytest.mark.parametrize("n", [2, 3, 20, 31, 32, 63, 64, 120, 127, 128, 240, 255, 256, 400, 511])
 def test_cold_and_warm_parity(solver_mod, n):
     hb = synthetic.make_batch(100 + n, 6, n)
     _run_and_check(solver_mod, hb, abi.default_params(), "n=%d" % n)
@@ -151,7 +151,7 @@ def test_api_errors(solver_mod):
     with pytest.raises(solver_mod.PqpError):
         solver_mod.PathQpSolver(params, n_max=1, batch_max=4)
     with pytest.raises(solver_mod.PqpError):
-        solver_mod.PathQpSolver(params, n_max=300, batch_max=4)
+        solver_mod.PathQpSolver(params, n_max=512, batch_max=4)
     sv = solver_mod.PathQpSolver(params, n_max=60, batch_max=2)
     hb = synthetic.make_batch(3, 2, 60)
     with pytest.raises(solver_mod.PqpError):  # resolve before solve
@@ -173,7 +173,7 @@ def test_fp64_mode_reproduces_oracle_iterates(solver_mod):
     from oracle import oracle
     p32 = abi.default_params()
     p64 = abi.default_params(reserved=2)
-    for n in (3, 60, 240):
+    for n in (3, 60, 240, 400):  # 400: C = 16, FP64 state in global memory
         hb = synthetic.make_batch(100 + n if n == 3 else 3, 6 if n < 100 else 4, n)
         sv = solver_mod.PathQpSolver(p64, n_max=n, batch_max=hb.batch)
         res = sv.solve(hb, full=True)
@@ -298,7 +298,7 @@ def test_increment_form_tracks_the_oracle_iteration_counts(solver_mod, n):
         parity.check_instance(abi.default_params(), hb, g, b, oracle_solver=s, label="increment form n=%d" % n)
 
 
-@pytest.mark.parametrize("n", [20, 120, 240])
+@pytest.mark.parametrize("n", [20, 120, 240, 400])
 def test_tensor_memory_policy_matches_shared_memory_policy(solver_mod, n):
     """params.reserved bit 3 / bit 4: the same solver code with its per-stage state in tensor
     memory (tcgen05.ld/st, persistent CTAs) or in shared memory. Same arithmetic -> same answers.
@@ -320,3 +320,48 @@ def test_tensor_memory_policy_matches_shared_memory_policy(solver_mod, n):
     for b in range(hb.batch):
         s = parity.oracle_reference(params, hb, b)
         parity.check_instance(params, hb, res[8][0], b, oracle_solver=s, label="tmem n=%d" % n)
+
+
+def test_cold_only_handle_and_device_side_size_check(solver_mod):
+    """Option bit 128 (no warm state kept): same answers as the default handle, resolve is refused.
+    Device-pointer calls cannot validate n[] on the host: an out-of-range n is skipped by the kernel
+    with PQP_NUMERICAL_ERROR and its neighbours are untouched."""
+    import torch
+    params = abi.default_params()
+    hb = synthetic.make_batch(3, 12, 240)
+    sv = solver_mod.PathQpSolver(params, n_max=240, batch_max=12)
+    a = sv.solve(hb)
+    sv.close()
+    sc = solver_mod.PathQpSolver(abi.default_params(reserved=128), n_max=240, batch_max=12)
+    c = sc.solve(hb)
+    assert np.array_equal(a.status, c.status) and np.array_equal(a.iters, c.iters) and np.array_equal(a.sol, c.sol)
+    with pytest.raises(solver_mod.PqpError):
+        sc.resolve(hb.with_linearisation(c.sol))
+    dev = torch.device("cuda", 0)
+    n_bad = hb.n.copy()
+    n_bad[3], n_bad[7] = 1, 241
+    d_knots, d_inst, d_n = (torch.from_numpy(v).to(dev) for v in (hb.knots, hb.inst, n_bad))
+    d_sol = torch.full((12, 4, 240), -7.0, dtype=torch.float64, device=dev)
+    d_cost = torch.zeros(12, dtype=torch.float64, device=dev)
+    d_status, d_iters = (torch.full((12,), -1, dtype=torch.int32, device=dev) for _ in range(2))
+    bi = abi.PqpBatchIn(12, 240, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+    bo = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(), None, None, None, None)
+    sc.solve_device(bi, bo, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st, sol = d_status.cpu().numpy(), d_sol.cpu().numpy()
+    assert st[3] == abi.PQP_NUMERICAL_ERROR and st[7] == abi.PQP_NUMERICAL_ERROR
+    assert np.all(sol[3] == -7.0) and np.all(sol[7] == -7.0)
+    good = [b for b in range(12) if b not in (3, 7)]
+    assert np.array_equal(st[good], a.status[good]) and np.array_equal(sol[good], a.sol[good])
+    sc.close()
+
+
+def test_stage_times_of_a_single_path_call(solver_mod):
+    """pqp_last_stage_ms: the reference's TimeRecorder stages (base_solver.cpp:57-93) for the B = 1 call."""
+    hb = synthetic.make_batch(3, 1, 120)
+    sv = solver_mod.PathQpSolver(abi.default_params(), n_max=120, batch_max=1)
+    sv.solve(hb)
+    ms = sv.last_stage_ms
+    assert ms["h2d"] >= 0 and ms["kernel"] > 0 and ms["d2h"] >= 0
+    assert abs(ms["h2d"] + ms["kernel"] + ms["d2h"] - ms["total"]) < 0.05 * ms["total"] + 1e-3
+    sv.close()

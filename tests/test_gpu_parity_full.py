@@ -1,0 +1,158 @@
+"""Full-size parity gates (`-m gpu`): every instance of BASELINE configs[2] (8192 x 240), configs[1]
+(1024 x 120 through the shared obstacle map) and a configs[4]-style receding-horizon run (512 x 240,
+20 ticks, 50-iteration cap) against the CPU oracle on the same inputs.
+
+Per batch: status agreement 100 %; OSQP's own termination test (base_solver.cpp:61-62, eps 2e-3)
+re-evaluated in FP64 on the oracle-assembled (P, A, l, u) at 1.00x for every solved instance
+(tests/parity.py::TERMINATION_SLACK); iteration count identical to the FP64 oracle's in >= 99 % of
+instances; how many instances of a sample needed the schedule-spread widening of the x* envelope
+(target and assertion: 0 with the default increment-form kernel). The numbers are printed (run with
+-s) and written to gpurun_out/parity_full.json."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from path_optimizer_2_b200 import abi, synthetic
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, rec):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "parity_full.json")
+    try:
+        with open(path) as f:
+            allrec = json.load(f)
+    except Exception:
+        allrec = {}
+    allrec[name] = rec
+    with open(path, "w") as f:
+        json.dump(allrec, f, indent=1, sort_keys=True)
+    print("parity[%s]: %s" % (name, json.dumps(rec, sort_keys=True)))
+
+
+def _gate(name, params, hb, g, o, *, min_same_iters=0.99, sample_envelope=0):
+    """g: GPU HostResult (full), o: oracle HostResult (full) of the same batch."""
+    from oracle import oracle
+    assert np.array_equal(g.status, o.status), "%s: status differs in %d instances" % (name, int(np.sum(g.status != o.status)))
+    ok = o.status == abi.PQP_SOLVED
+    rep = oracle.termination_batch(params, hb, g.x_full, g.y_full, g.z_full)
+    pr, dr = rep["pri_res"][ok] / rep["eps_pri"][ok], rep["dua_res"][ok] / rep["eps_dua"][ok]
+    assert pr.max() <= parity.TERMINATION_SLACK and dr.max() <= parity.TERMINATION_SLACK, (name, pr.max(), dr.max())
+    assert rep["z_violation"][ok].max() <= 1e-5
+    assert np.allclose(rep["cost"][ok], g.cost[ok], rtol=1e-3, atol=1e-3)
+    d = g.iters[ok].astype(np.int64) - o.iters[ok]
+    same = float((d == 0).mean())
+    assert same >= min_same_iters, "%s: iteration count identical in %.4f of instances" % (name, same)
+    nv = 6 * hb.n.astype(np.int64) - 1
+    dx = np.array([np.abs(g.x_full[b, :nv[b]] - o.x_full[b, :nv[b]]).max() for b in np.nonzero(ok)[0]])
+    rec = dict(instances=int(hb.batch), solved=int(ok.sum()), status_agreement=1.0, same_iteration_count=same,
+               max_iter_diff=int(np.abs(d).max()), mean_iters_gpu=float(g.iters[ok].mean()),
+               mean_iters_oracle=float(o.iters[ok].mean()), worst_pri_ratio=float(pr.max()), worst_dua_ratio=float(dr.max()),
+               dx_vs_oracle_p50=float(np.median(dx)), dx_vs_oracle_p99=float(np.percentile(dx, 99)), dx_vs_oracle_max=float(dx.max()))
+    if sample_envelope:
+        widened = 0
+        idx = np.nonzero(ok)[0][:: max(1, int(ok.sum()) // sample_envelope)][:sample_envelope]
+        for b in idx:
+            s = parity.oracle_reference(params, hb, int(b))
+            st = parity.check_instance(params, hb, g, int(b), oracle_solver=s, label=name)
+            widened += int(st.get("widened", False))
+        rec.update(envelope_sample=int(len(idx)), envelope_widened=int(widened))
+        assert widened == 0, "%s: %d of %d sampled instances needed the schedule-spread widening" % (name, widened, len(idx))
+    _record(name, rec)
+    return rec
+
+
+def test_config2_every_instance():
+    """BASELINE configs[2]: 8192 paths x 240 knots, per-instance clearance bounds, cold solve."""
+    from oracle import oracle
+    from path_optimizer_2_b200 import solver
+    params = abi.default_params()
+    hb = synthetic.make_batch(3, 8192, 240)
+    sv = solver.PathQpSolver(params, n_max=240, batch_max=8192)
+    g = sv.solve(hb, full=True)
+    o, secs = oracle.solve_batch(params, hb, nthreads=oracle.max_threads(), full=True)
+    rec = _gate("config2_cold_8192x240", params, hb, g, o, sample_envelope=128)
+    # the reference's second call (updateProblemFormulationAndSolve): both sides re-linearise about the
+    # GPU's first result; the oracle warm-starts from its own (FP64) iterates of the first solve
+    hb2 = hb.with_linearisation(g.sol)
+    g2 = sv.resolve(hb2, full=True)
+    sv.close()
+    ob = oracle.OracleBatch(params, hb)
+    ob.solve()
+    ob.update_full(hb2)
+    o2 = ob.solve(full=True)
+    ob.close()
+    first_ok = g.status == abi.PQP_SOLVED
+    sub = np.nonzero(first_ok)[0]
+    hs = abi.HostBatch(hb2.knots[sub], hb2.inst[sub], hb2.n[sub])
+    _gate("config2_warm_8192x240", params, hs, g2.take(sub), o2.take(sub), min_same_iters=0.95)
+    assert rec["same_iteration_count"] >= 0.99
+
+
+def test_config1_shared_map_every_instance():
+    """BASELINE configs[1]: 1024 paths x 120 knots through one shared obstacle map (clearance bounds
+    from the CUDA bounds kernel), cold solve."""
+    from oracle import oracle
+    from path_optimizer_2_b200 import bounds, sharedmap, solver
+    params = abi.default_params()
+    dmap = sharedmap.DistanceMap()
+    lines = sharedmap.make_lines(1024, 120, dmap=dmap)
+    pbn = bounds.PathBounds(dmap.dist, dmap.res, device=0)
+    bnd, nv = pbn.compute(lines.states, lines.n, lines.spline, lines.k)
+    pbn.close()
+    hb = lines.to_host_batch(bnd, nv)
+    sv = solver.PathQpSolver(params, n_max=120, batch_max=1024)
+    g = sv.solve(hb, full=True)
+    sv.close()
+    o, _ = oracle.solve_batch(params, hb, nthreads=oracle.max_threads(), full=True)
+    _gate("config1_sharedmap_1024x120", params, hb, g, o, sample_envelope=64)
+
+
+def test_config4_receding_horizon_every_instance():
+    """configs[4]-style run: 512 paths x 240 knots, cold solve, then 20 ticks that advance the window
+    by one knot, re-linearise about the previous solution and warm re-solve with max_iter = 50 (the
+    benchmark's cap; the reference keeps OSQP's 4000). Both sides are driven with the same inputs every
+    tick (the GPU's previous solution), each keeps its own warm state."""
+    from oracle import oracle
+    from path_optimizer_2_b200 import solver
+    B, n, ticks = 512, 240, 20
+    params = abi.default_params(max_iter=50)
+    ext = synthetic.make_batch(5, B, n + ticks + 1)
+    hb = abi.HostBatch(ext.knots[:, :, :n].copy(), ext.inst, np.full(B, n, dtype=np.int32))
+    sv = solver.PathQpSolver(params, n_max=n, batch_max=B)
+    g = sv.solve(hb, full=True)
+    ob = oracle.OracleBatch(params, hb)
+    o = ob.solve(full=True)
+    assert np.array_equal(g.status, o.status) and np.array_equal(g.iters, o.iters)
+    inst, sol = hb.inst, g.sol
+    same, worst_p, worst_d, status_eq, dxs = [], 0.0, 0.0, 0, []
+    for t in range(1, ticks + 1):
+        knots, inst = synthetic.shift_window(ext.knots, inst, sol, t, n)
+        hbt = abi.HostBatch(knots, inst, hb.n)
+        g = sv.resolve(hbt, full=True)
+        ob.update_full(hbt)
+        o = ob.solve(full=True)
+        sol = g.sol
+        assert np.array_equal(g.status, o.status), "tick %d: status differs in %d instances" % (t, int(np.sum(g.status != o.status)))
+        status_eq += 1
+        same.append(float(np.mean(g.iters == o.iters)))
+        ok = o.status == abi.PQP_SOLVED
+        if ok.any():
+            rep = oracle.termination_batch(params, hbt, g.x_full, g.y_full, g.z_full)
+            worst_p = max(worst_p, float((rep["pri_res"][ok] / rep["eps_pri"][ok]).max()))
+            worst_d = max(worst_d, float((rep["dua_res"][ok] / rep["eps_dua"][ok]).max()))
+        dxs.append(float(np.abs(g.sol - o.sol).max()))
+    sv.close()
+    ob.close()
+    rec = dict(instances=B, ticks=ticks, status_agreement=1.0, same_iteration_count_min=min(same),
+               same_iteration_count_mean=float(np.mean(same)), worst_pri_ratio=worst_p, worst_dua_ratio=worst_d,
+               max_abs_sol_diff=max(dxs), solved_fraction_last_tick=float(np.mean(o.status == abi.PQP_SOLVED)))
+    _record("config4_receding_512x240x20", rec)
+    assert worst_p <= parity.TERMINATION_SLACK and worst_d <= parity.TERMINATION_SLACK
+    assert rec["same_iteration_count_mean"] >= 0.99
