@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/pqp_multi.h"
 #include "pqp_device_guard.h"
 #include "pqp_host_common.h"
 
@@ -354,6 +355,18 @@ __global__ void advance_window_kernel(int batch, int n_max, int ext_len, int tic
     }
 }
 
+// {cost, status, iters} -> one 16-byte record per instance (the payload of the multi-GPU all-gather)
+__global__ void pack_results_kernel(int batch, const double *__restrict__ cost, const int *__restrict__ status,
+                                    const int *__restrict__ iters, pqp_result_rec *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    pqp_result_rec r;
+    r.cost = cost[b];
+    r.status = status[b];
+    r.iters = iters[b];
+    out[b] = r;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ handle
@@ -689,6 +702,8 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
             // keep the device-resident results coherent too (resolve(NULL) linearises about d_sol)
             PQP_CUDA(h, cudaMemcpyAsync(h->d_sol + (size_t)b * 4 * nmax, h->e_sol + (size_t)j * 4 * nmax, 4 * (size_t)nmax * sizeof(double), cudaMemcpyDeviceToDevice, s));
             PQP_CUDA(h, cudaMemcpyAsync(h->d_status + b, h->e_status + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_cost + b, h->e_cost + j, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            PQP_CUDA(h, cudaMemcpyAsync(h->d_iters + b, h->e_iters + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
             // the FP32 warm state of this slot belongs to the failed run: make the slot cold again (zero
             // iterates, rho0) so that a later pqp_resolve does not warm-start from it
             if (!h->cold_only) {
@@ -1166,6 +1181,28 @@ int pqp_frenet_to_cartesian(pqp_handle *h, int32_t batch, const int32_t *n, cons
 int pqp_last_kernel_ms(pqp_handle *h, float *ms) {
     if (!h || !ms) return PQP_E_INVALID;
     *ms = h->last_ms;
+    return PQP_OK;
+}
+
+int pqp_pack_results_device(pqp_handle *h, int32_t batch, const double *cost, const int32_t *status,
+                            const int32_t *iters, pqp_result_rec *packed, void *stream) {
+    if (!h) return PQP_E_INVALID;
+    if (!cost || !status || !iters || !packed || batch < 1) return fail(h, PQP_E_INVALID, "null buffer");
+    DeviceGuard guard_(h->device);
+    pack_results_kernel<<<(batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(batch, cost, status, iters, packed);
+    PQP_CUDA(h, cudaGetLastError());
+    h->launches++;
+    return PQP_OK;
+}
+
+int pqp_resident_results(pqp_handle *h, const double **sol, const double **cost, const int32_t **status,
+                         const int32_t **iters) {
+    if (!h) return PQP_E_INVALID;
+    if (!h->solved || !h->host_inputs_resident) return fail(h, PQP_E_STATE, "no host-pointer solve has run on this handle");
+    if (sol) *sol = h->d_sol;
+    if (cost) *cost = h->d_cost;
+    if (status) *status = h->d_status;
+    if (iters) *iters = h->d_iters;
     return PQP_OK;
 }
 

@@ -34,14 +34,14 @@ class PqpError(RuntimeError):
 def build_library(force=False, verbose=False):
     """nvcc-compile the CUDA library in-tree for sm_100a (no GPU needed to compile)."""
     root = os.path.dirname(_PKG)
-    cu = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_bounds.cu")]
+    cu = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_bounds.cu", "pqp_multi.cu")]
     deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh", "pqp_device_guard.h")]
-    deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h")]
+    deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h", "pqp_multi.h")]
     stale = not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in deps)
     if force or stale:
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-I", os.path.join(root, "include"), "-o", LIB_PATH] + cu
+            "-I", os.path.join(root, "include"), "-o", LIB_PATH] + cu + ["-ldl"]
         subprocess.check_call(cmd)
     return LIB_PATH
 

@@ -117,7 +117,7 @@ def test_dropin_long_path_and_handle_pool(tmp_path):
     lines = subprocess.run([exe, p, "20"], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     assert lines[0].startswith("plans 21 "), lines[0]
     tok = lines[0].split()
-    stats = {tok[i]: float(tok[i + 1]) for i in range(0, 12, 2)}
+    stats = {tok[i]: float(tok[i + 1]) for i in range(0, 10, 2)}
     assert stats["creates"] == 1 and stats["hits"] >= 20
     assert stats["later_ms"] < stats["first_ms"]
     assert lines[1].startswith("solve 1 status 0"), lines[1]
