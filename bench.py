@@ -13,13 +13,18 @@ of synthetic instances. Default workload: BASELINE.json configs[2] — batch 819
   roofline   : algorithmic bytes (104 n + 56 per cold solve) / kernel time vs the
                measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline: the oracle port (OSQP-algorithm restatement) on the host cores, bounded sample
+  config.fp64 / config.secondary : the same metric with the FP64 instantiation of the kernel (the
+               reference's OSQP is FP64), and the other BASELINE configs (configs[0] one path through
+               the C++ drop-in incl. handle creation, configs[1] shared map, configs[4] receding horizon)
 
 `--impl reference` times that CPU path alone (kind "port": OSQP itself is not available).
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -36,6 +41,7 @@ UNIT = "solves/s"
 CFG_ID = 3
 
 
+# --------------------------------------------------------------------------------------- workloads
 def make_workload(args, batch, first, device=None):
     """(HostBatch, description, extras) of `batch` instances starting at global index `first`.
     Shared-map workload: the clearance bounds come from the CUDA bounds kernel (pqp_bounds.h) on
@@ -141,7 +147,7 @@ def plan_pipeline(args, pbn, lines, d_spline, d_k, d_maxs, device):
     d_knots, d_bounds = torch.zeros((B, abi.NFIELDS, n), **f64), torch.zeros((B, 6, n), **f64)
     d_sol, d_cost = torch.zeros((B, 4, n), **f64), torch.zeros(B, **f64)
     d_n, d_nv, d_status, d_iters = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(4))
-    sv = solver.PathQpSolver(abi.default_params(reserved=args.option_bits), n_max=n, batch_max=B, device=device)
+    sv = solver.PathQpSolver(abi.default_params(reserved=args.option_bits & ~128), n_max=n, batch_max=B, device=device)
     si = bounds.StatesIn(B, n, lines.k_max, d_spline.data_ptr(), d_k.data_ptr(), d_maxs.data_ptr(), 0.15, 0.3, 1)
     so = bounds.StatesOut(d_states.data_ptr(), d_curv.data_ptr(), d_n.data_ptr(), None, d_knots.data_ptr())
     bi = bounds.BoundsIn(B, n, lines.k_max, d_states.data_ptr(), d_n.data_ptr(), d_spline.data_ptr(), d_k.data_ptr())
@@ -179,10 +185,12 @@ def algorithmic_bytes(n, warm=False):
     return (296 * n + 72) if warm else (104 * n + 56)
 
 
-def measured_traffic(n, instances):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+def measured_traffic(n, instances, cold_only):
+    """DRAM bytes per launch from the ncu --set full capture committed in the same round
+    (profiles/r2/traffic_*.json, written by profiles/traffic_from_ncu.py), or None."""
+    name = "traffic_cold_n%d%s.json" % (n, "_coldonly" if cold_only else "")
     try:
-        with open(os.path.join(ROOT, "profiles", "r1", "traffic_cold_n%d.json" % n)) as f:
+        with open(os.path.join(ROOT, "profiles", "r2", name)) as f:
             return float(json.load(f)["dram_bytes_per_instance"]) * instances
     except Exception:
         return None
@@ -243,44 +251,89 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def host_threads():
-    """Host cores this process may use (torchrun sets OMP_NUM_THREADS=1; ignore that)."""
+# --------------------------------------------------------------------------------------- CPU arm
+def host_cores():
+    """Cores this process can really use: the scheduler affinity mask, capped by the cgroup CPU quota
+    (a container may see 128 CPUs in its mask and be entitled to a fraction of them: round 1's CPU arm
+    differed 5.5x between two boxes that both reported 128 cores)."""
     try:
-        return len(os.sched_getaffinity(0))
+        affinity = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        affinity = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2: "<quota|max> <period>"
+            q, p = f.read().split()
+            if q != "max":
+                quota = float(q) / float(p)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                p = float(f.read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    eff = affinity if quota is None else max(1, min(affinity, int(math.ceil(quota))))
+    return {"affinity": affinity, "nproc": os.cpu_count(), "cgroup_quota": quota, "effective": eff}
 
 
-def cpu_baseline(params, hb, sample, threads):
+def pick_threads(params, hb, cores):
+    """Short sweep of OpenMP thread counts on a slice of the workload (torchrun's OMP_NUM_THREADS=1 is
+    ignored: the count is passed explicitly); returns (best thread count, {threads: solves/s})."""
+    from oracle import oracle
+    cand = sorted({t for t in (1, 8, 16, 32, 64, 96, 128, 192, 256, cores["effective"], cores["affinity"])
+                   if 1 <= t <= cores["affinity"]})
+    sub = hb.slice(0, min(hb.batch, 512))
+    oracle.solve_batch(params, sub.slice(0, min(64, sub.batch)), nthreads=cand[-1])  # warm the thread pool
+    sweep = {}
+    for t in cand:
+        s = sub.slice(0, min(sub.batch, max(32, 4 * t)))
+        _, secs = oracle.solve_batch(params, s, nthreads=t, mode=0, dense_assembly=False)
+        sweep[t] = s.batch / secs
+    multi = {t: v for t, v in sweep.items() if t > 1} or sweep
+    best = max(multi, key=multi.get)
+    return best, {str(t): round(v, 1) for t, v in sweep.items()}
+
+
+def cpu_baseline(params, hb, sample):
     """Oracle port on the host cores. `value` is the OSQP-algorithm cost alone (direct CSC
     assembly, the conservative figure); the reference's own plumbing additionally zero-fills
     and scans dense m x nv / nv x nv temporaries per solve (base_solver.cpp:122,145,159,210),
     timed separately and quoted in `sample`."""
     from oracle import oracle
+    cores = host_cores()
+    threads, sweep = pick_threads(params, hb, cores)
     sub = hb.slice(0, min(sample, hb.batch))
     res, secs = oracle.solve_batch(params, sub, nthreads=threads, mode=0, dense_assembly=False)
     dsub = sub.slice(0, min(256, sub.batch))
     _, dsecs = oracle.solve_batch(params, dsub, nthreads=threads, mode=0, dense_assembly=True)
-    _, s1 = oracle.solve_batch(params, sub.slice(0, min(64, sub.batch)), nthreads=1, mode=0)
     solved = int(np.sum(res.status == abi.PQP_SOLVED))
     return {"value": sub.batch / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "host": cores, "thread_sweep_solves_per_s": sweep,
             "sample": "%d instances of the same workload, oracle port (OSQP-algorithm restatement, FP64, "
-                      "sparse LDL'), %d OpenMP threads, %.2f s wall, %d solved; 1 thread: %.0f solves/s; with the "
-                      "reference-style dense assembly temporaries: %.0f solves/s on %d threads"
-                      % (sub.batch, threads, secs, solved, min(64, sub.batch) / s1, dsub.batch / dsecs, threads)}, secs
+                      "sparse LDL'), %d OpenMP threads (fastest of the sweep; cgroup quota %s, affinity %d), %.2f s "
+                      "wall, %d solved; 1 thread: %s solves/s; with the reference-style dense assembly temporaries: "
+                      "%.0f solves/s on %d threads"
+                      % (sub.batch, threads, cores["cgroup_quota"], cores["affinity"], secs, solved, sweep.get("1"),
+                         dsub.batch / dsecs, threads)}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU path alone (rank 0 only under torchrun)."""
+    """--impl reference: the CPU path alone (rank 0 only under torchrun), on the FULL batch of the
+    b200 arm's config every step, with the fastest OpenMP thread count of a short sweep."""
     if rank != 0:
         return
     from oracle import oracle
     params = abi.default_params()
-    threads = host_threads()
-    sample = args.cpu_sample
+    cores = host_cores()
+    sample = args.batch if args.cpu_sample is None else args.cpu_sample
     hb, workload, _ = make_workload(args, sample, 0)
-    for _ in range(args.warmup):
-        oracle.solve_batch(params, hb.slice(0, min(64, sample)), nthreads=threads)
+    threads, sweep = pick_threads(params, hb, cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle.solve_batch(params, hb.slice(0, min(sample, 8 * threads)), nthreads=threads)
     t_tot = 0.0
     for _ in range(args.steps):
         _, secs = oracle.solve_batch(params, hb, nthreads=threads, mode=0, dense_assembly=False)
@@ -291,17 +344,176 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload.replace("per GPU: batch %d paths" % sample, "per GPU, bounded sample: %d paths "
-                                                "per step" % sample),
-                   "n_knots": args.n, "batch_per_step": sample, "cold_solve": True},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d instances per step, OSQP-algorithm restatement with direct CSC assembly "
-                                   "(real OSQP is not vendored by the reference and not installable here; the "
-                                   "reference's dense assembly temporaries are NOT included)" % sample},
+        "config": {"workload": workload, "n_knots": args.n, "batch_per_gpu": sample, "batch_per_step": sample,
+                   "global_batch": sample, "cold_solve": True, "eps_abs": params.eps_abs, "eps_rel": params.eps_rel,
+                   "max_iter": params.max_iter,
+                   "note": "CPU arm: rank 0 alone, one GPU-rank's batch per step whatever --gpus says"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "host": cores,
+                         "thread_sweep_solves_per_s": sweep,
+                         "sample": "%d instances per step (the whole batch of one GPU rank), OSQP-algorithm restatement "
+                                   "with direct CSC assembly, %d OpenMP threads = fastest of the sweep (real OSQP is not "
+                                   "vendored by the reference and not installable here; the reference's dense assembly "
+                                   "temporaries are NOT included)" % (sample, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class GatherPipe:
+    """The only exchange of the multi-GPU path - an all-gather of {cost f64, status i32, iters i32} =
+    16 B per instance - taken off the solve stream: the records are packed by one library kernel
+    (pqp_pack_results_device) and gathered over NCCL on a side stream while the next batch already
+    solves, so a rank is no longer held in lock step with the slowest rank's launch tail every step
+    (round 1: blocking gather + 6 eager torch launches per step, efficiency 0.92 at 8 GPUs)."""
+
+    def __init__(self, sv, B, world, dev):
+        import torch
+        from path_optimizer_2_b200 import multi
+        self.torch, self.multi, self.sv, self.B, self.world = torch, multi, sv, B, world
+        self.side = torch.cuda.Stream(device=dev)
+        self.packed = torch.zeros(B * 16, dtype=torch.uint8, device=dev)
+        self.gathered = torch.zeros(world * B * 16, dtype=torch.uint8, device=dev)
+        self.ev_solved, self.ev_packed = torch.cuda.Event(), torch.cuda.Event()
+
+    def submit(self, d_cost, d_status, d_iters):
+        """Call right after the solve was queued on the current stream."""
+        import torch.distributed as dist
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        self.ev_solved.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_solved)
+            self.multi.pack_results_device(self.sv, self.B, d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
+                                           self.packed.data_ptr(), stream=self.side.cuda_stream)
+            self.ev_packed.record(self.side)
+            dist.all_gather_into_tensor(self.gathered, self.packed)
+        main.wait_event(self.ev_packed)  # the next solve overwrites cost/status/iters: wait for the 2 us pack only
+
+    def finish(self):
+        self.torch.cuda.current_stream().wait_stream(self.side)
+
+    def table(self):
+        return self.gathered.cpu().numpy().view(self.multi.RESULT_REC)
+
+
+def reduce_max(value, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_scalars(value, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    if world == 1:
+        return [float(value)]
+    out = torch.zeros(world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    return [float(v) for v in out.cpu().numpy()]
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, world, dev, gather=True, clocks=False):
+    """Cold solves of this rank's batch `hb`: device-resident value, end-to-end value, kernel time."""
+    import torch
+    from path_optimizer_2_b200 import solver
+    params = abi.default_params(reserved=option_bits)
+    B, n = hb.batch, hb.n_max
+    sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
+    # inputs smaller than L2 (the shared-map config): evict them between timed steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if hb.knots.nbytes < (160 << 20) else None
+    d_knots, d_inst, d_n = (torch.from_numpy(v).to(dev) for v in (hb.knots, hb.inst, hb.n))
+    d_sol = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
+    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
+    d_status, d_iters = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2))
+    bin_s = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+    bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
+                             None, None, None, None)
+    pipe = GatherPipe(sv, B, world, dev) if (gather and world > 1) else None
+
+    def step():
+        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
+        if pipe:
+            pipe.submit(d_cost, d_status, d_iters)
+
+    for _ in range(warmup):
+        step()
+    if pipe:
+        pipe.finish()
+    barrier(world)
+    sampler = ClockSampler(local_rank) if clocks else None
+    if sampler:
+        sampler.start()
+    launches0 = sv.launch_count
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    e0.record()
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 255)
+        kev[i][0].record()
+        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
+        kev[i][1].record()
+        if pipe:
+            pipe.submit(d_cost, d_status, d_iters)
+    if pipe:
+        pipe.finish()  # the timed region ends when the last gather has landed
+    e1.record()
+    barrier(world)
+    launches = sv.launch_count - launches0
+    clk = sampler.stop() if sampler else None
+    my_ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    total_ms = reduce_max(my_ms, dev, world)
+    status, iters = d_status.cpu().numpy(), d_iters.cpu().numpy()
+    if pipe:  # the gathered table holds every rank's records; this rank's block must equal its own results
+        tab = pipe.table()
+        rank = int(os.environ.get("RANK", "0"))
+        mine = tab[rank * B:(rank + 1) * B]
+        assert np.array_equal(mine["status"], status) and np.array_equal(mine["iters"], iters), "gathered table is wrong"
+
+    # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed)
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    p_knots, p_inst, p_n = pin(hb.knots), pin(hb.inst), pin(hb.n)
+    hbp = abi.HostBatch(p_knots.numpy(), p_inst.numpy(), p_n.numpy())
+    hres = abi.HostResult(B, n, full=False, info=False)
+    p_sol, p_cost = pin(hres.sol), pin(hres.cost)
+    p_status, p_iters = pin(hres.status), pin(hres.iters)
+    hres.sol, hres.cost, hres.status, hres.iters = p_sol.numpy(), p_cost.numpy(), p_status.numpy(), p_iters.numpy()
+    for _ in range(2):
+        sv.solve(hbp, out=hres)
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sv.solve(hbp, out=hres)  # synchronous: returns after the D2H copy completed
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0, dev, world)
+    h2d = int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes)
+    d2h = int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes)
+    if not (option_bits & 2):  # the host call escalates suspected-infeasible instances to FP64, the device call cannot
+        assert np.array_equal(hres.status, status), "host-API and device-API runs disagree"
+    info = sv.kernel_info
+    kms = gather_scalars(kernel_ms, dev, world)
+    sv.close()
+    return {"value": world * B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms,
+            "kernel_ms_per_rank": kms, "e2e_value": world * B * e2e_steps / e2e_s, "e2e_steps": e2e_steps,
+            "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clk, "status": status, "iters": iters,
+            "info": info, "params": params, "flushed": flush is not None, "steps": steps}
 
 
 def run_receding(args, rank, local_rank, world, dev):
@@ -310,8 +522,7 @@ def run_receding(args, rank, local_rank, world, dev):
     re-linearise about the previous solution, warm re-solve with max_iter = 50 through
     pqp_resolve_device; x, z, y, rho stay resident in the handle between ticks."""
     import torch
-    import torch.distributed as dist
-    from path_optimizer_2_b200 import sharding, solver
+    from path_optimizer_2_b200 import solver
 
     B, n = args.batch, args.n
     ticks = args.warmup + args.steps
@@ -326,27 +537,12 @@ def run_receding(args, rank, local_rank, world, dev):
     d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
     d_status = torch.zeros(B, dtype=torch.int32, device=dev)
     d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
-    gathered = torch.zeros((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
     bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
                              None, None, None, None)
-
-    def launch(knots, inst, warm):
-        bin_s = abi.PqpBatchIn(B, n, knots.data_ptr(), inst.data_ptr(), d_n.data_ptr(), None)
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream, warm=warm)
-        if world > 1:
-            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    launch(d_knots, d_inst, False)  # tick 0: cold
-    tick = 0
-    ext_len = int(d_ext.shape[2])
+    pipe = GatherPipe(sv, B, world, dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
     bin_w = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
+    ext_len = int(d_ext.shape[2])
 
     def tick_device(t):
         # window bookkeeping in one launch of the library's own kernel, in place: the previous
@@ -354,18 +550,23 @@ def run_receding(args, rank, local_rank, world, dev):
         sv.advance_window_device(B, ext_len, t, d_ext.data_ptr(), d_sol.data_ptr(), d_knots.data_ptr(),
                                  d_inst.data_ptr(), stream=stream)
 
+    sv.solve_device(bin_w, bout_s, stream=stream, warm=False)  # tick 0: cold
+    tick = 0
     for _ in range(args.warmup):
         tick += 1
         tick_device(tick)
-        launch(d_knots, d_inst, True)
-    barrier()
+        sv.solve_device(bin_w, bout_s, stream=stream, warm=True)
+        if pipe:
+            pipe.submit(d_cost, d_status, d_iters)
+    if pipe:
+        pipe.finish()
+    barrier(world)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sv.launch_count
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters_sum, solved_sum = 0.0, 0.0
-    barrier()
+    barrier(world)
     e0.record()
     for i in range(args.steps):
         tick += 1
@@ -373,21 +574,20 @@ def run_receding(args, rank, local_rank, world, dev):
         kev[i][0].record()
         sv.solve_device(bin_w, bout_s, stream=stream, warm=True)
         kev[i][1].record()
-        if world > 1:
-            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
+        if pipe:
+            pipe.submit(d_cost, d_status, d_iters)
+    if pipe:
+        pipe.finish()
     e1.record()
-    barrier()
+    barrier(world)
     launches = sv.launch_count - launches0
     clocks = sampler.stop()
-    total_ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = reduce_max(e0.elapsed_time(e1), dev, world)
     value = world * B * args.steps / (total_ms * 1e-3)
     status = d_status.cpu().numpy()
     iters = d_iters.cpu().numpy()
+    kms = gather_scalars(kernel_ms, dev, world)
 
     # e2e: the same tick through the host-pointer call (pinned host buffers, H2D + D2H timed);
     # the window bookkeeping runs on the host in numpy and is part of the timed region
@@ -397,51 +597,117 @@ def run_receding(args, rank, local_rank, world, dev):
     sv2.solve(hb, out=hres)
     inst_h, tick2 = ext.inst, 0
     e2e_steps = args.e2e_steps or args.steps
-    torch.cuda.synchronize()
+    barrier(world)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         tick2 += 1
         k_h, inst_h = synthetic.shift_window(ext.knots, inst_h, hres.sol, tick2, n)
         sv2.resolve(abi.HostBatch(k_h, inst_h, hb.n), out=hres)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
-    if rank == 0:
-        peak, peak_src = hbm_peak()
-        bytes_per_launch = B * algorithmic_bytes(n, warm=True)
-        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-        info = sv.kernel_info
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "BASELINE configs[4] per GPU: receding-horizon warm re-solve, batch %d, %d knots, "
-                            "50-iteration cap, window advances one knot per step" % (B, n),
-                "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                "max_iter": 50, "l2_policy": "inputs %.0f MB per step (smaller than L2; each step reads freshly "
-                                             "written window buffers)" % (d_knots.numel() * 8 / 1e6),
-                "collective": "all_gather of {cost,status,iters} (16 B/instance)" if world > 1 else "none",
-                "mean_admm_iters": float(np.mean(iters)),
-                "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
-                "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
-            },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes),
-                    "d2h_bytes_per_step": int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes),
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "pqp_admm_kernel (warm)", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": bytes_per_launch},
-        }
-        print(json.dumps(line))
+    e2e_s = reduce_max(time.perf_counter() - t0, dev, world)
+    e2e_value = world * B * e2e_steps / e2e_s
+    info = sv.kernel_info
     sv.close()
     sv2.close()
+    peak, peak_src = hbm_peak()
+    bytes_per_launch = B * algorithmic_bytes(n, warm=True)
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[4] per GPU: receding-horizon warm re-solve, batch %d, %d knots, "
+                        "50-iteration cap, window advances one knot per step" % (B, n),
+            "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+            "max_iter": 50, "l2_policy": "inputs %.0f MB per step (smaller than L2; each step reads freshly "
+                                         "written window buffers)" % (d_knots.numel() * 8 / 1e6),
+            "collective": "all_gather of {cost,status,iters} (16 B/instance) on a side stream, overlapping the next "
+                          "tick's solve" if world > 1 else "none",
+            "mean_admm_iters": float(np.mean(iters)),
+            "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
+            "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
+            "kernel_ms_per_rank": {"min": min(kms), "max": max(kms)},
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes),
+                "d2h_bytes_per_step": int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes),
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "pqp_admm_kernel_tmem (warm)", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": bytes_per_launch},
+    }
+
+
+def dropin_single_path(n=120, plans=200):
+    """BASELINE configs[0]: ONE path of ~120 knots through the C++ drop-in (include/pqp_base_solver.hpp),
+    driven like PathOptimizer::optimizePath at 30 Hz (path_optimizer.cpp:138-153): a BaseSolver object
+    is constructed per plan, solve() + updateProblemFormulationAndSolve(), destructed. Wall time per
+    plan INCLUDING construction/destruction; the first plan pays pqp_create, later ones borrow the
+    pooled handle."""
+    from path_optimizer_2_b200 import sharedmap
+    from tests import test_dropin
+    exe = test_dropin._build(False)
+    dmap = sharedmap.DistanceMap()
+    lines = sharedmap.make_lines(1, n, dmap=dmap)
+    from oracle import bounds_oracle
+    bnd, nv = bounds_oracle.update_bounds(dmap.dist, dmap.res, lines.spline_rows(0), *lines.states[0])
+    hb = lines.to_host_batch(bnd[None], np.array([nv], dtype=np.int32))
+    nn = int(hb.n[0])
+    ref = np.stack([lines.states[0][1], lines.states[0][2], lines.states[0][3]])
+    path = os.path.join(ROOT, "gpurun_out", "bench_dropin_instance.txt")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    test_dropin._write_instance(path, hb.knots[0], hb.inst[0], nn, ref, 0.0, constraint_end_heading=0)
+    out = subprocess.run([exe, path, str(plans)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    tok = out[0].split()
+    if tok[0] != "plans":
+        return {"error": out[0]}
+    st = {tok[i]: float(tok[i + 1]) for i in range(0, 10, 2)}
+    sg = {tok[i]: float(tok[i + 1]) for i in range(11, len(tok) - 1, 2)}
+    return {"what": "BASELINE configs[0]: one path, %d knots, gridmap.png clearance bounds, C++ drop-in BaseSolverT "
+                    "constructed per plan (solve + updateProblemFormulationAndSolve = 2 solves per plan)" % nn,
+            "plans": int(st["plans"]), "first_plan_ms_incl_pqp_create": st["first_ms"], "later_plan_ms": st["later_ms"],
+            "plans_per_s": 1e3 / st["later_ms"], "solves_per_s": 2e3 / st["later_ms"],
+            "handle_pool": {"creates": int(st["creates"]), "hits": int(st["hits"])},
+            "last_call_stage_ms": sg}
+
+
+def secondary(args, rank, local_rank, world, dev, hb_primary):
+    """The other BASELINE configs and the FP64 instantiation, measured in the same run (short loops)."""
+    sec = {}
+    # the like-for-like precision against FP64 OSQP: the same kernel instantiated in double (option bit 2)
+    steps = max(2, min(args.steps, 3))
+    r = measure_cold(args, hb_primary, 2, steps, 1, 2, local_rank, world, dev, gather=False)
+    fp64 = {"value": r["value"], "unit": UNIT, "e2e": r["e2e_value"], "kernel_ms": r["kernel_ms"], "steps": steps,
+            "mean_admm_iters": float(np.mean(r["iters"])), "solved_fraction": float(np.mean(r["status"] == abi.PQP_SOLVED)),
+            "what": "same workload, pqp_params.reserved = 2: iterates, factorisation and residuals in FP64 "
+                    "(reproduces the FP64 oracle's iterates to 1e-8, tests/test_gpu_parity.py)"}
+    # configs[4] at this N
+    a4 = argparse.Namespace(**vars(args))
+    a4.batch, a4.n, a4.steps, a4.warmup, a4.e2e_steps = 512, 240, 20, 3, 5
+    l4 = run_receding(a4, rank, local_rank, world, dev)
+    sec["configs[4]"] = {"workload": l4["config"]["workload"], "value": l4["value"], "unit": UNIT, "n_gpus": world,
+                         "ms_per_step": l4["ms_per_step"], "e2e": l4["e2e"]["value"], "kernel_ms": l4["roofline"]["kernel_ms"],
+                         "mean_admm_iters": l4["config"]["mean_admm_iters"], "solved_fraction": l4["config"]["solved_fraction"],
+                         "kernel_ms_per_rank": l4["config"]["kernel_ms_per_rank"]}
+    if world == 1:
+        a1 = argparse.Namespace(**vars(args))
+        a1.workload, a1.batch, a1.n = "sharedmap", 1024, 120
+        hb1, wl1, ex1 = make_workload(a1, 1024, 0, device=local_rank)
+        r1 = measure_cold(a1, hb1, args.option_bits, min(args.steps, 10), 3, 5, local_rank, world, dev, gather=False)
+        sec["configs[1]"] = {"workload": wl1, "value": r1["value"], "unit": UNIT, "e2e": r1["e2e_value"],
+                             "ms_per_step": r1["ms_per_step"], "kernel_ms": r1["kernel_ms"],
+                             "mean_admm_iters": float(np.mean(r1["iters"])),
+                             "solved_fraction": float(np.mean(r1["status"] == abi.PQP_SOLVED)),
+                             "l2_policy": "L2 flushed between timed steps", **ex1}
+        if rank == 0:
+            try:
+                sec["configs[0]"] = dropin_single_path()
+            except Exception as e:  # the drop-in binary needs g++ on the box; report rather than lose the line
+                sec["configs[0]"] = {"error": repr(e)}
+    return fp64, sec
 
 
 def main():
@@ -452,12 +718,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step")
     ap.add_argument("--n", type=int, default=240, help="knots per path")
-    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="instances of the CPU baseline leg (default: 2048 inside the b200 arm, the whole batch "
+                         "for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip config.fp64 / config.secondary")
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--option-bits", type=int, default=0,
-                    help="pqp_params.reserved: 1 FP32 factorisation, 2 FP64 iterates, 4 no FP64 escalation, "
-                         "8 state in tensor memory, 16 state in shared memory, 32 increment-form ADMM step, 64 textbook form")
+    ap.add_argument("--option-bits", type=int, default=128,
+                    help="pqp_params.reserved: 2 FP64 iterates, 4 no FP64 escalation, 8 state in tensor memory, "
+                         "16 state in shared memory, 32 increment-form ADMM step, 64 textbook form, 128 cold-only "
+                         "handle (default for the cold workloads: nothing is ever re-solved, so no warm state is written)")
     ap.add_argument("--workload", default="cold", choices=["cold", "receding", "sharedmap"],
                     help="cold: BASELINE configs[2]/[3] (default); receding: configs[4], warm re-solves with a "
                          "50-iteration cap on a window that advances one knot per step; sharedmap: configs[1], "
@@ -470,7 +740,6 @@ def main():
             args.batch = 1024
         if args.n == 240:
             args.n = 120
-        args.cpu_sample = min(args.cpu_sample, args.batch)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
 
@@ -483,7 +752,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from path_optimizer_2_b200 import sharding, solver
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -493,110 +761,29 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     if args.workload == "receding":
-        run_receding(args, rank, local_rank, world, dev)
+        line = run_receding(args, rank, local_rank, world, dev)
+        if rank == 0:
+            print(json.dumps(line))
         if world > 1:
             dist.destroy_process_group()
         return
-    params = abi.default_params(reserved=args.option_bits)
+
     B, n = args.batch, args.n
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
     hb, workload, extras = make_workload(args, B, rank * B, device=local_rank)
-    sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
-    # inputs smaller than L2 (the shared-map config): evict them between timed steps
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if hb.knots.nbytes < (160 << 20) else None
-
-    # ---- device-resident inputs/outputs (torch owns the memory, the C ABI gets raw pointers)
-    d_knots = torch.from_numpy(hb.knots).to(dev)
-    d_inst = torch.from_numpy(hb.inst).to(dev)
-    d_n = torch.from_numpy(hb.n).to(dev)
-    d_sol = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
-    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
-    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
-    d_iters = torch.zeros(B, dtype=torch.int32, device=dev)
-    bin_s = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
-    bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
-                             None, None, None, None)
-    # gathered per-instance results {cost f64, status i32, iters i32} = 16 B / instance
-    gathered = torch.zeros((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
-
-    def step_device():
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
-        if world > 1:  # the only exchange: all-gather of {cost, status, iters} over NCCL
-            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = sv.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.fill_(i & 255)
-        kev[i][0].record()
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
-        kev[i][1].record()
-        if world > 1:
-            sharding.gather_results(sharding.pack_results(d_cost, d_status, d_iters), gathered)
-        ev[i + 1].record()
-    barrier()
-    launches = sv.launch_count - launches0
-    clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms * 1e-3)
-    status = d_status.cpu().numpy()
-    iters = d_iters.cpu().numpy()
-
-    # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed)
-    e2e_steps = args.e2e_steps or args.steps
-    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
-    p_knots, p_inst, p_n = pin(hb.knots), pin(hb.inst), pin(hb.n)
-    hbp = abi.HostBatch(p_knots.numpy(), p_inst.numpy(), p_n.numpy())
-    hres = abi.HostResult(B, n, full=False, info=False)
-    p_sol, p_cost = pin(hres.sol), pin(hres.cost)
-    p_status, p_iters = pin(hres.status), pin(hres.iters)
-    hres.sol, hres.cost, hres.status, hres.iters = p_sol.numpy(), p_cost.numpy(), p_status.numpy(), p_iters.numpy()
-    for _ in range(2):
-        sv.solve(hbp, out=hres)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sv.solve(hbp, out=hres)  # synchronous: returns after the D2H copy completed
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * B * e2e_steps / e2e_s
-    h2d = int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes)
-    d2h = int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes)
-    assert np.array_equal(hres.status, status), "host-API and device-API runs disagree"
+    r = measure_cold(args, hb, args.option_bits, args.steps, args.warmup, args.e2e_steps or args.steps, local_rank,
+                     world, dev, gather=True, clocks=True)
+    fp64, sec = (None, None) if args.no_secondary else secondary(args, rank, local_rank, world, dev, hb)
 
     if rank == 0:
+        params, info = r["params"], r["info"]
         peak, peak_src = hbm_peak()
         bytes_per_launch = B * algorithmic_bytes(n)
-        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-        info = sv.kernel_info
+        achieved = bytes_per_launch / (r["kernel_ms"] * 1e-3) / 1e9
+        cold_only = bool(args.option_bits & 128)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload,
@@ -604,35 +791,42 @@ def main():
                 "n_knots": n, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                 "eps_abs": params.eps_abs, "eps_rel": params.eps_rel, "max_iter": params.max_iter,
                 "l2_policy": ("inputs larger than L2 (%.0f MB per step vs 126 MB)" % (hb.knots.nbytes / 1e6))
-                if flush is None else "L2 flushed between timed steps (256 MB fill inside the timed region)",
-                "collective": "all_gather of {cost,status,iters} (16 B/instance)" if world > 1 else "none",
-                "mean_admm_iters": float(np.mean(iters)),
-                "solved_fraction": float(np.mean(status == abi.PQP_SOLVED)),
+                if not r["flushed"] else "L2 flushed between timed steps (256 MB fill inside the timed region)",
+                "collective": ("all_gather of {cost,status,iters} (16 B/instance): one pack kernel + NCCL on a side "
+                               "stream, overlapping the next step's solve; the timed region ends after the last gather")
+                if world > 1 else "none",
+                "mean_admm_iters": float(np.mean(r["iters"])),
+                "solved_fraction": float(np.mean(r["status"] == abi.PQP_SOLVED)),
                 "warps_per_sm": info["warps_per_sm"], "smem_per_warp": info["smem_per_warp"],
+                "kernel_ms_per_rank": {"min": min(r["kernel_ms_per_rank"]), "max": max(r["kernel_ms_per_rank"]),
+                                       "all": r["kernel_ms_per_rank"]},
+                "option_bits": args.option_bits,
+                "warm_state": "not kept (cold-only handle, option bit 128: these batches are solved once)" if cold_only
+                else "kept per instance for pqp_resolve",
                 "admm_step": ("increment form (dx solve, carried row values)"
                               if (args.option_bits & 32) or (not (args.option_bits & (64 | 2)) and n >= 64)
                               else "textbook form"),
                 "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if info["smem_per_warp"] < 72 * 128 else "shared memory",
             },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "clocks": r["clocks"],
+            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "steps": r["e2e_steps"]},
+            "gpu_launches": r["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(n, B), "peak_source": peak_src,
-                         "kernel": "pqp_admm_kernel", "kernel_ms": kernel_ms,
+                         "frac": achieved / peak, "traffic": measured_traffic(n, B, cold_only), "peak_source": peak_src,
+                         "kernel": "pqp_admm_kernel_tmem", "kernel_ms": r["kernel_ms"],
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "per-iteration state is on-chip (tensor memory / shared memory); the path is "
                                  "latency/issue bound, not HBM bound (see DESIGN.md)"},
         }
+        if fp64 is not None:
+            line["config"]["fp64"] = fp64
+            line["config"]["secondary"] = sec
         if world == 1 and not args.no_cpu:
-            from oracle import oracle
-            cb, _ = cpu_baseline(params, hb, args.cpu_sample, host_threads())
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_baseline(params, hb, args.cpu_sample or 2048)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    sv.close()
 
 
 if __name__ == "__main__":

@@ -1759,7 +1759,10 @@ struct QpWarp {
             // iter % interval == 0 without an integer division in the loop
             const bool last = iter >= P.max_iter;
             const bool can_check = (--to_check == 0) || last;
-            const bool can_adapt = (--to_adapt == 0) && !last;
+            // OSQP adapts rho on the last iteration too (osqp_solve: the rho update follows the regular
+            // termination check inside the loop body): no further solve uses the refactorisation, but the
+            // adapted rho is what the next warm solve starts from
+            const bool can_adapt = (--to_adapt == 0);
             if (to_check <= 0) to_check = P.check_every > 0 ? P.check_every : -1;
             if (to_adapt <= 0) to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
             if (Incr) {
@@ -1773,12 +1776,16 @@ struct QpWarp {
                 nr = residuals();
                 if (can_check) {
                     status = check_termination(nr, last);
-                    if (status != kUnsolved) break;
+                    // at the iteration cap the statuses of the final 10x re-check are decided on the same
+                    // residuals, but OSQP reaches that re-check only after the loop body's rho update
+                    const bool capped = last && (status == kMaxIter || status == kSolvedInacc || status == kPrimInfInacc);
+                    if (status != kUnsolved && !(capped && can_adapt)) break;
                 }
                 if (can_adapt && adapt_rho(nr)) {
                     ++rho_updates;
                     need_factor = true;
                 }
+                if (last) break;
             }
         }
         epilogue(status, iter, rho_updates, nr);

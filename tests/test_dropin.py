@@ -112,6 +112,8 @@ def test_dropin_long_path_and_handle_pool(tmp_path):
     params = abi.default_params()
     knots, inst, n, ref = synthetic.make_instance(3, 1, 400)
     assert n == 400 and knots[abi.F_S, n - 1] > 60.0
+    inst = inst.copy()
+    inst[abi.I_EPSI_LO], inst[abi.I_EPSI_HI] = -abi.INFTY, abi.INFTY  # constraint_end_heading = 0 below
     p = str(tmp_path / "long.txt")
     _write_instance(p, knots, inst, n, ref, 0.0, constraint_end_heading=0)
     lines = subprocess.run([exe, p, "20"], capture_output=True, text=True, check=True).stdout.strip().split("\n")

@@ -181,7 +181,9 @@ def test_fp64_mode_reproduces_oracle_iterates(solver_mod):
             s = oracle.OracleSolver(p32, hb.knots[b], hb.inst[b], n)
             st = s.solve()
             assert res.status[b] == st and res.iters[b] == s.iters
-            assert abs(res.info[b, 2] - s.rho) <= 1e-5 * s.rho
+            # rho = rho_prev * sqrt(ratio of RESIDUAL norms): iterates that agree to 1e-8 give residual norms
+            # (1e-3 .. 1e-5) that agree to 1e-5 .. 1e-3 relative
+            assert abs(res.info[b, 2] - s.rho) <= 2e-3 * s.rho
             if st == abi.PQP_SOLVED:
                 assert np.max(np.abs(res.x_full[b, :s.nv] - s.x())) < 1e-5
         sv.close()
