@@ -194,7 +194,8 @@ int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out)
  * whose n is outside [2, n_max] is skipped by the kernel with status PQP_NUMERICAL_ERROR; (2) there
  * is no FP64 re-solve of suspected-infeasible instances (that needs the statuses on the host): an
  * infeasible instance the FP32 certificate cannot resolve ends as PQP_MAX_ITER_REACHED here and as
- * PQP_PRIMAL_INFEASIBLE through pqp_solve. Both mean `false` to the reference's caller
+ * PQP_PRIMAL_INFEASIBLE through pqp_solve (cold solves only: pqp_resolve never escalates, the FP64 re-solve
+ * would start cold). Both mean `false` to the reference's caller
  * (base_solver.cpp:88). After a host-pointer call escalated an instance, its warm slot is reset to
  * the cold state (zero iterates, rho = params.rho). */
 int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,

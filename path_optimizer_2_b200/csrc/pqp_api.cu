@@ -163,17 +163,18 @@ struct TmemStore {
         return g == pqp::GR5 ? 0 : g == pqp::GS6 ? 1 : g <= 4 ? 6 - g : g >= pqp::GF0 ? 7 + (17 - g) : 13 + (11 - g);
     }
     __host__ __device__ static constexpr bool spilled(int g) { return spill_rank(g) < kSpill; }
-    // position among the groups kept in tensor memory / among the spilled ones (ascending group order)
-    __host__ __device__ static constexpr int slot(int g) {
-        int s = 0;
-        for (int j = 0; j < g; ++j) s += spilled(j) ? 0 : 1;
-        return s;
+    // number of spilled groups with an index below g, in closed form (no loops: g reaches these helpers as a
+    // function argument and must fold to a constant after inlining - a loop here grew the kernel by 40 %)
+    __host__ __device__ static constexpr int imax(int a, int b) { return a > b ? a : b; }
+    __host__ __device__ static constexpr int imin(int a, int b) { return a < b ? a : b; }
+    __host__ __device__ static constexpr int spilled_below(int g) {
+        return ((kSpill > 0 && g > pqp::GR5) ? 1 : 0) + ((kSpill > 1 && g > pqp::GS6) ? 1 : 0) +
+               imax(0, imin(g, 5) - imax(0, 7 - kSpill)) +           // read-only groups 4, 3, .. leave from the top
+               imax(0, imin(g, 12) - imax(7, 25 - kSpill)) +         // read-write groups 11 .. 7 (last to leave)
+               imax(0, imin(g, 18) - imax(12, 25 - kSpill));         // factor groups 17 .. 12
     }
-    __host__ __device__ static constexpr int spslot(int g) {
-        int s = 0;
-        for (int j = 0; j < g; ++j) s += spilled(j) ? 1 : 0;
-        return s;
-    }
+    __host__ __device__ static constexpr int slot(int g) { return g - spilled_below(g); }
+    __host__ __device__ static constexpr int spslot(int g) { return spilled_below(g); }
     __device__ uint32_t col(int g, int k) const { return tb + (uint32_t)((k * kGroups + slot(g)) * 4); }
     __device__ float4 *sp(int g, int k) const { return reinterpret_cast<float4 *>(sm) + ((spslot(g) * C + k) * 32 + lane); }
     __device__ float ld(int f, int k) const {
@@ -797,7 +798,7 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     PQP_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     for (int i = 0; i < PQP_NSTAGES; ++i) h->stage_ms[i] = -1.0f;  // copies and kernel overlap: only the total is defined
     h->stage_ms[PQP_STAGE_TOTAL] = h->last_ms;
-    if (!h->fp64 && h->escalate) return escalate_fp64(h, in, out, B);
+    if (!h->fp64 && h->escalate && mode == 0) return escalate_fp64(h, in, out, B);
     return PQP_OK;
 }
 
@@ -923,7 +924,9 @@ int run_host(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     }
     h->stage_ms[PQP_STAGE_TOTAL] = h->last_ms;
     h->stage_ms[PQP_STAGE_ESCALATION] = 0.0f;
-    if (!h->fp64 && h->escalate) {
+    // cold solves only: the FP64 re-solve starts cold, which is not what a warm re-solve under an iteration
+    // cap (receding horizon) is; the increment-form kernel certifies infeasibility by itself there
+    if (!h->fp64 && h->escalate && mode == 0) {
         PQP_CUDA(h, cudaEventRecord(h->ev_st[2], streams[0]));
         rc = escalate_fp64(h, in, out, B);
         if (rc) return rc;

@@ -14,6 +14,7 @@
 
 #include "../../include/pqp_bounds.h"
 #include "pqp_bounds_core.cuh"
+#include "pqp_bounds_internal.h"
 #include "pqp_device_guard.h"
 
 namespace {
@@ -135,6 +136,11 @@ struct pqp_bounds_handle {
     bool timed = false;
     std::string err;
 };
+
+namespace pqb {
+const MapView *handle_map(const pqp_bounds_handle *h) { return h ? &h->map : nullptr; }
+int handle_device(const pqp_bounds_handle *h) { return h ? h->device : -1; }
+}  // namespace pqb
 
 namespace {
 

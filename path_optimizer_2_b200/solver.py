@@ -35,13 +35,20 @@ def build_library(force=False, verbose=False):
     """nvcc-compile the CUDA library in-tree for sm_100a (no GPU needed to compile)."""
     root = os.path.dirname(_PKG)
     cu = [os.path.join(_CSRC, f) for f in ("pqp_api.cu", "pqp_bounds.cu", "pqp_multi.cu")]
-    deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh", "pqp_device_guard.h")]
-    deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h", "pqp_multi.h")]
+    deps = cu + [os.path.join(_CSRC, f) for f in ("pqp_kernel.cuh", "pqp_host_common.h", "pqp_bounds_core.cuh", "pqp_device_guard.h",
+                                                  "pqp_dp.cu", "pqp_dp_core.cuh", "pqp_bounds_internal.h")]
+    deps += [os.path.join(root, "include", f) for f in ("pqp.h", "pqp_bounds.h", "pqp_multi.h", "pqp_dp.h")]
     stale = not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in deps)
     if force or stale:
+        # the lattice DP (pqp_dp.cu) is a chain of threshold / strict-minimum decisions in FP64: it is compiled
+        # without multiply-add contraction so that every operation rounds as in the host restatement
+        obj = os.path.join(_PKG, "pqp_dp.o")
+        common = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + [
+            "-I", os.path.join(root, "include")]
+        subprocess.check_call(["nvcc"] + common + ["--fmad=false", "-c", os.path.join(_CSRC, "pqp_dp.cu"), "-o", obj])
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-I", os.path.join(root, "include"), "-o", LIB_PATH] + cu + ["-ldl"]
+            "-I", os.path.join(root, "include"), "-o", LIB_PATH] + cu + [obj, "-ldl"]
         subprocess.check_call(cmd)
     return LIB_PATH
 

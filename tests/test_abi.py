@@ -72,6 +72,21 @@ def test_library_contains_sm100a_code_and_tma():
     sass = subprocess.run(["cuobjdump", "-sass", solver.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass          # cp.async.bulk global->shared (TMA 1-D bulk copy)
     assert "SHFL" in sass            # warp-shuffle cyclic reduction / norm reductions
+    assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / tcgen05.st: per-lane state in tensor memory
+    # code-size guard of the headline kernel (n_max 128..255, tensor memory, increment form): beyond one warp
+    # per scheduler the kernel is instruction-fetch bound, and an innocent-looking helper that stops folding to a
+    # constant once cost 42 % more instructions, register spills and 2.3x the run time (profiles/r2/README.md)
+    count, spills, name = 0, 0, None
+    for ln in sass.splitlines():
+        if "Function :" in ln:
+            name = ln
+        elif name and "pqp_admm_kernel_tmemILi8ELi4ELb1" in name and "/*" in ln and ln.lstrip().startswith("/*0") or \
+                (name and "pqp_admm_kernel_tmemILi8ELi4ELb1" in name and ln.lstrip().startswith("/*") and ";" in ln):
+            count += 1
+            if " STL" in ln or " LDL" in ln:
+                spills += 1
+    assert 4000 < count < 9200, count
+    assert spills <= 6, spills   # the kernel's 40-byte stack frame; a spilling build adds to these
 
 
 def test_no_cpu_fallback_without_device(lib):
