@@ -68,3 +68,40 @@ def osqp_smooth(x_list, y_list, angle_list, k_list, s_list, **weights):
     rx, ry = x[:p], x[p:2 * p]
     rs = np.concatenate(([0.0], np.cumsum(np.hypot(np.diff(rx), np.diff(ry)))))
     return ok, rx, ry, rs, g
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ReferencePathSmoother::postSmooth's QP (/root/reference/src/reference_path_smoother/reference_path_smoother.cpp:526-636)
+# Variables (3p): x_0..x_{p-1} (lateral offsets of the DP layers), dx_0.., ddx_0..; constraints (3p - 2):
+#   x_i in [layers_bounds_[i]]  (row 0: x_0 = vehicle_l_wrt_smoothed_ref_, :628-633)
+#   x_{i+1} - x_i - ds_i dx_i = 0,  dx_{i+1} - dx_i - ds_i ddx_i = 0          (:612-622)
+# Cost: 1/2 (1 x^2 + 100 dx^2 + 1000 ddx^2) (Hessian :584-597 = diag(weight), no factor 2), q = 0. OSQP defaults.
+POST_W_X, POST_W_DX, POST_W_DDX = 1.0, 100.0, 1000.0
+
+
+def assemble_post(layer_s, lower, upper, vehicle_l, w_x=POST_W_X, w_dx=POST_W_DX, w_ddx=POST_W_DDX):
+    layer_s, lower, upper = (np.asarray(v, dtype=np.float64) for v in (layer_s, lower, upper))
+    p = len(layer_s)
+    nv, m = 3 * p, 3 * p - 2
+    H = sp.diags(np.concatenate((np.full(p, w_x), np.full(p, w_dx), np.full(p, w_ddx)))).tocsc()
+    A = sp.lil_matrix((m, nv))
+    lo, up = np.zeros(m), np.zeros(m)
+    cdx, cddx = p, 2 * p - 1
+    for i in range(p):
+        A[i, i] = 1.0
+    for i in range(p - 1):
+        ds = layer_s[i + 1] - layer_s[i]
+        A[cdx + i, i + 1], A[cdx + i, i], A[cdx + i, p + i] = 1.0, -1.0, -ds
+        A[cddx + i, p + i + 1], A[cddx + i, p + i], A[cddx + i, 2 * p + i] = 1.0, -1.0, -ds
+    lo[0] = up[0] = vehicle_l
+    lo[1:p], up[1:p] = lower[1:], upper[1:]
+    return H, np.zeros(nv), sp.csc_matrix(A), lo, up
+
+
+def post_smooth(layer_s, lower, upper, vehicle_l, **kw):
+    """-> (ok, offsets = QPSolution(0..p-1), solver)."""
+    H, q, A, lo, up = assemble_post(layer_s, lower, upper, vehicle_l)
+    g = osqp_generic.GenericOsqp(H, q, A, lo, up, **kw)
+    ok = g.solve() == osqp_generic.SOLVED
+    x, _, _ = g.solution()
+    return ok, x[:len(layer_s)], g
