@@ -196,8 +196,8 @@ int pqp_resolve(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out)
  * infeasible instance the FP32 certificate cannot resolve ends as PQP_MAX_ITER_REACHED here and as
  * PQP_PRIMAL_INFEASIBLE through pqp_solve (cold solves only: pqp_resolve never escalates, the FP64 re-solve
  * would start cold). Both mean `false` to the reference's caller
- * (base_solver.cpp:88). After a host-pointer call escalated an instance, its warm slot is reset to
- * the cold state (zero iterates, rho = params.rho). */
+ * (base_solver.cpp:88). After a host-pointer call escalated an instance, its warm slot holds the FP64
+ * run's iterates and rho (cast to FP32), i.e. a later pqp_resolve warm-starts from the run that was returned. */
 int pqp_solve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,
                      void *stream);
 int pqp_resolve_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out,

@@ -356,6 +356,18 @@ __global__ void advance_window_kernel(int batch, int n_max, int ext_len, int tic
     }
 }
 
+// After an FP64 re-solve: the instance's warm slot (FP32) takes over the FP64 run's scaled iterates and rho, so
+// that a later pqp_resolve warm-starts from the run whose result was returned, not from the abandoned FP32 one.
+__global__ void adopt_warm_kernel(int count, size_t warm_len, const int *__restrict__ slots, const double *__restrict__ e_warm,
+                                  const double *__restrict__ e_rho, float *__restrict__ d_warm, float *__restrict__ d_rho) {
+    const int j = blockIdx.y;
+    if (j >= count) return;
+    const size_t b = (size_t)slots[j];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < warm_len; i += (size_t)gridDim.x * blockDim.x)
+        d_warm[b * warm_len + i] = (float)e_warm[(size_t)j * warm_len + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) d_rho[b] = (float)e_rho[j];
+}
+
 // {cost, status, iters} -> one 16-byte record per instance (the payload of the multi-GPU all-gather)
 __global__ void pack_results_kernel(int batch, const double *__restrict__ cost, const int *__restrict__ status,
                                     const int *__restrict__ iters, pqp_result_rec *__restrict__ out) {
@@ -398,7 +410,6 @@ struct pqp_handle {
     bool escalate = true;          // params.reserved bit 2 clears it
     bool cold_only = false;        // params.reserved bit 128: no warm state is kept (pqp_resolve* is refused)
     float stage_ms[PQP_NSTAGES] = {0, 0, 0, 0, 0};
-    float rho0_f = 0.1f;           // source of the async "slot is cold again" copy after an escalation
     cudaEvent_t ev_st[4] = {};     // stage boundaries of the single-stream host call
     size_t smem_bytes64 = 0;
     bool prepared64 = false;
@@ -408,7 +419,7 @@ struct pqp_handle {
     int esc_cap = 0;
     double *e_knots = nullptr, *e_inst = nullptr, *e_sol = nullptr, *e_cost = nullptr, *e_info = nullptr;
     double *e_xf = nullptr, *e_yf = nullptr, *e_zf = nullptr;
-    int *e_n = nullptr, *e_p = nullptr, *e_status = nullptr, *e_iters = nullptr;
+    int *e_n = nullptr, *e_p = nullptr, *e_status = nullptr, *e_iters = nullptr, *e_slots = nullptr;
     void *e_warm = nullptr, *e_scal = nullptr, *e_dy = nullptr, *e_rho = nullptr;
     long long escalated = 0;
     double *d_sol2 = nullptr;
@@ -670,6 +681,7 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
         PQP_CUDA(h, cudaMalloc(&h->e_scal, E * pqp::scal_floats(c) * sizeof(double)));
         PQP_CUDA(h, cudaMalloc(&h->e_dy, E * pqp::dy_floats(c) * sizeof(double)));
         PQP_CUDA(h, cudaMalloc(&h->e_rho, E * sizeof(double)));
+        PQP_CUDA(h, dmalloc(&h->e_slots, E));
     }
     cudaStream_t s = h->stream;
     const size_t kb = (size_t)PQP_NFIELDS * nmax;
@@ -705,13 +717,15 @@ int escalate_fp64(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *ou
             PQP_CUDA(h, cudaMemcpyAsync(h->d_status + b, h->e_status + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
             PQP_CUDA(h, cudaMemcpyAsync(h->d_cost + b, h->e_cost + j, sizeof(double), cudaMemcpyDeviceToDevice, s));
             PQP_CUDA(h, cudaMemcpyAsync(h->d_iters + b, h->e_iters + j, sizeof(int), cudaMemcpyDeviceToDevice, s));
-            // the FP32 warm state of this slot belongs to the failed run: make the slot cold again (zero
-            // iterates, rho0) so that a later pqp_resolve does not warm-start from it
-            if (!h->cold_only) {
-                const size_t wf = pqp::warm_floats(c);
-                PQP_CUDA(h, cudaMemsetAsync(static_cast<float *>(h->d_warm) + (size_t)b * wf, 0, wf * sizeof(float), s));
-                PQP_CUDA(h, cudaMemcpyAsync(static_cast<float *>(h->d_rho) + b, &h->rho0_f, sizeof(float), cudaMemcpyHostToDevice, s));
-            }
+        }
+        // the warm slots of these instances adopt the FP64 run's scaled iterates and rho
+        if (!h->cold_only) {
+            PQP_CUDA(h, cudaMemcpyAsync(h->e_slots, idx.data() + start, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, s));
+            const size_t wf = pqp::warm_floats(c);
+            adopt_warm_kernel<<<dim3((unsigned)((wf + 255) / 256), (unsigned)E), 256, 0, s>>>(
+                E, wf, h->e_slots, static_cast<const double *>(h->e_warm), static_cast<const double *>(h->e_rho),
+                static_cast<float *>(h->d_warm), static_cast<float *>(h->d_rho));
+            PQP_CUDA(h, cudaGetLastError());
         }
         PQP_CUDA(h, cudaStreamSynchronize(s));
         h->escalated += E;
@@ -1046,7 +1060,6 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     const size_t slots = h->use_tmem ? (size_t)h->sm_count * tmem_warps(h->chunk) : B;
     PQP_CREATE_CUDA(cudaMalloc(&h->d_scal, slots * pqp::scal_floats(c) * esz));
     PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, slots * pqp::dy_floats(c) * esz));
-    h->rho0_f = (float)params->rho;
     for (int i = 0; i < 4; ++i) PQP_CREATE_CUDA(cudaEventCreate(&h->ev_st[i]));
     PQP_CREATE_CUDA(dmalloc(&h->d_counters, (size_t)pqp_handle::kCounters));
     PQP_CREATE_CUDA(dmalloc(&h->d_ready, (size_t)pqp_handle::kStreams));
@@ -1082,7 +1095,7 @@ int pqp_destroy(pqp_handle *h) {
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->e_knots); cudaFree(h->e_inst); cudaFree(h->e_sol); cudaFree(h->e_cost); cudaFree(h->e_info);
     cudaFree(h->e_xf); cudaFree(h->e_yf); cudaFree(h->e_zf); cudaFree(h->e_n); cudaFree(h->e_p);
-    cudaFree(h->e_status); cudaFree(h->e_iters); cudaFree(h->e_warm); cudaFree(h->e_scal); cudaFree(h->e_dy); cudaFree(h->e_rho);
+    cudaFree(h->e_slots); cudaFree(h->e_status); cudaFree(h->e_iters); cudaFree(h->e_warm); cudaFree(h->e_scal); cudaFree(h->e_dy); cudaFree(h->e_rho);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 4; ++i) if (h->ev_st[i]) cudaEventDestroy(h->ev_st[i]);

@@ -142,6 +142,54 @@ PQB_HD double constrain_angle(double a) {  // include/tools/tools.hpp:25-35 (rec
     return a;
 }
 
+// One side of a ray march: probe k sits at v_k = v_{k-1} + inc (accumulated, as the reference accumulates it) along
+// the direction (c, s) from (sx, sy). The probe POSITIONS do not depend on earlier probe results, only the stopping
+// index does - so the probes are issued four at a time (16 independent map gathers in flight per side) and scanned in
+// order afterwards, instead of one dependent lookup per step. Same positions, same comparisons, same results.
+struct MarchSide {
+    double c, s;      // direction
+    double v, inc;    // current accumulated offset, increment per probe
+    int left;         // probes still allowed
+    bool hit;         // a probe below the radius was found; v is the offset of that probe
+};
+PQB_HD void march_two(const MapView &m, double sx, double sy, double radius, MarchSide &A, MarchSide &B) {
+    while ((!A.hit && A.left > 0) || (!B.hit && B.left > 0)) {
+        double va[4], vb[4], da[4], db[4];
+        const int na = (!A.hit && A.left > 0) ? (A.left < 4 ? A.left : 4) : 0;
+        const int nb = (!B.hit && B.left > 0) ? (B.left < 4 ? B.left : 4) : 0;
+        double v = A.v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v += A.inc;
+            va[k] = v;
+        }
+        v = B.v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v += B.inc;
+            vb[k] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            da[k] = k < na ? map_distance(m, sx + va[k] * A.c, sy + va[k] * A.s) : radius;
+            db[k] = k < nb ? map_distance(m, sx + vb[k] * B.c, sy + vb[k] * B.s) : radius;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < na && !A.hit) {
+                A.v = va[k];
+                --A.left;
+                if (da[k] < radius) A.hit = true;
+            }
+            if (k < nb && !B.hit) {
+                B.v = vb[k];
+                --B.left;
+                if (db[k] < radius) B.hit = true;
+            }
+        }
+    }
+}
+
 // ReferencePathImpl::getClearanceWithDirectionStrict (reference_path_impl.cpp:232-312).
 // lb = right bound (<= 0 side), ub = left bound; {0, 0} when the state is too close to an
 // obstacle or the corridor is narrower than the car.
@@ -155,34 +203,20 @@ PQB_HD void clearance(const MapView &m, const Params &P, double sx, double sy, d
     double cl, sl, cr, sr;
     sincos(left_angle, &sl, &cl);
     sincos(right_angle, &sr, &cr);
-    double right_s = 0.0;
-    for (int j = 0; j != n; ++j) {
-        right_s += delta_s;
-        if (map_distance(m, sx + right_s * cr, sy + right_s * sr) < search_radius) break;
-    }
-    double left_s = 0.0;
-    for (int j = 0; j != n; ++j) {
-        left_s += delta_s;
-        if (map_distance(m, sx + left_s * cl, sy + left_s * sl) < search_radius) break;
-    }
+    // coarse marches, both sides together (:242-262): s += 0.3 until the clearance drops below the radius
+    MarchSide R = {cr, sr, 0.0, delta_s, n, false}, L = {cl, sl, 0.0, delta_s, n, false};
+    march_two(m, sx, sy, search_radius, R, L);
+    const double right_s = R.v, left_s = L.v;
     double right_bound = -(right_s - delta_s);
     double left_bound = left_s - delta_s;
+    // fine marches (:266-299): 0.05 m steps from one coarse step back; a hit steps back once (v -= inc, as written)
     const int fine = (int)(delta_s / smaller_ds);
-    for (int i = 1; i != fine; ++i) {
-        left_bound += smaller_ds;
-        if (map_distance(m, sx + left_bound * cl, sy + left_bound * sl) < search_radius) {
-            left_bound -= smaller_ds;
-            break;
-        }
-    }
-    for (int i = 1; i != fine; ++i) {
-        right_bound -= smaller_ds;
-        // as the reference: the negative bound times the right-hand direction (:288-291)
-        if (map_distance(m, sx + right_bound * cr, sy + right_bound * sr) < search_radius) {
-            right_bound += smaller_ds;
-            break;
-        }
-    }
+    MarchSide FL = {cl, sl, left_bound, smaller_ds, fine - 1, false};
+    // as the reference: the negative bound times the right-hand direction (:288-291)
+    MarchSide FR = {cr, sr, right_bound, -smaller_ds, fine - 1, false};
+    march_two(m, sx, sy, search_radius, FL, FR);
+    left_bound = FL.hit ? FL.v - smaller_ds : FL.v;
+    right_bound = FR.hit ? FR.v + smaller_ds : FR.v;
     const double diff_radius = P.car_width * 0.5 - search_radius;
     left_bound -= diff_radius;
     right_bound += diff_radius;
