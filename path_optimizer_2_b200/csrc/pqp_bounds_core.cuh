@@ -5,6 +5,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define PQB_HD __host__ __device__ __forceinline__
@@ -35,6 +36,24 @@ struct SplineView {
 // INTER_LINEAR lookup of the float "distance" layer - bilinear between the four cell centres
 // around the position (grid_map itself is not in the tree; at the outermost half cell it falls
 // back to the nearest cell, which the clamped weights below reproduce).
+// floor(v) for |v| < 2^31 without a conversion instruction: adding 1.5 * 2^52 leaves round-to-nearest(v - 0.5) in the
+// low mantissa bits (as an integer) and, after subtracting the constant again, as a double. F2I / I2F in FP64 run on
+// the XU pipe (16 lanes per clock and SM) and were 36 % of the bounds kernel's pipe time. At an exact integer v the
+// tie may round down by one cell; the bilinear interpolant is continuous across cell borders, so the looked-up value
+// is the same to rounding.
+PQB_HD int floor_to_int(double v, double &as_double) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = (v - 0.5) + magic;
+    as_double = t - magic;
+#ifdef __CUDA_ARCH__
+    return __double2loint(t);
+#else
+    long long bits;
+    memcpy(&bits, &t, sizeof(bits));
+    return (int)(bits & 0xffffffffll);
+#endif
+}
+
 PQB_HD double map_distance(const MapView &m, double x, double y) {
     const double dx = x - m.cx, dy = y - m.cy;
     if (!(fabs(dx) < m.half_lx && fabs(dy) < m.half_ly)) return 0.0;
@@ -42,10 +61,12 @@ PQB_HD double map_distance(const MapView &m, double x, double y) {
     // cell borders, so a last-bit difference in fi, fj cannot change the value beyond rounding
     const double fi = (m.half_lx - dx) * m.inv_res - 0.5;
     const double fj = (m.half_ly - dy) * m.inv_res - 0.5;
-    int i0 = (int)floor(fi), j0 = (int)floor(fj);
-    i0 = i0 < 0 ? 0 : (i0 > m.rows - 2 ? m.rows - 2 : i0);
-    j0 = j0 < 0 ? 0 : (j0 > m.cols - 2 ? m.cols - 2 : j0);
-    double ti = fi - i0, tj = fj - j0;
+    double di, dj;
+    int i0 = floor_to_int(fi, di), j0 = floor_to_int(fj, dj);
+    // outermost half cells: clamp the base cell (the double copies follow; the bounds are loop invariants)
+    if (i0 < 0) { i0 = 0; di = 0.0; } else if (i0 > m.rows - 2) { i0 = m.rows - 2; di = (double)(m.rows - 2); }
+    if (j0 < 0) { j0 = 0; dj = 0.0; } else if (j0 > m.cols - 2) { j0 = m.cols - 2; dj = (double)(m.cols - 2); }
+    double ti = fi - di, tj = fj - dj;
     ti = ti < 0.0 ? 0.0 : (ti > 1.0 ? 1.0 : ti);
     tj = tj < 0.0 ? 0.0 : (tj > 1.0 ? 1.0 : tj);
     const float *r0 = m.dist + (size_t)i0 * m.cols + j0;
@@ -145,7 +166,10 @@ PQB_HD double constrain_angle(double a) {  // include/tools/tools.hpp:25-35 (rec
 // One side of a ray march: probe k sits at v_k = v_{k-1} + inc (accumulated, as the reference accumulates it) along
 // the direction (c, s) from (sx, sy). The probe POSITIONS do not depend on earlier probe results, only the stopping
 // index does - so the probes are issued four at a time (16 independent map gathers in flight per side) and scanned in
-// order afterwards, instead of one dependent lookup per step. Same positions, same comparisons, same results.
+// order afterwards (PQB_PROBE_CHUNK = 1 is the one-dependent-lookup-per-step march). Same positions, same comparisons, same results.
+#ifndef PQB_PROBE_CHUNK
+#define PQB_PROBE_CHUNK 4
+#endif
 struct MarchSide {
     double c, s;      // direction
     double v, inc;    // current accumulated offset, increment per probe
@@ -154,28 +178,29 @@ struct MarchSide {
 };
 PQB_HD void march_two(const MapView &m, double sx, double sy, double radius, MarchSide &A, MarchSide &B) {
     while ((!A.hit && A.left > 0) || (!B.hit && B.left > 0)) {
-        double va[4], vb[4], da[4], db[4];
-        const int na = (!A.hit && A.left > 0) ? (A.left < 4 ? A.left : 4) : 0;
-        const int nb = (!B.hit && B.left > 0) ? (B.left < 4 ? B.left : 4) : 0;
+        constexpr int K = PQB_PROBE_CHUNK;
+        double va[K], vb[K], da[K], db[K];
+        const int na = (!A.hit && A.left > 0) ? (A.left < K ? A.left : K) : 0;
+        const int nb = (!B.hit && B.left > 0) ? (B.left < K ? B.left : K) : 0;
         double v = A.v;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < K; ++k) {
             v += A.inc;
             va[k] = v;
         }
         v = B.v;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < K; ++k) {
             v += B.inc;
             vb[k] = v;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < K; ++k) {
             da[k] = k < na ? map_distance(m, sx + va[k] * A.c, sy + va[k] * A.s) : radius;
             db[k] = k < nb ? map_distance(m, sx + vb[k] * B.c, sy + vb[k] * B.s) : radius;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < K; ++k) {
             if (k < na && !A.hit) {
                 A.v = va[k];
                 --A.left;
