@@ -377,11 +377,11 @@ class GatherPipe:
         self.gathered = torch.zeros(world * B * 16, dtype=torch.uint8, device=dev)
         self.ev_solved, self.ev_packed = torch.cuda.Event(), torch.cuda.Event()
 
-    def submit(self, d_cost, d_status, d_iters):
-        """Call right after the solve was queued on the current stream."""
+    def submit(self, d_cost, d_status, d_iters, stream=None):
+        """Call right after the solve was queued on `stream` (default: the current stream)."""
         import torch.distributed as dist
         torch = self.torch
-        main = torch.cuda.current_stream()
+        main = stream if stream is not None else torch.cuda.current_stream()
         self.ev_solved.record(main)
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.ev_solved)
@@ -427,65 +427,104 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, world, dev, gather=True, clocks=False):
-    """Cold solves of this rank's batch `hb`: device-resident value, end-to-end value, kernel time."""
+def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, world, dev, gather=True, clocks=False,
+                 inflight=1):
+    """Cold solves of this rank's batch `hb`: device-resident value, end-to-end value, kernel time.
+    inflight = 2: consecutive steps alternate between two handles on two streams, so the next batch's CTAs take
+    over SMs as the previous batch's persistent CTAs run out of work (iteration counts are heavy-tailed: 10 % of a
+    lone launch is tail). Every step is still one full batch; the timed region covers all of them."""
     import torch
     from path_optimizer_2_b200 import solver
     params = abi.default_params(reserved=option_bits)
     B, n = hb.batch, hb.n_max
-    sv = solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank)
+    K = max(1, int(inflight))
+    svs = [solver.PathQpSolver(params, n_max=n, batch_max=B, device=local_rank) for _ in range(K)]
+    sv = svs[0]
     # inputs smaller than L2 (the shared-map config): evict them between timed steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if hb.knots.nbytes < (160 << 20) else None
     d_knots, d_inst, d_n = (torch.from_numpy(v).to(dev) for v in (hb.knots, hb.inst, hb.n))
-    d_sol = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
-    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
-    d_status, d_iters = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2))
+    outs = []
+    for _ in range(K):
+        d_sol = torch.zeros((B, 4, n), dtype=torch.float64, device=dev)
+        d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
+        d_status, d_iters = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2))
+        outs.append((d_sol, d_cost, d_status, d_iters,
+                     abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(), None, None, None, None)))
     bin_s = abi.PqpBatchIn(B, n, d_knots.data_ptr(), d_inst.data_ptr(), d_n.data_ptr(), None)
-    bout_s = abi.PqpBatchOut(d_sol.data_ptr(), d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
-                             None, None, None, None)
-    pipe = GatherPipe(sv, B, world, dev) if (gather and world > 1) else None
+    main = torch.cuda.current_stream()
+    streams = [main] if K == 1 else [torch.cuda.Stream(device=dev) for _ in range(K)]
+    pipes = [GatherPipe(svs[k], B, world, dev) if (gather and world > 1) else None for k in range(K)]
 
-    def step():
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
-        if pipe:
-            pipe.submit(d_cost, d_status, d_iters)
+    def step(i, ev=None):
+        k = i % K
+        st = streams[k]
+        if ev is not None:
+            ev[0].record(st)
+        svs[k].solve_device(bin_s, outs[k][4], stream=st.cuda_stream)
+        if ev is not None:
+            ev[1].record(st)
+        if pipes[k]:
+            pipes[k].submit(outs[k][1], outs[k][2], outs[k][3], stream=st)
 
-    for _ in range(warmup):
-        step()
-    if pipe:
-        pipe.finish()
+    def join():
+        for k in range(K):
+            if pipes[k]:
+                with torch.cuda.stream(streams[k]):
+                    pipes[k].finish()
+            if streams[k] is not main:
+                main.wait_stream(streams[k])
+
+    def fork():
+        for st in streams:
+            if st is not main:
+                st.wait_stream(main)
+
+    fork()
+    for i in range(warmup):
+        step(i)
+    join()
     barrier(world)
+    # launch duration of the dominant kernel, timed alone (one launch at a time) - the roofline's denominator
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(steps, 5))]
+    for i in range(len(kev)):
+        if flush is not None:
+            flush.fill_(i & 255)
+        kev[i][0].record(main)
+        svs[0].solve_device(bin_s, outs[0][4], stream=main.cuda_stream)
+        kev[i][1].record(main)
+    barrier(world)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     sampler = ClockSampler(local_rank) if clocks else None
     if sampler:
         sampler.start()
-    launches0 = sv.launch_count
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    launches0 = sum(s_.launch_count for s_ in svs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
-    e0.record()
+    e0.record(main)
+    fork()
     for i in range(steps):
         if flush is not None:
-            flush.fill_(i & 255)
-        kev[i][0].record()
-        sv.solve_device(bin_s, bout_s, stream=torch.cuda.current_stream().cuda_stream)
-        kev[i][1].record()
-        if pipe:
-            pipe.submit(d_cost, d_status, d_iters)
-    if pipe:
-        pipe.finish()  # the timed region ends when the last gather has landed
-    e1.record()
+            with torch.cuda.stream(streams[i % K]):
+                flush.fill_(i & 255)
+        step(i)
+    join()  # the timed region ends when the last solve and the last gather have landed
+    e1.record(main)
     barrier(world)
-    launches = sv.launch_count - launches0
+    launches = sum(s_.launch_count for s_ in svs) - launches0
     clk = sampler.stop() if sampler else None
     my_ms = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     total_ms = reduce_max(my_ms, dev, world)
-    status, iters = d_status.cpu().numpy(), d_iters.cpu().numpy()
-    if pipe:  # the gathered table holds every rank's records; this rank's block must equal its own results
-        tab = pipe.table()
+    last = (steps - 1) % K
+    status, iters = outs[last][2].cpu().numpy(), outs[last][3].cpu().numpy()
+    for k in range(K):  # every handle solved the same batch: identical results
+        assert np.array_equal(outs[k][2].cpu().numpy(), status) or steps <= k
+    if pipes[last]:  # the gathered table holds every rank's records; this rank's block must equal its own results
+        tab = pipes[last].table()
         rank = int(os.environ.get("RANK", "0"))
         mine = tab[rank * B:(rank + 1) * B]
         assert np.array_equal(mine["status"], status) and np.array_equal(mine["iters"], iters), "gathered table is wrong"
+    for s_ in svs[1:]:
+        s_.close()
 
     # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed)
     pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
@@ -510,7 +549,7 @@ def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, wo
     info = sv.kernel_info
     kms = gather_scalars(kernel_ms, dev, world)
     sv.close()
-    return {"value": world * B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms,
+    return {"value": world * B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms, "inflight": K,
             "kernel_ms_per_rank": kms, "e2e_value": world * B * e2e_steps / e2e_s, "e2e_steps": e2e_steps,
             "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clk, "status": status, "iters": iters,
             "info": info, "params": params, "flushed": flush is not None, "steps": steps}
@@ -724,6 +763,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip config.fp64 / config.secondary")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight in the device-resident loop: 2 = consecutive steps alternate between two handles "
+                         "on two streams (hides the launch tail of the persistent kernel); 1 = one launch at a time")
     ap.add_argument("--option-bits", type=int, default=128,
                     help="pqp_params.reserved: 2 FP64 iterates, 4 no FP64 escalation, 8 state in tensor memory, "
                          "16 state in shared memory, 32 increment-form ADMM step, 64 textbook form, 128 cold-only "
@@ -772,7 +814,7 @@ def main():
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
     hb, workload, extras = make_workload(args, B, rank * B, device=local_rank)
     r = measure_cold(args, hb, args.option_bits, args.steps, args.warmup, args.e2e_steps or args.steps, local_rank,
-                     world, dev, gather=True, clocks=True)
+                     world, dev, gather=True, clocks=True, inflight=args.inflight)
     fp64, sec = (None, None) if args.no_secondary else secondary(args, rank, local_rank, world, dev, hb)
 
     if rank == 0:
@@ -801,6 +843,10 @@ def main():
                 "kernel_ms_per_rank": {"min": min(r["kernel_ms_per_rank"]), "max": max(r["kernel_ms_per_rank"]),
                                        "all": r["kernel_ms_per_rank"]},
                 "option_bits": args.option_bits,
+                "batches_in_flight": r["inflight"],
+                "step_overlap": ("consecutive steps run on two handles / two streams: the next batch takes over SMs as the "
+                                 "previous batch's persistent CTAs drain (each step is one full batch; `roofline.kernel_ms` is a "
+                                 "launch timed alone)") if r["inflight"] > 1 else "none: one launch at a time",
                 "warm_state": "not kept (cold-only handle, option bit 128: these batches are solved once)" if cold_only
                 else "kept per instance for pqp_resolve",
                 "admm_step": ("increment form (dx solve, carried row values)"

@@ -409,7 +409,6 @@ struct pqp_handle {
     bool fp64 = false;             // params.reserved bit 1: iterate in FP64
     bool escalate = true;          // params.reserved bit 2 clears it
     bool cold_only = false;        // params.reserved bit 128: no warm state is kept (pqp_resolve* is refused)
-    bool wt5 = false;              // params.reserved bit 256 (experiment): five warps per SM at n_max 128..255
     float stage_ms[PQP_NSTAGES] = {0, 0, 0, 0, 0};
     cudaEvent_t ev_st[4] = {};     // stage boundaries of the single-stream host call
     size_t smem_bytes64 = 0;
@@ -524,19 +523,6 @@ template <int C>
 cudaError_t launch_tmem_form(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count, bool incr) {
     return incr ? launch_tmem<C, true>(ka, s, sm_count) : launch_tmem<C, false>(ka, s, sm_count);
 }
-// Experiment (option bit 256, n_max 128..255, increment form): FIVE warps per SM instead of four. Each warp keeps
-// 8 of its 18 groups in 256 tensor-memory columns and 10 groups (40 KB) in shared memory; same code for every warp.
-struct Tmem5 {
-    static constexpr int C = 8, WT = 5;
-    typedef TmemStore<C, 256> Store;
-    static constexpr size_t kSmem = (size_t)WT * Store::kSpill * C * 32 * 4 * sizeof(float);
-};
-cudaError_t launch_tmem5(const pqp::KernelArgs &ka, cudaStream_t s, int sm_count) {
-    int ctas = (ka.batch + Tmem5::WT - 1) / Tmem5::WT;
-    if (ctas > sm_count) ctas = sm_count;
-    pqp_admm_kernel_tmem<8, 5, true><<<ctas, 32 * Tmem5::WT, Tmem5::kSmem, s>>>(ka);
-    return cudaGetLastError();
-}
 cudaError_t launch_tmem_chunk(int chunk, const pqp::KernelArgs &ka, cudaStream_t s, int sm_count, bool incr) {
     switch (chunk) {
         case 1: return launch_tmem_form<1>(ka, s, sm_count, incr);
@@ -646,8 +632,7 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
         int *ctr = h->d_counters + (h->counter_next++ % pqp_handle::kCounters);
         PQP_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(int), s));
         ka.work_counter = ctr;
-        if (h->wt5) PQP_CUDA(h, launch_tmem5(ka, s, h->sm_count));
-        else PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count, h->incr));
+        PQP_CUDA(h, launch_tmem_chunk(h->chunk, ka, s, h->sm_count, h->incr));
     } else {
         PQP_CUDA(h, launch_chunk<float>(h->chunk, ka, h->smem_bytes, s, h->incr));
     }
@@ -1035,9 +1020,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     // +15 % (one wave: its slowest instances need fewer iterations), n = 60 -3.5 %. Default: increment
     // form for n_max >= 64, textbook form below; bits 32 / 64 force one or the other.
     h->incr = !h->fp64 && ((params->reserved & 32) != 0 || ((params->reserved & 64) == 0 && h->chunk >= 4));
-    h->wt5 = h->use_tmem && h->incr && h->chunk == 8 && (params->reserved & 256) != 0;
     if (h->use_tmem) PQP_CREATE_CUDA(prepare_tmem_chunk(h->chunk));
-    if (h->wt5) PQP_CREATE_CUDA(cudaFuncSetAttribute(pqp_admm_kernel_tmem<8, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tmem5::kSmem));
     h->smem_bytes64 = pqp::smem_floats(h->chunk) * sizeof(double) + 16;
     int bps = 0;
     if (h->fp64) {
@@ -1046,7 +1029,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     } else {
         PQP_CREATE_CUDA(prepare_chunk<float>(h->chunk, h->smem_bytes, &bps, h->incr));
     }
-    h->warps_per_sm = h->use_tmem ? (h->wt5 ? 5 : tmem_warps(h->chunk)) : bps;
+    h->warps_per_sm = h->use_tmem ? tmem_warps(h->chunk) : bps;
     for (int i = 0; i < pqp_handle::kStreams; ++i) {
         PQP_CREATE_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
         PQP_CREATE_CUDA(cudaEventCreateWithFlags(&h->evs[i], cudaEventDisableTiming));
@@ -1074,7 +1057,7 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
         PQP_CREATE_CUDA(cudaMemset(h->d_warm, 0, B * pqp::warm_floats(c) * esz));
         PQP_CREATE_CUDA(cudaMalloc(&h->d_rho, B * esz));
     }
-    const size_t slots = h->use_tmem ? (size_t)h->sm_count * (h->wt5 ? 5 : tmem_warps(h->chunk)) : B;
+    const size_t slots = h->use_tmem ? (size_t)h->sm_count * tmem_warps(h->chunk) : B;
     PQP_CREATE_CUDA(cudaMalloc(&h->d_scal, slots * pqp::scal_floats(c) * esz));
     PQP_CREATE_CUDA(cudaMalloc(&h->d_dy, slots * pqp::dy_floats(c) * esz));
     for (int i = 0; i < 4; ++i) PQP_CREATE_CUDA(cudaEventCreate(&h->ev_st[i]));
@@ -1257,7 +1240,7 @@ int pqp_kernel_info(pqp_handle *h, int32_t *sm_count, int32_t *warps_per_sm, int
     if (warps_per_sm) *warps_per_sm = h->warps_per_sm;
     // tensor-memory policy: only the groups that do not fit the warp's columns live in shared memory
     if (smem_per_warp)
-        *smem_per_warp = h->use_tmem ? (int32_t)(h->wt5 ? Tmem5::kSmem / Tmem5::WT : tmem_spill_bytes(h->chunk)) : (int32_t)h->smem_bytes;
+        *smem_per_warp = h->use_tmem ? (int32_t)tmem_spill_bytes(h->chunk) : (int32_t)h->smem_bytes;
     return PQP_OK;
 }
 

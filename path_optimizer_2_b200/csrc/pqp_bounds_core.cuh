@@ -5,7 +5,6 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
-#include <string.h>
 
 #ifdef __CUDACC__
 #define PQB_HD __host__ __device__ __forceinline__
@@ -36,24 +35,6 @@ struct SplineView {
 // INTER_LINEAR lookup of the float "distance" layer - bilinear between the four cell centres
 // around the position (grid_map itself is not in the tree; at the outermost half cell it falls
 // back to the nearest cell, which the clamped weights below reproduce).
-// floor(v) for |v| < 2^31 without a conversion instruction: adding 1.5 * 2^52 leaves round-to-nearest(v - 0.5) in the
-// low mantissa bits (as an integer) and, after subtracting the constant again, as a double. F2I / I2F in FP64 run on
-// the XU pipe (16 lanes per clock and SM) and were 36 % of the bounds kernel's pipe time. At an exact integer v the
-// tie may round down by one cell; the bilinear interpolant is continuous across cell borders, so the looked-up value
-// is the same to rounding.
-PQB_HD int floor_to_int(double v, double &as_double) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const double t = (v - 0.5) + magic;
-    as_double = t - magic;
-#ifdef __CUDA_ARCH__
-    return __double2loint(t);
-#else
-    long long bits;
-    memcpy(&bits, &t, sizeof(bits));
-    return (int)(bits & 0xffffffffll);
-#endif
-}
-
 PQB_HD double map_distance(const MapView &m, double x, double y) {
     const double dx = x - m.cx, dy = y - m.cy;
     if (!(fabs(dx) < m.half_lx && fabs(dy) < m.half_ly)) return 0.0;
@@ -61,12 +42,10 @@ PQB_HD double map_distance(const MapView &m, double x, double y) {
     // cell borders, so a last-bit difference in fi, fj cannot change the value beyond rounding
     const double fi = (m.half_lx - dx) * m.inv_res - 0.5;
     const double fj = (m.half_ly - dy) * m.inv_res - 0.5;
-    double di, dj;
-    int i0 = floor_to_int(fi, di), j0 = floor_to_int(fj, dj);
-    // outermost half cells: clamp the base cell (the double copies follow; the bounds are loop invariants)
-    if (i0 < 0) { i0 = 0; di = 0.0; } else if (i0 > m.rows - 2) { i0 = m.rows - 2; di = (double)(m.rows - 2); }
-    if (j0 < 0) { j0 = 0; dj = 0.0; } else if (j0 > m.cols - 2) { j0 = m.cols - 2; dj = (double)(m.cols - 2); }
-    double ti = fi - di, tj = fj - dj;
+    int i0 = (int)floor(fi), j0 = (int)floor(fj);
+    i0 = i0 < 0 ? 0 : (i0 > m.rows - 2 ? m.rows - 2 : i0);
+    j0 = j0 < 0 ? 0 : (j0 > m.cols - 2 ? m.cols - 2 : j0);
+    double ti = fi - i0, tj = fj - j0;
     ti = ti < 0.0 ? 0.0 : (ti > 1.0 ? 1.0 : ti);
     tj = tj < 0.0 ? 0.0 : (tj > 1.0 ? 1.0 : tj);
     const float *r0 = m.dist + (size_t)i0 * m.cols + j0;
@@ -163,58 +142,6 @@ PQB_HD double constrain_angle(double a) {  // include/tools/tools.hpp:25-35 (rec
     return a;
 }
 
-// One side of a ray march: probe k sits at v_k = v_{k-1} + inc (accumulated, as the reference accumulates it) along
-// the direction (c, s) from (sx, sy). The probe POSITIONS do not depend on earlier probe results, only the stopping
-// index does - so the probes are issued four at a time (16 independent map gathers in flight per side) and scanned in
-// order afterwards (PQB_PROBE_CHUNK = 1 is the one-dependent-lookup-per-step march). Same positions, same comparisons, same results.
-#ifndef PQB_PROBE_CHUNK
-#define PQB_PROBE_CHUNK 4
-#endif
-struct MarchSide {
-    double c, s;      // direction
-    double v, inc;    // current accumulated offset, increment per probe
-    int left;         // probes still allowed
-    bool hit;         // a probe below the radius was found; v is the offset of that probe
-};
-PQB_HD void march_two(const MapView &m, double sx, double sy, double radius, MarchSide &A, MarchSide &B) {
-    while ((!A.hit && A.left > 0) || (!B.hit && B.left > 0)) {
-        constexpr int K = PQB_PROBE_CHUNK;
-        double va[K], vb[K], da[K], db[K];
-        const int na = (!A.hit && A.left > 0) ? (A.left < K ? A.left : K) : 0;
-        const int nb = (!B.hit && B.left > 0) ? (B.left < K ? B.left : K) : 0;
-        double v = A.v;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            v += A.inc;
-            va[k] = v;
-        }
-        v = B.v;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            v += B.inc;
-            vb[k] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            da[k] = k < na ? map_distance(m, sx + va[k] * A.c, sy + va[k] * A.s) : radius;
-            db[k] = k < nb ? map_distance(m, sx + vb[k] * B.c, sy + vb[k] * B.s) : radius;
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (k < na && !A.hit) {
-                A.v = va[k];
-                --A.left;
-                if (da[k] < radius) A.hit = true;
-            }
-            if (k < nb && !B.hit) {
-                B.v = vb[k];
-                --B.left;
-                if (db[k] < radius) B.hit = true;
-            }
-        }
-    }
-}
-
 // ReferencePathImpl::getClearanceWithDirectionStrict (reference_path_impl.cpp:232-312).
 // lb = right bound (<= 0 side), ub = left bound; {0, 0} when the state is too close to an
 // obstacle or the corridor is narrower than the car.
@@ -228,20 +155,34 @@ PQB_HD void clearance(const MapView &m, const Params &P, double sx, double sy, d
     double cl, sl, cr, sr;
     sincos(left_angle, &sl, &cl);
     sincos(right_angle, &sr, &cr);
-    // coarse marches, both sides together (:242-262): s += 0.3 until the clearance drops below the radius
-    MarchSide R = {cr, sr, 0.0, delta_s, n, false}, L = {cl, sl, 0.0, delta_s, n, false};
-    march_two(m, sx, sy, search_radius, R, L);
-    const double right_s = R.v, left_s = L.v;
+    double right_s = 0.0;
+    for (int j = 0; j != n; ++j) {
+        right_s += delta_s;
+        if (map_distance(m, sx + right_s * cr, sy + right_s * sr) < search_radius) break;
+    }
+    double left_s = 0.0;
+    for (int j = 0; j != n; ++j) {
+        left_s += delta_s;
+        if (map_distance(m, sx + left_s * cl, sy + left_s * sl) < search_radius) break;
+    }
     double right_bound = -(right_s - delta_s);
     double left_bound = left_s - delta_s;
-    // fine marches (:266-299): 0.05 m steps from one coarse step back; a hit steps back once (v -= inc, as written)
     const int fine = (int)(delta_s / smaller_ds);
-    MarchSide FL = {cl, sl, left_bound, smaller_ds, fine - 1, false};
-    // as the reference: the negative bound times the right-hand direction (:288-291)
-    MarchSide FR = {cr, sr, right_bound, -smaller_ds, fine - 1, false};
-    march_two(m, sx, sy, search_radius, FL, FR);
-    left_bound = FL.hit ? FL.v - smaller_ds : FL.v;
-    right_bound = FR.hit ? FR.v + smaller_ds : FR.v;
+    for (int i = 1; i != fine; ++i) {
+        left_bound += smaller_ds;
+        if (map_distance(m, sx + left_bound * cl, sy + left_bound * sl) < search_radius) {
+            left_bound -= smaller_ds;
+            break;
+        }
+    }
+    for (int i = 1; i != fine; ++i) {
+        right_bound -= smaller_ds;
+        // as the reference: the negative bound times the right-hand direction (:288-291)
+        if (map_distance(m, sx + right_bound * cr, sy + right_bound * sr) < search_radius) {
+            right_bound += smaller_ds;
+            break;
+        }
+    }
     const double diff_radius = P.car_width * 0.5 - search_radius;
     left_bound -= diff_radius;
     right_bound += diff_radius;

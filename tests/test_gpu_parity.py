@@ -368,20 +368,3 @@ def test_stage_times_of_a_single_path_call(solver_mod):
     assert abs(ms["h2d"] + ms["kernel"] + ms["d2h"] - ms["total"]) < 0.05 * ms["total"] + 1e-3
     sv.close()
 
-
-def test_five_warps_per_sm_variant_is_the_same_arithmetic(solver_mod):
-    """Option bit 256 (experiment): five warps per SM at n_max 128..255, each with 8 groups in tensor memory and 10 in
-    shared memory. Only where the state lives changes - results are bit-identical to the default four-warp kernel."""
-    hb = synthetic.make_batch(3, 777, 240, ragged=True)
-    out = []
-    for bits in (0, 256):
-        sv = solver_mod.PathQpSolver(abi.default_params(reserved=bits), n_max=240, batch_max=hb.batch)
-        r1 = sv.solve(hb)
-        r2 = sv.resolve(hb.with_linearisation(r1.sol))
-        out.append((r1, r2, sv.kernel_info["warps_per_sm"]))
-        sv.close()
-    assert out[0][2] == 4 and out[1][2] == 5
-    live = np.arange(240)[None, :] < hb.n[:, None]
-    for a, b in zip(out[0][:2], out[1][:2]):
-        assert np.array_equal(a.status, b.status) and np.array_equal(a.iters, b.iters) and np.array_equal(a.cost, b.cost)
-        assert np.array_equal(np.where(live[:, None, :], a.sol, 0.0), np.where(live[:, None, :], b.sol, 0.0))
