@@ -199,6 +199,21 @@ struct TmemStore {
         if (spilled(g)) { *sp(g, k) = v; return; }
         tmem_st4(col(g, k), v);
     }
+    // split form: issue the loads of N consecutive groups, wait later (wait_ld) together with other batches
+    template <int N> __device__ void ld4n_nowait(int g0, int k, float (&out)[4 * N]) const {
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+            float o[4];
+            if (spilled(g0 + g)) {
+                const float4 v = *sp(g0 + g, k);
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            } else {
+                tmem_ld4_nowait(col(g0 + g, k), o);
+            }
+            out[4 * g] = o[0]; out[4 * g + 1] = o[1]; out[4 * g + 2] = o[2]; out[4 * g + 3] = o[3];
+        }
+    }
+    __device__ void wait_ld() const { tmem_wait_ld(); }
     template <int N> __device__ void ld4n(int g0, int k, float (&out)[4 * N]) const {
 #pragma unroll
         for (int g = 0; g < N; ++g) {

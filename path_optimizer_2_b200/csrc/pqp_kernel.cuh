@@ -302,6 +302,9 @@ struct SmemStore {
             out[4 * g] = v.x; out[4 * g + 1] = v.y; out[4 * g + 2] = v.z; out[4 * g + 3] = v.w;
         }
     }
+    // split form: issue loads, then wait once for all of them (a no-op split under this policy)
+    template <int N> PQP_DEV void ld4n_nowait(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k, out); }
+    PQP_DEV void wait_ld() const {}
     PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
 };
 
@@ -1333,14 +1336,28 @@ struct QpWarp {
     // this / the next stage. The row values A x are carried in the FS slots (q.Sw) and advanced by
     // alpha A dx - never re-evaluated from the rounded x - so their error scales with |dx|.
     // Same outputs as update_stage; the rhs produced is again the increment-form one.
+    // the 11 groups of stage k (7 read-only + 4 read-write, consecutive group numbers) unpacked from one load batch
+    PQP_DEV void unpack_stage(const real (&t)[44], StageRO &q, Vec4 &x0, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
+        q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
+        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
+        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
+        q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
+        q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
+        q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
+        q.Sw[2] = t[24]; q.Sw[3] = t[25]; q.Sw[4] = t[26]; q.Sw[5] = t[27];
+        x0.x = t[28]; x0.y = t[29]; x0.z = t[30]; x0.w = t[31];
+        x1.x = t[32]; x1.y = t[33]; x1.z = t[34]; x1.w = t[35];
+        oy.x = t[36]; oy.y = t[37]; oy.z = t[38]; oy.w = t[39];
+        cz.x = t[40]; cz.y = t[41]; cz.z = t[42]; cz.w = t[43];
+    }
+
     template <bool kCheck>
     PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
-                                   real (&wo)[3], real (&bk)[3]) {
+                                   real (&wo)[3], real (&bk)[3], const real (&loaded)[44]) {
         const StagePred sp = pred(k);
         StageRO q;
-        load_ro(k, q);
         Vec4 x0, x1, oy, cz;
-        load_rw(k, x0, x1, oy, cz);
+        unpack_stage(loaded, q, x0, x1, oy, cz);
         real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
         real ax[6];
 #pragma unroll
@@ -1462,14 +1479,22 @@ struct QpWarp {
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
-            const Vec4 dw = V(GBV, k < C - 1 ? k + 1 : k);
+            // one load batch per stage: the next stage's dx and this stage's 11 groups are issued together and
+            // waited for once (three dependent load -> wait round trips per stage before; the tensor-memory
+            // access code held 24 % of the kernel's stall samples, profiles/r2/README.md)
+            real dwv[4], loaded[44];
+            store.template ld4n_nowait<1>(GBV, k < C - 1 ? k + 1 : k, dwv);
+            store.template ld4n_nowait<11>(GA0, k, loaded);
+            store.wait_ld();
             const real dt[3] = {dv.x, dv.y, dv.z};
             real dn[3];
-            dn[0] = (k == C - 1) ? dnb[0] : dw.x;
-            dn[1] = (k == C - 1) ? dnb[1] : dw.y;
-            dn[2] = (k == C - 1) ? dnb[2] : dw.z;
+            dn[0] = (k == C - 1) ? dnb[0] : dwv[0];
+            dn[1] = (k == C - 1) ? dnb[1] : dwv[1];
+            dn[2] = (k == C - 1) ? dnb[2] : dwv[2];
+            Vec4 dw;
+            dw.x = dwv[0]; dw.y = dwv[1]; dw.z = dwv[2]; dw.w = dwv[3];
             real wo[3], bk[3];
-            update_stage_incr<kCheck>(k, first, warm, dt, dn, wo, bk);
+            update_stage_incr<kCheck>(k, first, warm, dt, dn, wo, bk, loaded);
             Vec4 bv;
             bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
@@ -1523,8 +1548,20 @@ struct QpWarp {
                     const real kc = cl == 1 ? ke_eq : (cl == 0 ? ke_in : ke_lo);
                     ev[r] = (cl == 3 || !(Rr > real(0.0))) ? real(0.0) : Rr * xfast_rsqrt(Rr) * kc;
                 }
+                if (Incr) {
+                    // c d_j straight from the Ruiz D (the increment form keeps no S on chip; recomputing
+                    // S = sigma / (c d^2) only to take kd / sqrt(S) = c d cost a division and a rsqrt per entry:
+                    // 0.9 % of the instructions but 4.7 % of the stall samples, profiles/r2/README.md)
 #pragma unroll
-                for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(s_weight<real>(j, k, sp));
+                    for (int j = 0; j < 6; ++j) {
+                        const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
+                        const real d = G(gscal, GD + j, k);
+                        dv[j] = exists ? c * d : kd;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(s_weight<real>(j, k, sp));
+                }
             }
             const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
                         a12 = S(FA + 4, k), ds = S(FA + 5, k);
