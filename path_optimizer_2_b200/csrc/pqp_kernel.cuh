@@ -65,9 +65,8 @@ constexpr int kSolved = 0, kMaxIter = 1, kPrimInf = 2, kDualInf = 3, kSolvedInac
 // are rewritten every iteration), 7-11 are read-write, 12-17 are the factor.
 enum : int {
     FA = 0,     // 6: a00 a01 a10 a11 | a12 ds        (stage transition coefficients)
-    FES = 6,    // 2: 1/m_s0 1/m_s1 (closed-form elimination constants of the two slacks; an aligned pair)
-    FOB = 8,    // 3: outgoing-row bound (lower; upper = lower [+ end-row width]); rows 0, 1 an aligned pair
-    FEU = 11,   //    1/m_u (elimination constant of the control)
+    FE = 6,     // 3: 1/m_u 1/m_s0 | 1/m_s1            (closed-form elimination constants)
+    FOB = 9,    // 3: outgoing-row bound (lower; upper = lower [+ end-row width])
     FOR_ = 12,  // 3: outgoing-row weight R
     FKR = 15,   //    kappa-row weight R
     FCLO = 16, FCHI = 18,  // clearance-row bounds (2 each)
@@ -193,51 +192,6 @@ template <typename T> struct Vec4T;
 template <> struct Vec4T<float> { typedef float4 type; };
 struct alignas(32) pqp_double4 { double x, y, z, w; };
 template <> struct Vec4T<double> { typedef pqp_double4 type; };
-
-// ------------------------------------------------------------------ packed pairs
-// Two values that go through the same arithmetic (the two clearance rows of a stage, its outgoing rows 0 and 1).
-// In the FP32 kernel a pair is one 64-bit register and every operation one packed instruction (FFMA2 / FADD2 /
-// FMUL2 on sm_100a, half the issue slots of the scalar form; a splat operand folds into the instruction's scalar
-// broadcast); in FP64 and in the host emulation it is just two scalars.
-template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
-template <typename T> PQP_DEV Pair<T> pmake(T a, T b) { Pair<T> p; p.x = a; p.y = b; return p; }
-template <typename T> PQP_DEV Pair<T> psplat(T a) { return pmake(a, a); }
-template <typename T> PQP_DEV Pair<T> pfma(Pair<T> a, Pair<T> b, Pair<T> c) { return pmake(a.x * b.x + c.x, a.y * b.y + c.y); }
-template <typename T> PQP_DEV Pair<T> padd(Pair<T> a, Pair<T> b) { return pmake(a.x + b.x, a.y + b.y); }
-template <typename T> PQP_DEV Pair<T> psub(Pair<T> a, Pair<T> b) { return pmake(a.x - b.x, a.y - b.y); }
-template <typename T> PQP_DEV Pair<T> pmul(Pair<T> a, Pair<T> b) { return pmake(a.x * b.x, a.y * b.y); }
-#if !defined(PQP_EMU) && !defined(PQP_NO_F32X2)
-PQP_DEV unsigned long long pair_bits(Pair<float> a) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-    return r;
-}
-PQP_DEV Pair<float> pair_of(unsigned long long r) {
-    Pair<float> a;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
-    return a;
-}
-template <> PQP_DEV Pair<float> pfma<float>(Pair<float> a, Pair<float> b, Pair<float> c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pair_bits(a)), "l"(pair_bits(b)), "l"(pair_bits(c)));
-    return pair_of(d);
-}
-template <> PQP_DEV Pair<float> padd<float>(Pair<float> a, Pair<float> b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pair_bits(a)), "l"(pair_bits(b)));
-    return pair_of(d);
-}
-template <> PQP_DEV Pair<float> psub<float>(Pair<float> a, Pair<float> b) {
-    unsigned long long d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pair_bits(a)), "l"(pair_bits(b)));
-    return pair_of(d);
-}
-template <> PQP_DEV Pair<float> pmul<float>(Pair<float> a, Pair<float> b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pair_bits(a)), "l"(pair_bits(b)));
-    return pair_of(d);
-}
-#endif
 
 // ------------------------------------------------------------------ 3x3 helpers
 // symmetric 3x3 as [6] = (00,01,02,11,12,22); general 3x3 row-major [9]
@@ -695,7 +649,7 @@ struct QpWarp {
         const T pu = sp.mid ? T(w_dkappa) : T(0);
         const T mu = pu + s_weight<T>(3, k, sp) + R2 * ds * ds;
         const T miu = T(1) / mu;
-        if (store) S(FEU, k) = (real)miu;
+        if (store) S(FE + 0, k) = (real)miu;
         Rt[0] = S(FOR_ + 0, k);
         Rt[1] = S(FOR_ + 1, k);
         Rt[2] = R2 - (R2 * ds * miu) * R2 * ds;
@@ -714,7 +668,7 @@ struct QpWarp {
             const T Rcj = S(FCR + j, k);
             const T ms = ps + s_weight<T>(4 + j, k, sp) + Rcj;
             const T mis = T(1) / ms;
-            S(FES + j, k) = (real)mis;
+            S(FE + 1 + j, k) = (real)mis;
             Rc[j] = Rcj - (Rcj * mis) * Rcj;
         }
         const T h0 = sp.h0, h1 = sp.h1;
@@ -886,12 +840,13 @@ struct QpWarp {
     // -------------------------------------------------------------- solve  M_red x = b
     // b lives in shared memory (group GBV); overwritten by the solution. The factor of one
     // stage is 6 Vec4 (Dinv[6] G[9] F[9] packed contiguously).
+    // issues the loads only: the caller waits once (store.wait_ld) for this and whatever else it issued
     PQP_DEV void load_factor(int k, real (&f)[24], bool with_dinv) {
         if (with_dinv) {
-            store.template ld4n<6>(GF0, k, f);
+            store.template ld4n_nowait<6>(GF0, k, f);
         } else {
             real t[20];
-            store.template ld4n<5>(GF0 + 1, k, t);
+            store.template ld4n_nowait<5>(GF0 + 1, k, t);
 #pragma unroll
             for (int j = 0; j < 20; ++j) f[4 + j] = t[j];
         }
@@ -900,27 +855,38 @@ struct QpWarp {
     // (before the contribution of the right neighbour's interior), acc = sum_k F_k b_k
     PQP_DEV void forward_sweep(real (&bk)[3], real (&acc)[3]) {
         acc[0] = acc[1] = acc[2] = real(0.0);
-        Vec4 bv = V(GBV, 0);
-        bk[0] = bv.x; bk[1] = bv.y; bk[2] = bv.z;
-        real f[24], fnx[24];
-        if (C > 1) load_factor(0, f, false);
+        real f[24], fnx[24], bvv[4], nvv[4], nnx[4];
+        store.template ld4n_nowait<1>(GBV, 0, bvv);
+        if (C > 1) {
+            load_factor(0, f, false);
+            store.template ld4n_nowait<1>(GBV, 1, nvv);
+        }
+        store.wait_ld();
+        bk[0] = bvv[0]; bk[1] = bvv[1]; bk[2] = bvv[2];
         PQP_ROLL
         for (int k = 0; k < C - 1; ++k) {
-            if (k + 1 < C - 1) load_factor(k + 1, fnx, false);
+            // the next step's factor and rhs are in flight while this step computes; one wait at the end
+            if (k + 1 < C - 1) {
+                load_factor(k + 1, fnx, false);
+                store.template ld4n_nowait<1>(GBV, k + 2, nnx);
+            }
             const real *Gm = f + 6, *Fm = f + 15;
-            Vec4 nv = V(GBV, k + 1);
-            real bn[3] = {nv.x, nv.y, nv.z};
+            real bn[3] = {nvv[0], nvv[1], nvv[2]};
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 bn[r] -= Gm[3 * r] * bk[0] + Gm[3 * r + 1] * bk[1] + Gm[3 * r + 2] * bk[2];
                 acc[r] += Fm[3 * r] * bk[0] + Fm[3 * r + 1] * bk[1] + Fm[3 * r + 2] * bk[2];
             }
-            nv.x = bn[0]; nv.y = bn[1]; nv.z = bn[2];
+            Vec4 nv;
+            nv.x = bn[0]; nv.y = bn[1]; nv.z = bn[2]; nv.w = nvv[3];
             V(GBV, k + 1) = nv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) bk[r] = bn[r];
+            store.wait_ld();
 #pragma unroll
             for (int j = 4; j < 24; ++j) f[j] = fnx[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nvv[j] = nnx[j];
         }
     }
     PQP_DEV void solve() {
@@ -1003,11 +969,21 @@ struct QpWarp {
         }
         // backward sweep, same prefetch scheme (the rhs of the next stage rides along)
         Vec4 vcur;
-        if (C > 1) { load_factor(C - 2, f, true); vcur = V(GBV, C - 2); }
+        if (C > 1) {
+            real t4[4];
+            load_factor(C - 2, f, true);
+            store.template ld4n_nowait<1>(GBV, C - 2, t4);
+            store.wait_ld();
+            vcur.x = t4[0]; vcur.y = t4[1]; vcur.z = t4[2]; vcur.w = t4[3];
+        }
         PQP_ROLL
         for (int k = C - 2; k >= 0; --k) {
-            Vec4 vnx;
-            if (k > 0) { load_factor(k - 1, fnx, true); vnx = V(GBV, k - 1); }
+            // the next step's factor and rhs are in flight while this step computes; one wait at the end
+            real t4[4];
+            if (k > 0) {
+                load_factor(k - 1, fnx, true);
+                store.template ld4n_nowait<1>(GBV, k - 1, t4);
+            }
             const real *Di = f, *Gm = f + 6, *Fm = f + 15;
             const real b0 = vcur.x, b1 = vcur.y, b2 = vcur.z;
             real xk[3];
@@ -1021,9 +997,12 @@ struct QpWarp {
             V(GBV, k) = vcur;
 #pragma unroll
             for (int c = 0; c < 3; ++c) xn[c] = xk[c];
+            if (k > 0) {
+                store.wait_ld();
 #pragma unroll
-            for (int j = 0; j < 24; ++j) f[j] = fnx[j];
-            vcur = vnx;
+                for (int j = 0; j < 24; ++j) f[j] = fnx[j];
+                vcur.x = t4[0]; vcur.y = t4[1]; vcur.z = t4[2]; vcur.w = t4[3];
+            }
         }
     }
 
@@ -1035,8 +1014,8 @@ struct QpWarp {
         real t[28];
         store.template ld4n<7>(GA0, k, t);
         q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
-        q.a12 = t[4]; q.ds = t[5]; q.mis0 = t[6]; q.mis1 = t[7];
-        q.ob[0] = t[8]; q.ob[1] = t[9]; q.ob[2] = t[10]; q.miu = t[11];
+        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
+        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
         q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
         q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
         q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
@@ -1385,8 +1364,8 @@ struct QpWarp {
     // the 11 groups of stage k (7 read-only + 4 read-write, consecutive group numbers) unpacked from one load batch
     PQP_DEV void unpack_stage(const real (&t)[44], StageRO &q, Vec4 &x0, Vec4 &x1, Vec4 &oy, Vec4 &cz) {
         q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3];
-        q.a12 = t[4]; q.ds = t[5]; q.mis0 = t[6]; q.mis1 = t[7];
-        q.ob[0] = t[8]; q.ob[1] = t[9]; q.ob[2] = t[10]; q.miu = t[11];
+        q.a12 = t[4]; q.ds = t[5]; q.miu = t[6]; q.mis0 = t[7];
+        q.mis1 = t[8]; q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
         q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
         q.clo[0] = t[16]; q.clo[1] = t[17]; q.chi[0] = t[18]; q.chi[1] = t[19];
         q.Rc[0] = t[20]; q.Rc[1] = t[21]; q.Sw[0] = t[22]; q.Sw[1] = t[23];
@@ -1397,133 +1376,116 @@ struct QpWarp {
         cz.x = t[40]; cz.y = t[41]; cz.z = t[42]; cz.w = t[43];
     }
 
-    // The two clearance rows (rows 4, 5) and the outgoing rows 0, 1 of a stage go through the same arithmetic: they
-    // are carried as packed pairs (Pair<real>: one FFMA2 / FADD2 / FMUL2 per operation in the FP32 kernel). Their
-    // operands are aligned float pairs of the stage's groups (z, yhat, bounds, weights, carried row values), so no
-    // packing moves are needed.
     template <bool kCheck>
     PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
                                    real (&wo)[3], real (&bk)[3], const real (&loaded)[44]) {
-        typedef Pair<real> P2;
         const StagePred sp = pred(k);
         StageRO q;
         Vec4 x0, x1, oy, cz;
         unpack_stage(loaded, q, x0, x1, oy, cz);
-        const P2 al = psplat(alpha);
-        // ---------------- clearance rows (pair)
-        const P2 Zc = pmake(cz.x, cz.y), Yc = pmake(cz.z, cz.w), Rc = pmake(q.Rc[0], q.Rc[1]);
-        const P2 Mis = pmake(q.mis0, q.mis1), Hh = pmake((real)sp.h0, (real)sp.h1);
-        const P2 Pw = pmake(sp.act0 ? w_slack : real(0.0), sp.act1 ? w_slack : real(0.0));
-        const P2 Act = pmake(sp.act0 ? real(1.0) : real(0.0), sp.act1 ? real(1.0) : real(0.0));
-        P2 Axc = pmake(q.Sw[4], q.Sw[5]), Xs = pmake(x1.x, x1.y);
-        const P2 zmx_c = psub(Zc, Axc);                                      // z - A x
-        const P2 aux_s = psub(pmul(Rc, psub(zmx_c, Yc)), pmul(Pw, Xs));     // rhs of the eliminated slacks
-        const P2 base = pfma(Hh, psplat(dt[1]), psplat(dt[0]));              // dl + h dpsi
-        const P2 dS = pmul(Mis, psub(aux_s, pmul(Rc, base)));                // slack increments
-        const P2 dzc = pmul(pmul(al, padd(base, dS)), Act);                  // alpha A dx of the two rows
-        Xs = pfma(al, dS, Xs);
-        const P2 ztc = padd(Zc, psub(dzc, pmul(al, zmx_c)));
-        const P2 zhc = padd(ztc, Yc);
-        const P2 znc = pmake(clampf(zhc.x, q.clo[0], q.chi[0]), clampf(zhc.y, q.clo[1], q.chi[1]));
-        Axc = padd(Axc, dzc);
-        const P2 ync = psub(zhc, znc);
-        P2 Wc = pmul(Rc, psub(psub(znc, Axc), ync));
-        if (kCheck) {
-            const P2 dyc = pmul(Rc, psub(ztc, znc));
-            cert_row(4, k, dyc.x, q.clo[0], q.chi[0]);
-            cert_row(5, k, dyc.y, q.clo[1], q.chi[1]);
+        real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+        real ax[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ax[j] = q.Sw[j];
+        const real oyv[3] = {oy.x, oy.y, oy.z};
+        // z - A x of the outgoing rows at the old iterate
+        real zo_old[3], zmax[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (sp.last && r < 2) zo_old[r] = zend[r];
+            else zo_old[r] = first ? z0_out(warm, r, k) : q.ob[r];
+            zmax[r] = zo_old[r] - ax[r];
         }
-        // ---------------- outgoing rows 0, 1 (pair) and 2
-        const real zo2 = first ? z0_out(warm, 2, k) : q.ob[2];
-        P2 Zo = pmake(first ? z0_out(warm, 0, k) : q.ob[0], first ? z0_out(warm, 1, k) : q.ob[1]);
-        if (sp.last) Zo = pmake(zend[0], zend[1]);
-        const P2 Ob = pmake(q.ob[0], q.ob[1]), Ro = pmake(q.Ro[0], q.Ro[1]), Oy = pmake(oy.x, oy.y);
-        P2 Axo = pmake(q.Sw[0], q.Sw[1]);
-        const P2 zmx_o = psub(Zo, Axo);
-        const real zmx2 = zo2 - q.Sw[2];
-        // increment of the eliminated control (its rhs recomputed from the old iterates)
+        // increments of the eliminated variables (their rhs recomputed from the old iterates)
         const real pu = sp.mid ? w_dkappa : real(0.0);
-        const real aux_u = q.ds * (q.Ro[2] * (zmx2 - oy.z)) - pu * x0.w;
+        const real p0 = sp.act0 ? w_slack : real(0.0), p1 = sp.act1 ? w_slack : real(0.0);
+        const real aux_u = q.ds * (q.Ro[2] * (zmax[2] - oyv[2])) - pu * x[3];
+        const real aux_s0 = q.Rc[0] * ((cz.x - ax[4]) - cz.z) - p0 * x[4];
+        const real aux_s1 = q.Rc[1] * ((cz.y - ax[5]) - cz.w) - p1 * x[5];
         const real du = q.miu * (aux_u - q.Ro[2] * q.ds * (sp.a22 * dt[2] + sp.gn * dn[2]));
-        const P2 dzo = pmul(al, pmake(q.a00 * dt[0] + q.a01 * dt[1] + sp.gn * dn[0],
-                                      q.a10 * dt[0] + q.a11 * dt[1] + q.a12 * dt[2] + sp.gn * dn[1]));
-        const real dz2 = alpha * (sp.a22 * dt[2] + q.ds * du + sp.gn * dn[2]);
-        const real dz3 = sp.real ? alpha * dt[2] : real(0.0);
-        const P2 step = psub(dzo, pmul(al, zmx_o));
-        Axo = padd(Axo, dzo);
-        // equality rows: z+ = b, yhat+ = yhat + (z_old + step - b); z_old = b unless `first`
-        P2 Zn = Ob;
-        P2 Dy = padd(step, psub(Zo, Ob));
-        P2 Oyn = padd(Oy, Dy);
-        if (sp.last) {  // the last knot's rows 0, 1 are the end-state rows: boxes [b, b + endw]
-            const P2 zt = padd(Zo, step);
-            const P2 zh = padd(zt, Oy);
-            Zn = pmake(clampf(zh.x, q.ob[0], q.ob[0] + endw[0]), clampf(zh.y, q.ob[1], q.ob[1] + endw[1]));
-            zend[0] = Zn.x;
-            zend[1] = Zn.y;
-            Oyn = psub(zh, Zn);
-            Dy = psub(zt, Zn);
-        }
-        const P2 Wo = pmul(Ro, psub(psub(Zn, Axo), Oyn));
-        wo[0] = Wo.x;
-        wo[1] = Wo.y;
-        real ax2 = q.Sw[2], ax3 = q.Sw[3];
-        real oy2;
-        {
-            const real step2 = dz2 - alpha * zmx2;
-            ax2 += dz2;
-            const real dy2 = step2 + (zo2 - q.ob[2]);
-            oy2 = oy.z + dy2;
-            wo[2] = q.Ro[2] * ((q.ob[2] - ax2) - oy2);
-            if (kCheck) {
-                const P2 dyo = pmul(Ro, Dy);
-                cert_row(0, k, dyo.x, q.ob[0], sp.last ? q.ob[0] + endw[0] : q.ob[0]);
-                cert_row(1, k, dyo.y, q.ob[1], sp.last ? q.ob[1] + endw[1] : q.ob[1]);
-                cert_row(2, k, q.Ro[2] * dy2, q.ob[2], q.ob[2]);
+        const real ds0 = q.mis0 * (aux_s0 - q.Rc[0] * (dt[0] + sp.h0 * dt[1]));
+        const real ds1 = q.mis1 * (aux_s1 - q.Rc[1] * (dt[0] + sp.h1 * dt[1]));
+        // alpha A dx
+        real dz[6];
+        dz[0] = alpha * (q.a00 * dt[0] + q.a01 * dt[1] + sp.gn * dn[0]);
+        dz[1] = alpha * (q.a10 * dt[0] + q.a11 * dt[1] + q.a12 * dt[2] + sp.gn * dn[1]);
+        dz[2] = alpha * (sp.a22 * dt[2] + q.ds * du + sp.gn * dn[2]);
+        dz[3] = sp.real ? alpha * dt[2] : real(0.0);
+        dz[4] = sp.act0 ? alpha * (dt[0] + sp.h0 * dt[1] + ds0) : real(0.0);
+        dz[5] = sp.act1 ? alpha * (dt[0] + sp.h1 * dt[1] + ds1) : real(0.0);
+        // x+ = x + alpha dx
+        x[0] += alpha * dt[0]; x[1] += alpha * dt[1]; x[2] += alpha * dt[2];
+        x[3] += alpha * du; x[4] += alpha * ds0; x[5] += alpha * ds1;
+        x0.x = x[0]; x0.y = x[1]; x0.z = x[2]; x0.w = x[3]; x1.x = x[4]; x1.y = x[5];
+        // rows: zt = z_old + alpha (z~ - z_old) = z_old + (alpha A dx - alpha (z_old - A x));
+        // afterwards A x+ = A x + alpha A dx
+        real wk, wc[2], oyn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const real bnd = q.ob[r];
+            const real step = dz[r] - alpha * zmax[r];
+            const real axn = ax[r] + dz[r];
+            real zn, dyr;
+            if (sp.last && r < 2) {
+                const real zt = zo_old[r] + step;
+                const real zh = zt + oyv[r];
+                zn = clampf(zh, bnd, bnd + endw[r]);
+                zend[r] = zn;
+                oyn[r] = zh - zn;
+                dyr = zt - zn;
+            } else {
+                // equality row: z+ = b, yhat+ = yhat + (z_old + step - b); z_old = b unless `first`
+                zn = bnd;
+                dyr = step + (zo_old[r] - bnd);
+                oyn[r] = oyv[r] + dyr;
             }
+            wo[r] = q.Ro[r] * ((zn - axn) - oyn[r]);
+            ax[r] = axn;
+            if (kCheck) cert_row(r, k, q.Ro[r] * dyr, bnd, (sp.last && r < 2) ? bnd + endw[r] : bnd);
         }
-        // ---------------- kappa box row
-        real wk;
+        oy.x = oyn[0]; oy.y = oyn[1]; oy.z = oyn[2];
         {
-            const real zt = x1.z + (dz3 - alpha * (x1.z - ax3));
+            const real zt = x1.z + (dz[3] - alpha * (x1.z - ax[3]));
             const real zh = zt + x1.w;
             const real zn = clampf(zh, -kmax, kmax);
-            ax3 += dz3;
+            ax[3] += dz[3];
             x1.z = zn;
             x1.w = zh - zn;
-            wk = q.Rk * ((zn - ax3) - x1.w);
+            wk = q.Rk * ((zn - ax[3]) - x1.w);
             if (kCheck) cert_row(3, k, q.Rk * (zt - zn), -kmax, kmax);
         }
-        // ---------------- x+ = x + alpha dx
-        const P2 X01 = pfma(al, pmake(dt[0], dt[1]), pmake(x0.x, x0.y));
-        x0.x = X01.x; x0.y = X01.y;
-        x0.z += alpha * dt[2];
-        x0.w += alpha * du;
-        x1.x = Xs.x; x1.y = Xs.y;
-        oy.x = Oyn.x; oy.y = Oyn.y; oy.z = oy2;
-        cz.x = znc.x; cz.y = znc.y; cz.z = ync.x; cz.w = ync.y;
+        {
+            const real zt = cz.x + (dz[4] - alpha * (cz.x - ax[4]));
+            const real zh = zt + cz.z;
+            const real zn = clampf(zh, q.clo[0], q.chi[0]);
+            ax[4] += dz[4];
+            cz.x = zn;
+            cz.z = zh - zn;
+            wc[0] = q.Rc[0] * ((zn - ax[4]) - cz.z);
+            if (kCheck) cert_row(4, k, q.Rc[0] * (zt - zn), q.clo[0], q.chi[0]);
+        }
+        {
+            const real zt = cz.y + (dz[5] - alpha * (cz.y - ax[5]));
+            const real zh = zt + cz.w;
+            const real zn = clampf(zh, q.clo[1], q.chi[1]);
+            ax[5] += dz[5];
+            cz.y = zn;
+            cz.w = zh - zn;
+            wc[1] = q.Rc[1] * ((zn - ax[5]) - cz.w);
+            if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
+        }
         V(GX0, k) = x0;
         V(GX1, k) = x1;
         V(GOY, k) = oy;
         V(GCZ, k) = cz;
         {
             Vec4 g5, g6;
-            g5.x = q.Rc[0]; g5.y = q.Rc[1]; g5.z = Axo.x; g5.w = Axo.y;
-            g6.x = ax2; g6.y = ax3; g6.z = Axc.x; g6.w = Axc.y;
+            g5.x = q.Rc[0]; g5.y = q.Rc[1]; g5.z = ax[0]; g5.w = ax[1];
+            g6.x = ax[2]; g6.y = ax[3]; g6.z = ax[4]; g6.w = ax[5];
             V(GR5, k) = g5;
             V(GS6, k) = g6;
         }
-        // ---------------- stage-local part of the next rhs (local_rhs_incr, the slack pair packed)
-        {
-            const real pl = sp.real ? w_l : real(0.0), pk = sp.real ? w_kappa : real(0.0);
-            const real rhs_u = q.ds * wo[2] - pu * x0.w;
-            wo[2] -= (q.Ro[2] * q.ds * q.miu) * rhs_u;
-            const P2 rhs_s = psub(Wc, pmul(Pw, Xs));
-            Wc = psub(Wc, pmul(pmul(Rc, Mis), rhs_s));
-            bk[0] = q.a00 * wo[0] + q.a10 * wo[1] + Wc.x + Wc.y - pl * x0.x;
-            bk[1] = q.a01 * wo[0] + q.a11 * wo[1] + sp.h0 * Wc.x + sp.h1 * Wc.y;
-            bk[2] = q.a12 * wo[1] + sp.a22 * wo[2] + wk - pk * x0.z;
-        }
+        local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
 
     template <bool kCheck>
@@ -1596,18 +1558,27 @@ struct QpWarp {
         }
         const real ke_in = xsqrt(c / rho), ke_eq = xsqrt(c / (real(kRhoEqOverIneq) * rho)),
                    ke_lo = xsqrt(c / real(kRhoMin)), kd = xsqrt(sigma * c);
+        real yprev[3] = {yLb[0], yLb[1], yLb[2]};  // y of the previous stage's outgoing rows
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
+            // the stage's 11 groups and the next stage's x in ONE load batch (one wait), as in the update
+            real loaded[44], xn4[4];
+            store.template ld4n_nowait<11>(GA0, k, loaded);
+            store.template ld4n_nowait<1>(GX0, k < C - 1 ? k + 1 : k, xn4);
+            store.wait_ld();
+            StageRO q;
+            Vec4 x0, x1, oy, cz;
+            unpack_stage(loaded, q, x0, x1, oy, cz);
             // Ruiz scalings recovered from the weights held on chip: R_r = base_r e_r^2 / c and
-            // S_j = sigma / (c d_j^2)  (no global loads, no divisions in the check path)
+            // S_j = sigma / (c d_j^2)  (no divisions in the check path)
             real ev[6], dv[6];
             {
-                const int cls = cls_of(k);
+                const int cls = (int)oy.w;
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
                     const int cl = (cls >> (2 * r)) & 3;
-                    const real Rr = (r < 3) ? S(FOR_ + r, k) : (r == 3 ? S(FKR, k) : S(FCR + r - 4, k));
+                    const real Rr = (r < 3) ? q.Ro[r] : (r == 3 ? q.Rk : q.Rc[r - 4]);
                     const real kc = cl == 1 ? ke_eq : (cl == 0 ? ke_in : ke_lo);
                     ev[r] = (cl == 3 || !(Rr > real(0.0))) ? real(0.0) : Rr * xfast_rsqrt(Rr) * kc;
                 }
@@ -1623,21 +1594,15 @@ struct QpWarp {
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(s_weight<real>(j, k, sp));
+                    for (int j = 0; j < 6; ++j) dv[j] = kd * xfast_rsqrt(q.Sw[j]);  // textbook form: Sw holds S
                 }
             }
-            const real a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
-                        a12 = S(FA + 4, k), ds = S(FA + 5, k);
-            const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
-                        s0 = S(FX + 4, k), s1 = S(FX + 5, k);
-            const int kn1 = k < C - 1 ? k + 1 : k;
-            const real ln = (k < C - 1) ? (real)S(FX + 0, kn1) : xNb[0];
-            const real pn = (k < C - 1) ? (real)S(FX + 1, kn1) : xNb[1];
-            const real kn = (k < C - 1) ? (real)S(FX + 2, kn1) : xNb[2];
-            const int kp1 = k > 0 ? k - 1 : 0;
-            real yl[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) yl[r] = (k > 0) ? (real)S(FOR_ + r, kp1) * (real)S(FOY + r, kp1) : yLb[r];
+            const real a00 = q.a00, a01 = q.a01, a10 = q.a10, a11 = q.a11, a12 = q.a12, ds = q.ds;
+            const real l = x0.x, ps = x0.y, kp = x0.z, u = x0.w, s0 = x1.x, s1 = x1.y;
+            const real ln = (k < C - 1) ? xn4[0] : xNb[0];
+            const real pn = (k < C - 1) ? xn4[1] : xNb[1];
+            const real kn = (k < C - 1) ? xn4[2] : xNb[2];
+            const real yl[3] = {yprev[0], yprev[1], yprev[2]};
             real ax[6], z[6], y[6];
             ax[0] = a00 * l + a01 * ps + sp.gn * ln;
             ax[1] = a10 * l + a11 * ps + a12 * kp + sp.gn * pn;
@@ -1645,15 +1610,16 @@ struct QpWarp {
             ax[3] = sp.real ? kp : real(0.0);
             ax[4] = sp.act0 ? (l + sp.h0 * ps + s0) : real(0.0);
             ax[5] = sp.act1 ? (l + sp.h1 * ps + s1) : real(0.0);
+            const real oyv[3] = {oy.x, oy.y, oy.z};
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const real obr = S(FOB + r, k);
-                z[r] = (sp.last && r < 2) ? zend[r] : obr;
-                y[r] = (real)S(FOR_ + r, k) * (real)S(FOY + r, k);
+                z[r] = (sp.last && r < 2) ? zend[r] : q.ob[r];
+                y[r] = q.Ro[r] * oyv[r];
+                yprev[r] = y[r];
             }
-            z[3] = S(FKZ, k); y[3] = S(FKR, k) * S(FKY, k);
-            z[4] = S(FCZ + 0, k); y[4] = S(FCR + 0, k) * S(FCY + 0, k);
-            z[5] = S(FCZ + 1, k); y[5] = S(FCR + 1, k) * S(FCY + 1, k);
+            z[3] = x1.z; y[3] = q.Rk * x1.w;
+            z[4] = cz.x; y[4] = q.Rc[0] * cz.z;
+            z[5] = cz.y; y[5] = q.Rc[1] * cz.w;
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const real e = ev[r];
