@@ -963,8 +963,8 @@ struct QpWarp {
             xn[r] = xs[r];
         }
         {
-            Vec4 v = V(GBV, C - 1);
-            v.x = xs[0]; v.y = xs[1]; v.z = xs[2];
+            Vec4 v;  // the fourth component of the solve vector's group is padding
+            v.x = xs[0]; v.y = xs[1]; v.z = xs[2]; v.w = real(0.0);
             V(GBV, C - 1) = v;
         }
         // backward sweep, same prefetch scheme (the rhs of the next stage rides along)
@@ -1490,17 +1490,14 @@ struct QpWarp {
 
     template <bool kCheck>
     PQP_DEV void admm_update_incr(bool first, bool warm) {
+        Vec4 dv = V(GBV, 0);
         real dnb[3];
-        {
-            const Vec4 v = V(GBV, 0);
-            dnb[0] = shfl_down(v.x, 1, lane);
-            dnb[1] = shfl_down(v.y, 1, lane);
-            dnb[2] = shfl_down(v.z, 1, lane);
-            if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = real(0.0); }
-        }
+        dnb[0] = shfl_down(dv.x, 1, lane);
+        dnb[1] = shfl_down(dv.y, 1, lane);
+        dnb[2] = shfl_down(dv.z, 1, lane);
+        if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = real(0.0); }
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
-        Vec4 dv = V(GBV, 0);
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
