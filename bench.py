@@ -493,7 +493,7 @@ def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, wo
         svs[0].solve_device(bin_s, outs[0][4], stream=main.cuda_stream)
         kev[i][1].record(main)
     barrier(world)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_ms = float(np.median([a.elapsed_time(b) for a, b in kev]))
     sampler = ClockSampler(local_rank) if clocks else None
     if sampler:
         sampler.start()
