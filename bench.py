@@ -63,6 +63,7 @@ def make_workload(args, batch, first, device=None):
             extras = bounds_stage(args, dmap, lines, device)
             bnd, nv = extras.pop("bounds"), extras.pop("n_valid")
         hb = lines.to_host_batch(bnd, nv)
+        extras["_lines"], extras["_dmap"] = lines, dmap  # for the front-end stages (popped before the line is printed)
         return hb, ("BASELINE configs[1] per GPU: batch %d paths x %d knots through ONE shared obstacle map "
                     "(gridmap.png distance layer; clearance bounds = updateBoundsImproved, "
                     "reference_path_impl.cpp:177-312), cold BaseSolver::solve (configs[0] is batch 1 of the "
@@ -713,6 +714,82 @@ def dropin_single_path(n=120, plans=200):
             "last_call_stage_ms": sg}
 
 
+def front_end_stages(lines, dmap, device):
+    """SURVEY.md §8 rows f-4 and f-3 on the GPU for the shared-map batch: lattice DP search over the smoothed
+    references, then the post-smooth QP on the DP's corridor, and the tension-smoother QP on the references resampled
+    at 1 m - each one launch through its C ABI (host-pointer call; the kernel time is the CUDA-event time between the
+    copies). Checked against the oracles on a sample."""
+    from oracle import bounds_oracle as bo, dp_oracle, smoother_oracle
+    from path_optimizer_2_b200 import bounds, dp, smoother
+    B = lines.batch
+    length = np.array([lines.spline_rows(b)[0, lines.k[b] - 1] + 3.0 for b in range(B)])
+    start = np.zeros((B, 3))
+    rng = np.random.default_rng(11)
+    for b in range(B):
+        sp = bo.Spline2(lines.spline_rows(b))
+        x, y = dp_oracle._xy(sp, 0.5)
+        h = dp_oracle.heading(sp, 0.5)
+        off = rng.uniform(-1.0, 1.0)
+        start[b] = x - off * np.sin(h), y + off * np.cos(h), h
+    pbn = bounds.PathBounds(dmap.dist, dmap.res, device=device)
+    ds = dp.DpSearch(pbn, layers_max=64, batch_max=B)
+    for _ in range(2):
+        r = ds.search(lines.spline, lines.k, length, start, tables=False)
+    dp_ms = ds.last_kernel_ms
+    ok = r.status == dp.DP_OK
+    for b in np.nonzero(ok)[0][:8]:
+        o = dp_oracle.graph_search_dp(dmap.dist, dmap.res, lines.spline_rows(b), length[b], start[b])
+        assert np.array_equal(r.chosen[b, :r.n_out[b]], o["chosen"]), "DP kernel and oracle chose different nodes"
+    out = {"dp_search": {"kernel": "dp_search_kernel", "paths": int(B), "ok_fraction": float(ok.mean()),
+                         "mean_layers": float(r.n_layers.mean()), "ms_per_batch": dp_ms, "paths_per_s": B / (dp_ms * 1e-3),
+                         "algorithmic_bytes": int(lines.spline.nbytes + 3 * 8 * B + r.n_out.sum() * 28 + 40 * B)}}
+    idx = np.nonzero(ok & (r.n_out >= 4))[0]
+    sm = smoother.Smoother(p_max=64, batch_max=B, device=device)
+    ls = [r.layer_s[b, :r.n_out[b]] for b in idx]
+    lo = [r.lower[b, :r.n_out[b]] for b in idx]
+    up = [r.upper[b, :r.n_out[b]] for b in idx]
+    vl = r.vehicle_l[idx]
+    for _ in range(2):
+        pr = sm.post(ls, lo, up, vl)
+    post_ms = sm.last_kernel_ms
+    for j in range(min(4, len(idx))):
+        okp, off, g = smoother_oracle.post_smooth(ls[j], lo[j], up[j], vl[j])
+        assert pr["status"][j] == g.status and pr["iters"][j] == g.iters and np.allclose(pr["offsets"][j, :len(off)], off, atol=1e-6)
+    out["post_smooth_qp"] = {"kernel": "smoother_kernel (postSmooth QP)", "qps": int(len(idx)), "ms_per_batch": post_ms,
+                             "qps_per_s": len(idx) / (post_ms * 1e-3), "mean_iters": float(pr["iters"].mean()),
+                             "solved_fraction": float(np.mean(pr["status"] == abi.PQP_SOLVED)),
+                             "algorithmic_bytes": int(sum(len(v) for v in ls) * 32 + 16 * len(idx))}
+    sm.close()
+    # tension smoother: the references resampled at 1 m (segmentRawReference) with a little noise as the raw input
+    xs, ys, an, ks, ss = [], [], [], [], []
+    for b in range(B):
+        sp = bo.Spline2(lines.spline_rows(b))
+        s = np.arange(0.0, lines.spline_rows(b)[0, lines.k[b] - 1], 1.0)
+        x, dx, ddx = sp.x(s)
+        y, dy, ddy = sp.y(s)
+        xs.append(x + rng.normal(0, 0.03, len(s)))
+        ys.append(y + rng.normal(0, 0.03, len(s)))
+        an.append(np.arctan2(dy, dx))
+        ks.append((dx * ddy - dy * ddx) / np.power(dx * dx + dy * dy, 1.5))
+        ss.append(s)
+    pmax = max(len(v) for v in xs)
+    sm = smoother.Smoother(p_max=max(pmax, 8), batch_max=B, device=device)
+    for _ in range(2):
+        tr = sm.tension(xs, ys, an, ks, ss)
+    t_ms = sm.last_kernel_ms
+    for j in range(3):
+        okt, rx, ry, rs, g = smoother_oracle.osqp_smooth(xs[j], ys[j], an[j], ks[j], ss[j])
+        assert tr["status"][j] == g.status and tr["iters"][j] == g.iters and np.allclose(tr["x"][j, :len(rx)], rx, atol=1e-6)
+    out["tension_smoother_qp"] = {"kernel": "smoother_kernel (TensionSmoother2 QP)", "qps": int(B), "mean_points": float(np.mean([len(v) for v in xs])),
+                                  "ms_per_batch": t_ms, "qps_per_s": B / (t_ms * 1e-3), "mean_iters": float(tr["iters"].mean()),
+                                  "solved_fraction": float(np.mean(tr["status"] == abi.PQP_SOLVED)),
+                                  "algorithmic_bytes": int(sum(len(v) for v in xs) * 64 + 12 * B)}
+    sm.close()
+    ds.close()
+    pbn.close()
+    return out
+
+
 def secondary(args, rank, local_rank, world, dev, hb_primary):
     """The other BASELINE configs and the FP64 instantiation, measured in the same run (short loops)."""
     sec = {}
@@ -735,12 +812,17 @@ def secondary(args, rank, local_rank, world, dev, hb_primary):
         a1 = argparse.Namespace(**vars(args))
         a1.workload, a1.batch, a1.n = "sharedmap", 1024, 120
         hb1, wl1, ex1 = make_workload(a1, 1024, 0, device=local_rank)
+        lines1, dmap1 = ex1.pop("_lines"), ex1.pop("_dmap")
         r1 = measure_cold(a1, hb1, args.option_bits, min(args.steps, 10), 3, 5, local_rank, world, dev, gather=False)
         sec["configs[1]"] = {"workload": wl1, "value": r1["value"], "unit": UNIT, "e2e": r1["e2e_value"],
                              "ms_per_step": r1["ms_per_step"], "kernel_ms": r1["kernel_ms"],
                              "mean_admm_iters": float(np.mean(r1["iters"])),
                              "solved_fraction": float(np.mean(r1["status"] == abi.PQP_SOLVED)),
                              "l2_policy": "L2 flushed between timed steps", **ex1}
+        try:
+            sec["front_end"] = front_end_stages(lines1, dmap1, local_rank)
+        except Exception as e:  # report rather than lose the bench line
+            sec["front_end"] = {"error": repr(e)}
         if rank == 0:
             try:
                 sec["configs[0]"] = dropin_single_path()
@@ -813,6 +895,8 @@ def main():
     B, n = args.batch, args.n
     # this rank's shard of the global batch (weak scaling: B instances per GPU)
     hb, workload, extras = make_workload(args, B, rank * B, device=local_rank)
+    extras.pop("_lines", None)
+    extras.pop("_dmap", None)
     r = measure_cold(args, hb, args.option_bits, args.steps, args.warmup, args.e2e_steps or args.steps, local_rank,
                      world, dev, gather=True, clocks=True, inflight=args.inflight)
     fp64, sec = (None, None) if args.no_secondary else secondary(args, rank, local_rank, world, dev, hb)
