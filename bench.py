@@ -287,11 +287,13 @@ def pick_threads(params, hb, cores):
     from oracle import oracle
     cand = sorted({t for t in (1, 8, 16, 32, 64, 96, 128, 192, 256, cores["effective"], cores["affinity"])
                    if 1 <= t <= cores["affinity"]})
-    sub = hb.slice(0, min(hb.batch, 512))
+    sub = hb.slice(0, min(hb.batch, 2048))
     oracle.solve_batch(params, sub.slice(0, min(64, sub.batch)), nthreads=cand[-1])  # warm the thread pool
     sweep = {}
     for t in cand:
-        s = sub.slice(0, min(sub.batch, max(32, 4 * t)))
+        # long enough (a few hundred ms) to run into the cgroup's CPU quota: a short burst may use more cores than
+        # the container is entitled to and would pick a thread count that the full batch cannot sustain
+        s = sub.slice(0, min(sub.batch, 64 if t == 1 else 2048))
         _, secs = oracle.solve_batch(params, s, nthreads=t, mode=0, dense_assembly=False)
         sweep[t] = s.batch / secs
     multi = {t: v for t, v in sweep.items() if t > 1} or sweep

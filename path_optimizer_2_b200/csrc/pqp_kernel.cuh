@@ -433,15 +433,16 @@ struct QpWarp {
                     chi[1] = (real)hi;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 6; ++j) S(FA + j, k) = a[j];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) S(FOB + r, k) = ob[r];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                S(FCLO + j, k) = clo[j];
-                S(FCHI + j, k) = chi[j];
-            }
+            // whole groups (the elimination constants that share groups 1 and 2 are written by the factorisation)
+            Vec4 v;
+            v.x = a[0]; v.y = a[1]; v.z = a[2]; v.w = a[3];
+            store.st4(GA0, k, v);
+            v.x = a[4]; v.y = a[5]; v.z = real(0.0); v.w = real(0.0);
+            store.st4(GA1, k, v);
+            v.x = real(0.0); v.y = ob[0]; v.z = ob[1]; v.w = ob[2];
+            store.st4(GB2, k, v);
+            v.x = clo[0]; v.y = clo[1]; v.z = chi[0]; v.w = chi[1];
+            store.st4(GC4, k, v);
         }
     }
 
@@ -449,77 +450,113 @@ struct QpWarp {
     // OSQP scale_data on the structured matrix. d and e ping-pong between
     // two halves of the (still unused) factor region; D, E end up in global scratch, row
     // weights R / classes / S in shared memory.
-    PQP_DEV void scale_and_classify() {
-        const DevParams &P = ka.prm;
+    // One Ruiz pass: reads D, E from the three groups GF0 + 3 CUR .. (d0 d1 d2 d3 | d4 d5 e0 e1 | e2 e3 e4 e5), writes
+    // the other half. Whole groups, one load batch per stage (the stage's a-coefficients, its D / E, the next stage's D)
+    // and three group stores: the first version read and wrote the 24 values one 32-bit tensor-memory access at a
+    // time, each with its own wait (~2400 dependent round trips per solve, profiles/r2/README.md).
+    template <int CUR>
+    PQP_DEV void ruiz_pass(real c, real &psum) {
+        constexpr int G0 = GF0 + 3 * CUR, G1 = GF0 + 3 * (1 - CUR);
+        // neighbour lanes' boundary values: e of the left lane's last outgoing rows, d of the right lane's first x
+        real eLb[3], dRb[3];
+        {
+            real t[8], u[4];
+            store.template ld4n_nowait<2>(G0 + 1, C - 1, t);
+            store.template ld4n_nowait<1>(G0, 0, u);
+            store.wait_ld();
+            const real el[3] = {t[2], t[3], t[4]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                eLb[r] = shfl_up(el[r], 1, lane);
+                dRb[r] = shfl_down(u[r], 1, lane);
+                if (lane == 0) eLb[r] = real(0.0);
+                if (lane == 31) dRb[r] = real(0.0);
+            }
+        }
+        real eL[3] = {eLb[0], eLb[1], eLb[2]};
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
+            const StagePred sp = pred(k);
+            real ta[8], td[12], tn[4];
+            store.template ld4n_nowait<2>(GA0, k, ta);
+            store.template ld4n_nowait<3>(G0, k, td);
+            store.template ld4n_nowait<1>(G0, k < C - 1 ? k + 1 : k, tn);
+            store.wait_ld();
+            const real a00 = xabs(ta[0]), a01 = xabs(ta[1]), a10 = xabs(ta[2]), a11 = xabs(ta[3]), a12 = xabs(ta[4]),
+                       ds = xabs(ta[5]);
+            const real gn = xabs(sp.gn), h0 = xabs(sp.h0), h1 = xabs(sp.h1);
+            real dk[6], ek[6], dR[3];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) S(FT + j, k) = real(1.0);
+            for (int j = 0; j < 6; ++j) { dk[j] = td[j]; ek[j] = td[6 + j]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) dR[r] = (k < C - 1) ? tn[r] : dRb[r];
+            // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
+            const real hasL = sp.real ? real(1.0) : real(0.0);
+            const real ec0 = sp.act0 ? ek[4] : real(0.0), ec1 = sp.act1 ? ek[5] : real(0.0);
+            const real ekap = sp.real ? ek[3] : real(0.0);
+            real cn[6];
+            cn[0] = dk[0] * xmax(xmax(a00 * ek[0], a10 * ek[1]), xmax(hasL * eL[0], xmax(ec0, ec1)));
+            cn[1] = dk[1] * xmax(xmax(a01 * ek[0], a11 * ek[1]), xmax(hasL * eL[1], xmax(h0 * ec0, h1 * ec1)));
+            cn[2] = dk[2] * xmax(xmax(a12 * ek[1], sp.a22 * ek[2]), xmax(hasL * eL[2], ekap));
+            cn[3] = dk[3] * ds * ek[2];
+            cn[4] = dk[4] * ec0;
+            cn[5] = dk[5] * ec1;
+            const real pw[6] = {sp.real ? w_l : real(0.0), real(0.0), sp.real ? w_kappa : real(0.0),
+                                 sp.mid ? w_dkappa : real(0.0), sp.act0 ? w_slack : real(0.0),
+                                 sp.act1 ? w_slack : real(0.0)};
+#pragma unroll
+            for (int j = 0; j < 6; ++j) cn[j] = xmax(cn[j], c * dk[j] * dk[j] * pw[j]);
+            real rn[6];
+            rn[0] = ek[0] * xmax(xmax(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
+            rn[1] = ek[1] * xmax(xmax(a10 * dk[0], a11 * dk[1]), xmax(a12 * dk[2], gn * dR[1]));
+            rn[2] = ek[2] * xmax(xmax(sp.a22 * dk[2], ds * dk[3]), gn * dR[2]);
+            rn[3] = ekap * dk[2];
+            rn[4] = ec0 * xmax(xmax(dk[0], h0 * dk[1]), dk[4]);
+            rn[5] = ec1 * xmax(xmax(dk[0], h1 * dk[1]), dk[5]);
+            real dn[6], en[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                // 1/sqrt as one MUFU.RSQ in FP32 (2 ulp): the Ruiz factors are only required to be
+                // positive - any D, E give an equivalent problem - and 960 sqrt + divide pairs per
+                // solve were 7 % of the kernel's stall samples; the FP64 instantiation stays exact
+                dn[j] = dk[j] * xfast_rsqrt(limit_scaling(cn[j]));
+                en[j] = ek[j] * xfast_rsqrt(limit_scaling(rn[j]));
+                psum += dn[j] * dn[j] * pw[j];
+            }
+            Vec4 v;
+            v.x = dn[0]; v.y = dn[1]; v.z = dn[2]; v.w = dn[3];
+            store.st4(G1, k, v);
+            v.x = dn[4]; v.y = dn[5]; v.z = en[0]; v.w = en[1];
+            store.st4(G1 + 1, k, v);
+            v.x = en[2]; v.y = en[3]; v.z = en[4]; v.w = en[5];
+            store.st4(G1 + 2, k, v);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) eL[r] = ek[r];  // this stage's outgoing-row e is the next stage's "left" e
+        }
+        store.fence();
+    }
+
+    PQP_DEV void scale_and_classify() {
+        const DevParams &P = ka.prm;
+        {
+            Vec4 one;
+            one.x = one.y = one.z = one.w = real(1.0);
+            PQP_ROLL
+            for (int k = 0; k < C; ++k) {
+                store.st4(GF0, k, one);
+                store.st4(GF0 + 1, k, one);
+                store.st4(GF0 + 2, k, one);
+            }
+            store.fence();
         }
         real c = real(1.0);
         const real nv_inv = real(1.0) / (real)(3 * n + (n - 1) + (p + n));
         int cur = 0;
         for (int pass = 0; pass < P.scaling; ++pass) {
             sync_warp(lane);
-            const int FD0 = FT + 12 * cur, FE0 = FD0 + 6, FD1 = FT + 12 * (1 - cur), FE1 = FD1 + 6;
             real psum = real(0.0);
-            // neighbour lanes' boundary values: e of the left stage's outgoing rows, d of the right stage's x
-            real eLb[3], dRb[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                eLb[r] = shfl_up((real)S(FE0 + r, C - 1), 1, lane);
-                dRb[r] = shfl_down((real)S(FD0 + r, 0), 1, lane);
-                if (lane == 0) eLb[r] = real(0.0);
-                if (lane == 31) dRb[r] = real(0.0);
-            }
-            PQP_ROLL
-            for (int k = 0; k < C; ++k) {
-                const StagePred sp = pred(k);
-                const real a00 = xabs(S(FA + 0, k)), a01 = xabs(S(FA + 1, k)), a10 = xabs(S(FA + 2, k)),
-                            a11 = xabs(S(FA + 3, k)), a12 = xabs(S(FA + 4, k)), ds = xabs(S(FA + 5, k));
-                const real gn = xabs(sp.gn), h0 = xabs(sp.h0), h1 = xabs(sp.h1);
-                real dk[6], ek[6], eL[3], dR[3];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { dk[j] = S(FD0 + j, k); ek[j] = S(FE0 + j, k); }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    eL[r] = (k > 0) ? (real)S(FE0 + r, k > 0 ? k - 1 : 0) : eLb[r];
-                    dR[r] = (k < C - 1) ? (real)S(FD0 + r, k < C - 1 ? k + 1 : k) : dRb[r];
-                }
-                // the left stage's rows reach this stage's x with coefficient -1 iff 1 <= g <= n
-                const real hasL = sp.real ? real(1.0) : real(0.0);
-                const real ec0 = sp.act0 ? ek[4] : real(0.0), ec1 = sp.act1 ? ek[5] : real(0.0);
-                const real ekap = sp.real ? ek[3] : real(0.0);
-                real cn[6];
-                cn[0] = dk[0] * xmax(xmax(a00 * ek[0], a10 * ek[1]), xmax(hasL * eL[0], xmax(ec0, ec1)));
-                cn[1] = dk[1] * xmax(xmax(a01 * ek[0], a11 * ek[1]), xmax(hasL * eL[1], xmax(h0 * ec0, h1 * ec1)));
-                cn[2] = dk[2] * xmax(xmax(a12 * ek[1], sp.a22 * ek[2]), xmax(hasL * eL[2], ekap));
-                cn[3] = dk[3] * ds * ek[2];
-                cn[4] = dk[4] * ec0;
-                cn[5] = dk[5] * ec1;
-                const real pw[6] = {sp.real ? w_l : real(0.0), real(0.0), sp.real ? w_kappa : real(0.0),
-                                     sp.mid ? w_dkappa : real(0.0), sp.act0 ? w_slack : real(0.0),
-                                     sp.act1 ? w_slack : real(0.0)};
-#pragma unroll
-                for (int j = 0; j < 6; ++j) cn[j] = xmax(cn[j], c * dk[j] * dk[j] * pw[j]);
-                real rn[6];
-                rn[0] = ek[0] * xmax(xmax(a00 * dk[0], a01 * dk[1]), gn * dR[0]);
-                rn[1] = ek[1] * xmax(xmax(a10 * dk[0], a11 * dk[1]), xmax(a12 * dk[2], gn * dR[1]));
-                rn[2] = ek[2] * xmax(xmax(sp.a22 * dk[2], ds * dk[3]), gn * dR[2]);
-                rn[3] = ekap * dk[2];
-                rn[4] = ec0 * xmax(xmax(dk[0], h0 * dk[1]), dk[4]);
-                rn[5] = ec1 * xmax(xmax(dk[0], h1 * dk[1]), dk[5]);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    // 1/sqrt as one MUFU.RSQ in FP32 (2 ulp): the Ruiz factors are only required to be
-                    // positive - any D, E give an equivalent problem - and 960 sqrt + divide pairs per
-                    // solve were 7 % of the kernel's stall samples; the FP64 instantiation stays exact
-                    const real dnw = dk[j] * xfast_rsqrt(limit_scaling(cn[j]));
-                    S(FD1 + j, k) = dnw;
-                    S(FE1 + j, k) = ek[j] * xfast_rsqrt(limit_scaling(rn[j]));
-                    psum += dnw * dnw * pw[j];
-                }
-            }
+            if (cur == 0) ruiz_pass<0>(c, psum);
+            else ruiz_pass<1>(c, psum);
             // cost normalisation: c_temp = 1 / limit(max(mean_j |Pbar_jj|, 1))   (q = 0 -> 1)
             const real mean = c * warp_sum(psum, lane) * nv_inv;
             real ct = xmax(mean, real(1.0));
@@ -529,35 +566,49 @@ struct QpWarp {
         }
         sync_warp(lane);
         cscale = c;
-        const int FDc = FT + 12 * cur, FEc = FDc + 6;
+        if (cur == 0) classify<0>();
+        else classify<1>();
+    }
+
+    // D, E to global scratch; proximal weights S, row classes and row weights R onto the chip (whole groups)
+    template <int CUR>
+    PQP_DEV void classify() {
+        constexpr int G0 = GF0 + 3 * CUR;
+        const real c = cscale;
         const real cinv = real(1.0) / c;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
+            real td[12], tb[4], tc[4];
+            store.template ld4n_nowait<3>(G0, k, td);
+            store.template ld4n_nowait<1>(GB2, k, tb);   // (1/m_s1 | outgoing-row bounds)
+            store.template ld4n_nowait<1>(GC4, k, tc);   // clearance-row bounds
+            store.wait_ld();
             int cls = 0;
-            real e[6];
+            real e[6], sw[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const real d = S(FDc + j, k);
-                e[j] = S(FEc + j, k);
+                const real d = td[j];
+                e[j] = td[6 + j];
                 G(gscal, GD + j, k) = d;
                 G(gscal, GE + j, k) = e[j];
                 // dummy variables get an identity pivot (accessor calls stay warp-uniform)
                 const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
-                S(FS + j, k) = exists ? sigma * cinv / (d * d) : real(1.0);
+                sw[j] = exists ? sigma * cinv / (d * d) : real(1.0);
             }
+            real Rw[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 real lo, hi;
                 bool act;
                 if (r < 3) {
-                    lo = S(FOB + r, k);
+                    lo = tb[1 + r];
                     hi = lo + ((sp.last && r < 2) ? endw[r] : real(0.0));
                     act = (lane * C + k <= n - 1) || (sp.last && r < 2);
                 } else if (r == 3) {
                     lo = -kmax; hi = kmax; act = sp.real;
                 } else {
-                    lo = S(FCLO + r - 4, k); hi = S(FCHI + r - 4, k);
+                    lo = tc[r - 4]; hi = tc[2 + r - 4];
                     act = (r == 4) ? sp.act0 : sp.act1;
                 }
                 const real ls = lo * e[r], hs = hi * e[r];
@@ -568,11 +619,15 @@ struct QpWarp {
                 else cl = 0;
                 cls |= cl << (2 * r);
                 const real base = (cl == 3) ? real(0.0) : (cl == 2 ? real(kRhoMin) : (cl == 1 ? real(kRhoEqOverIneq) * rho : rho));
-                const real Rw = base * e[r] * e[r] * cinv;
-                if (r < 3) S(FOR_ + r, k) = Rw;
-                else if (r == 3) S(FKR, k) = Rw;
-                else S(FCR + r - 4, k) = Rw;
+                Rw[r] = base * e[r] * e[r] * cinv;
             }
+            Vec4 v;
+            v.x = Rw[0]; v.y = Rw[1]; v.z = Rw[2]; v.w = Rw[3];
+            store.st4(GR3, k, v);                               // FOR_ (3) + FKR
+            v.x = Rw[4]; v.y = Rw[5]; v.z = sw[0]; v.w = sw[1];
+            store.st4(GR5, k, v);                               // FCR (2) + FS 0..1
+            v.x = sw[2]; v.y = sw[3]; v.z = sw[4]; v.w = sw[5];
+            store.st4(GS6, k, v);                               // FS 2..5
             S(FOY + 3, k) = (real)cls;
         }
     }
@@ -584,13 +639,14 @@ struct QpWarp {
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             if (!warm) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) S(FX + j, k) = real(0.0);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) S(FOY + r, k) = real(0.0);
-                S(FKZ, k) = real(0.0); S(FKY, k) = real(0.0);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) { S(FCZ + j, k) = real(0.0); S(FCY + j, k) = real(0.0); }
+                // whole groups: x (l psi kappa u | s0 s1), kappa-row z / yhat, clearance z / yhat, outgoing yhat
+                Vec4 v;
+                v.x = v.y = v.z = v.w = real(0.0);
+                store.st4(GX0, k, v);
+                store.st4(GX1, k, v);
+                store.st4(GCZ, k, v);
+                v.w = S(FOY + 3, k);  // the row classes ride in the pad component of the yhat group
+                store.st4(GOY, k, v);
                 if (sp.last) { zend[0] = real(0.0); zend[1] = real(0.0); }
             } else {
                 // scaled iterates of the previous solve are re-interpreted in the NEW scaling
