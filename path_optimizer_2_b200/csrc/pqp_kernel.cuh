@@ -650,26 +650,41 @@ struct QpWarp {
                 if (sp.last) { zend[0] = real(0.0); zend[1] = real(0.0); }
             } else {
                 // scaled iterates of the previous solve are re-interpreted in the NEW scaling
-                // (OSQP keeps work->x/z/y untouched across osqp_update_A's re-scaling)
+                // (OSQP keeps work->x/z/y untouched across osqp_update_A's re-scaling); whole groups again
+                real r3[4], r5[4], oyc[4];
+                store.template ld4n_nowait<1>(GR3, k, r3);   // Ro0 Ro1 Ro2 Rk
+                store.template ld4n_nowait<1>(GR5, k, r5);   // Rc0 Rc1 | ..
+                store.template ld4n_nowait<1>(GOY, k, oyc);  // .w = row classes
+                store.wait_ld();
+                real xv[6], oyn[3], kz, ky, czn[2], cyn[2];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) S(FX + j, k) = G(gwarm, WX + j, k) * G(gscal, GD + j, k);
+                for (int j = 0; j < 6; ++j) xv[j] = G(gwarm, WX + j, k) * G(gscal, GD + j, k);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const real e = G(gscal, GE + r, k), R = S(FOR_ + r, k);
+                    const real e = G(gscal, GE + r, k), R = r3[r];
                     const real y = G(gwarm, WOY + r, k) * e / c;
-                    S(FOY + r, k) = R > real(0.0) ? y / R : real(0.0);
+                    oyn[r] = R > real(0.0) ? y / R : real(0.0);
                 }
                 {
-                    const real e = G(gscal, GE + 3, k), R = S(FKR, k);
-                    S(FKZ, k) = G(gwarm, WKZ, k) / e;
-                    S(FKY, k) = R > real(0.0) ? (G(gwarm, WKY, k) * e / c) / R : real(0.0);
+                    const real e = G(gscal, GE + 3, k), R = r3[3];
+                    kz = G(gwarm, WKZ, k) / e;
+                    ky = R > real(0.0) ? (G(gwarm, WKY, k) * e / c) / R : real(0.0);
                 }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const real e = G(gscal, GE + 4 + j, k), R = S(FCR + j, k);
-                    S(FCZ + j, k) = G(gwarm, WCZ + j, k) / e;
-                    S(FCY + j, k) = R > real(0.0) ? (G(gwarm, WCY + j, k) * e / c) / R : real(0.0);
+                    const real e = G(gscal, GE + 4 + j, k), R = r5[j];
+                    czn[j] = G(gwarm, WCZ + j, k) / e;
+                    cyn[j] = R > real(0.0) ? (G(gwarm, WCY + j, k) * e / c) / R : real(0.0);
                 }
+                Vec4 v;
+                v.x = xv[0]; v.y = xv[1]; v.z = xv[2]; v.w = xv[3];
+                store.st4(GX0, k, v);
+                v.x = xv[4]; v.y = xv[5]; v.z = kz; v.w = ky;
+                store.st4(GX1, k, v);
+                v.x = oyn[0]; v.y = oyn[1]; v.z = oyn[2]; v.w = oyc[3];
+                store.st4(GOY, k, v);
+                v.x = czn[0]; v.y = czn[1]; v.z = cyn[0]; v.w = cyn[1];
+                store.st4(GCZ, k, v);
                 if (sp.last) {
                     zend[0] = G(gwarm, WOZ + 0, k) / G(gscal, GE + 0, k);
                     zend[1] = G(gwarm, WOZ + 1, k) / G(gscal, GE + 1, k);
@@ -678,78 +693,95 @@ struct QpWarp {
         }
     }
 
-    // proximal weight S_j of stage k. The increment form keeps the carried row values A x in the
-    // FS slots during the iteration (it has no S x term), so S is recomputed from the Ruiz D in
-    // global scratch where it is needed (factorisation, checks).
-    template <typename T>
-    PQP_DEV T s_weight(int j, int k, const StagePred &sp) {
-        if (!Incr) return T(S(FS + j, k));
-        const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
-        const T d = T(G(gscal, GD + j, k));
-        return exists ? T(sigma) / (T(cscale) * d * d) : T(1.0);
-    }
-
     // z of outgoing row r at the start of a (warm) solve, before the first iteration
     PQP_DEV real z0_out(bool warm, int r, int k) {
         return warm ? G(gwarm, WOZ + r, k) / G(gscal, GE + r, k) : real(0.0);
     }
 
     // -------------------------------------------------------------- factorisation
-    // effective outgoing-row weights of stage k (row 2 after eliminating u); also stores the
-    // elimination constants of u when `store`
+    // What the factorisation reads of one stage, fetched as whole groups in ONE load batch (it used to read these
+    // ~18 values - several of them twice - one 32-bit tensor-memory access and one wait at a time).
+    struct FacIn {
+        real a00, a01, a10, a11, a12, ds, ob[3], Ro[3], Rk, Rc[2], Sw[6];
+    };
+    PQP_DEV void load_fac(int k, FacIn &q) {
+        real t[28];
+        store.template ld4n_nowait<7>(GA0, k, t);
+        store.wait_ld();
+        q.a00 = t[0]; q.a01 = t[1]; q.a10 = t[2]; q.a11 = t[3]; q.a12 = t[4]; q.ds = t[5];
+        q.ob[0] = t[9]; q.ob[1] = t[10]; q.ob[2] = t[11];
+        q.Ro[0] = t[12]; q.Ro[1] = t[13]; q.Ro[2] = t[14]; q.Rk = t[15];
+        q.Rc[0] = t[20]; q.Rc[1] = t[21];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) q.Sw[j] = t[22 + j];
+    }
+    // proximal weight of variable j of the stage (the increment form keeps the carried row values in those slots
+    // and recomputes S from the Ruiz D in global scratch)
     template <typename T>
-    PQP_DEV void stage_rt(int k, const StagePred &sp, T (&Rt)[3], bool store) {
-        const DevParams &P = ka.prm;
-        const T ds = S(FA + 5, k);
-        const T R2 = S(FOR_ + 2, k);
+    PQP_DEV T fac_weight(const FacIn &q, int j, int k, const StagePred &sp) {
+        if (!Incr) return T(q.Sw[j]);
+        const bool exists = (j == 3) ? sp.mid : (j == 5 ? sp.act1 : sp.real);
+        const T d = T(G(gscal, GD + j, k));
+        return exists ? T(sigma) / (T(cscale) * d * d) : T(1.0);
+    }
+    // effective outgoing-row weights of the stage (row 2 after eliminating u) and 1 / m_u
+    template <typename T>
+    PQP_DEV void stage_rt(const FacIn &q, int k, const StagePred &sp, T (&Rt)[3], T &miu) {
+        const T ds = q.ds;
+        const T R2 = q.Ro[2];
         const T pu = sp.mid ? T(w_dkappa) : T(0);
-        const T mu = pu + s_weight<T>(3, k, sp) + R2 * ds * ds;
-        const T miu = T(1) / mu;
-        if (store) S(FE + 0, k) = (real)miu;
-        Rt[0] = S(FOR_ + 0, k);
-        Rt[1] = S(FOR_ + 1, k);
+        const T mu = pu + fac_weight<T>(q, 3, k, sp) + R2 * ds * ds;
+        miu = T(1) / mu;
+        Rt[0] = q.Ro[0];
+        Rt[1] = q.Ro[1];
         Rt[2] = R2 - (R2 * ds * miu) * R2 * ds;
     }
-    // diagonal block of the reduced system of stage k (own rows + diag(RtL) of the left stage)
+    // diagonal block of the reduced system of the stage (own rows + diag(RtL) of the left stage) and 1 / m_s0, 1 / m_s1
     template <typename T>
-    PQP_DEV void stage_diag(int k, const StagePred &sp, const T (&Rt)[3], const T (&RtL)[3], T (&D)[6]) {
-        const DevParams &P = ka.prm;
-        const T a00 = S(FA + 0, k), a01 = S(FA + 1, k), a10 = S(FA + 2, k), a11 = S(FA + 3, k),
-                a12 = S(FA + 4, k), a22 = sp.a22;
+    PQP_DEV void stage_diag(const FacIn &q, int k, const StagePred &sp, const T (&Rt)[3], const T (&RtL)[3], T (&D)[6],
+                            T (&mis)[2]) {
+        const T a00 = q.a00, a01 = q.a01, a10 = q.a10, a11 = q.a11, a12 = q.a12, a22 = sp.a22;
         T Rc[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const bool act = j == 0 ? sp.act0 : sp.act1;
             const T ps = act ? T(w_slack) : T(0);
-            const T Rcj = S(FCR + j, k);
-            const T ms = ps + s_weight<T>(4 + j, k, sp) + Rcj;
-            const T mis = T(1) / ms;
-            S(FE + 1 + j, k) = (real)mis;
-            Rc[j] = Rcj - (Rcj * mis) * Rcj;
+            const T Rcj = q.Rc[j];
+            const T ms = ps + fac_weight<T>(q, 4 + j, k, sp) + Rcj;
+            mis[j] = T(1) / ms;
+            Rc[j] = Rcj - (Rcj * mis[j]) * Rcj;
         }
         const T h0 = sp.h0, h1 = sp.h1;
         const T pk = sp.real ? T(w_kappa) : T(0), pl = sp.real ? T(w_l) : T(0);
         const T hasL = sp.real ? T(1) : T(0);
-        D[0] = s_weight<T>(0, k, sp) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
+        D[0] = fac_weight<T>(q, 0, k, sp) + pl + Rt[0] * a00 * a00 + Rt[1] * a10 * a10 + Rc[0] + Rc[1] + hasL * RtL[0];
         D[1] = Rt[0] * a00 * a01 + Rt[1] * a10 * a11 + Rc[0] * h0 + Rc[1] * h1;
         D[2] = Rt[1] * a10 * a12;
-        D[3] = s_weight<T>(1, k, sp) + Rt[0] * a01 * a01 + Rt[1] * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1 + hasL * RtL[1];
+        D[3] = fac_weight<T>(q, 1, k, sp) + Rt[0] * a01 * a01 + Rt[1] * a11 * a11 + Rc[0] * h0 * h0 + Rc[1] * h1 * h1 + hasL * RtL[1];
         D[4] = Rt[1] * a11 * a12;
-        D[5] = s_weight<T>(2, k, sp) + pk + Rt[1] * a12 * a12 + Rt[2] * a22 * a22 + T(S(FKR, k)) + hasL * RtL[2];
+        D[5] = fac_weight<T>(q, 2, k, sp) + pk + Rt[1] * a12 * a12 + Rt[2] * a22 * a22 + T(q.Rk) + hasL * RtL[2];
     }
-    // coupling block between stage k and k+1: O[r][c] = gn * Rt_r * Ahat[r][c]
+    // coupling block between the stage and the next: O[r][c] = gn * Rt_r * Ahat[r][c]
     template <typename T>
-    PQP_DEV void stage_coupling(int k, const StagePred &sp, const T (&Rt)[3], T (&O)[9]) {
+    PQP_DEV void stage_coupling(const FacIn &q, const StagePred &sp, const T (&Rt)[3], T (&O)[9]) {
         const T gn = sp.gn;
-        O[0] = gn * Rt[0] * T(S(FA + 0, k));
-        O[1] = gn * Rt[0] * T(S(FA + 1, k));
+        O[0] = gn * Rt[0] * T(q.a00);
+        O[1] = gn * Rt[0] * T(q.a01);
         O[2] = T(0);
-        O[3] = gn * Rt[1] * T(S(FA + 2, k));
-        O[4] = gn * Rt[1] * T(S(FA + 3, k));
-        O[5] = gn * Rt[1] * T(S(FA + 4, k));
+        O[3] = gn * Rt[1] * T(q.a10);
+        O[4] = gn * Rt[1] * T(q.a11);
+        O[5] = gn * Rt[1] * T(q.a12);
         O[6] = T(0);
         O[7] = T(0);
         O[8] = gn * Rt[2] * T(sp.a22);
+    }
+    // the elimination constants share groups 1 and 2 with the stage's coefficients and bounds: rewrite both groups
+    PQP_DEV void store_elim(const FacIn &q, int k, real miu, real mis0, real mis1) {
+        Vec4 v;
+        v.x = q.a12; v.y = q.ds; v.z = miu; v.w = mis0;
+        store.st4(GA1, k, v);
+        v.x = mis1; v.y = q.ob[0]; v.z = q.ob[1]; v.w = q.ob[2];
+        store.st4(GB2, k, v);
     }
 
     // Block LDL' of the reduced system in nested-dissection order (see header comment).
@@ -760,9 +792,11 @@ struct QpWarp {
         T RtL[3], OL[9];
         {
             const StagePred spl = pred(C - 1);
-            T RtLast[3], Olast[9];
-            stage_rt<T>(C - 1, spl, RtLast, false);
-            stage_coupling<T>(C - 1, spl, RtLast, Olast);
+            T RtLast[3], Olast[9], miu_unused;
+            FacIn ql;
+            load_fac(C - 1, ql);
+            stage_rt<T>(ql, C - 1, spl, RtLast, miu_unused);
+            stage_coupling<T>(ql, spl, RtLast, Olast);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 RtL[r] = shfl_up(RtLast[r], 1, lane);
@@ -781,10 +815,14 @@ struct QpWarp {
             for (int c = 0; c < 3; ++c) Phi[3 * r + c] = OL[3 * c + r];
         T dA[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
         T Dt[6], Rt[3];
+        FacIn qc;  // the current stage's inputs (one load batch per stage)
         {
             const StagePred sp0 = pred(0);
-            stage_rt<T>(0, sp0, Rt, true);
-            stage_diag<T>(0, sp0, Rt, RtL, Dt);
+            T miu, mis[2];
+            load_fac(0, qc);
+            stage_rt<T>(qc, 0, sp0, Rt, miu);
+            stage_diag<T>(qc, 0, sp0, Rt, RtL, Dt, mis);
+            store_elim(qc, 0, (real)miu, (real)mis[0], (real)mis[1]);
         }
         // interior elimination with fill towards the left separator
         PQP_ROLL
@@ -792,13 +830,22 @@ struct QpWarp {
             const StagePred sp = pred(k);
             T Dinv[6], O[9], Gh[9], Fh[9];
             ok = inv_sym3(Dt, Dinv) && ok;
-            stage_coupling<T>(k, sp, Rt, O);
+            stage_coupling<T>(qc, sp, Rt, O);
             mul_ms(O, Dinv, Gh);
             mul_ms(Phi, Dinv, Fh);
+            {   // the stage's factor = six whole groups: Dinv[6] G[9] F[9]
+                real fv[24];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) S(FDI + j, k) = (real)Dinv[j];
+                for (int j = 0; j < 6; ++j) fv[j] = (real)Dinv[j];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { S(FG + j, k) = (real)Gh[j]; S(FF + j, k) = (real)Fh[j]; }
+                for (int j = 0; j < 9; ++j) { fv[6 + j] = (real)Gh[j]; fv[15 + j] = (real)Fh[j]; }
+#pragma unroll
+                for (int g = 0; g < 6; ++g) {
+                    Vec4 v;
+                    v.x = fv[4 * g]; v.y = fv[4 * g + 1]; v.z = fv[4 * g + 2]; v.w = fv[4 * g + 3];
+                    store.st4(GF0 + g, k, v);
+                }
+            }
             T t6[6], t9[9];
             mul_abt_sym(Fh, Phi, t6);
 #pragma unroll
@@ -810,9 +857,11 @@ struct QpWarp {
             // next stage's own block (its left neighbour is stage k)
             const StagePred spn = pred(k + 1);
             T RtPrev[3] = {Rt[0], Rt[1], Rt[2]};
-            stage_rt<T>(k + 1, spn, Rt, true);
-            T Dn[6];
-            stage_diag<T>(k + 1, spn, Rt, RtPrev, Dn);
+            T miu, mis[2], Dn[6];
+            load_fac(k + 1, qc);
+            stage_rt<T>(qc, k + 1, spn, Rt, miu);
+            stage_diag<T>(qc, k + 1, spn, Rt, RtPrev, Dn, mis);
+            store_elim(qc, k + 1, (real)miu, (real)mis[0], (real)mis[1]);
 #pragma unroll
             for (int j = 0; j < 6; ++j) Dt[j] = Dn[j] - t6[j];
         }
@@ -1791,16 +1840,35 @@ struct QpWarp {
         rho = est;
         PQP_ROLL
         for (int k = 0; k < C; ++k) {
-            const int cls = cls_of(k);
+            // the five groups that hold row weights / scaled duals, one load batch, five group stores
+            real r3[4], r5[4], x1[4], oy[4], cz[4];
+            store.template ld4n_nowait<1>(GR3, k, r3);   // Ro0 Ro1 Ro2 Rk
+            store.template ld4n_nowait<1>(GR5, k, r5);   // Rc0 Rc1 | (S or carried A x)
+            store.template ld4n_nowait<1>(GX1, k, x1);   // s0 s1 | kappa-row z, yhat
+            store.template ld4n_nowait<1>(GOY, k, oy);   // outgoing yhat 0..2 | row classes
+            store.template ld4n_nowait<1>(GCZ, k, cz);   // clearance z 0..1 | yhat 0..1
+            store.wait_ld();
+            const int cls = (int)oy[3];
+            real fr[6], fi[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const int cl = (cls >> (2 * r)) & 3;
-                const real fr = cl <= 1 ? ratio : real(1.0), fi = cl <= 1 ? rinv : real(1.0);
-                if (r < 3) { S(FOR_ + r, k) *= fr; S(FOY + r, k) *= fi; }
-                else if (r == 3) { S(FKR, k) *= fr; S(FKY, k) *= fi; }
-                else { S(FCR + r - 4, k) *= fr; S(FCY + r - 4, k) *= fi; }
+                fr[r] = cl <= 1 ? ratio : real(1.0);
+                fi[r] = cl <= 1 ? rinv : real(1.0);
             }
+            Vec4 v;
+            v.x = r3[0] * fr[0]; v.y = r3[1] * fr[1]; v.z = r3[2] * fr[2]; v.w = r3[3] * fr[3];
+            store.st4(GR3, k, v);
+            v.x = r5[0] * fr[4]; v.y = r5[1] * fr[5]; v.z = r5[2]; v.w = r5[3];
+            store.st4(GR5, k, v);
+            v.x = x1[0]; v.y = x1[1]; v.z = x1[2]; v.w = x1[3] * fi[3];
+            store.st4(GX1, k, v);
+            v.x = oy[0] * fi[0]; v.y = oy[1] * fi[1]; v.z = oy[2] * fi[2]; v.w = oy[3];
+            store.st4(GOY, k, v);
+            v.x = cz[0]; v.y = cz[1]; v.z = cz[2] * fi[4]; v.w = cz[3] * fi[5];
+            store.st4(GCZ, k, v);
         }
+        store.fence();
         return true;
     }
 
@@ -1925,8 +1993,15 @@ struct QpWarp {
         for (int k = 0; k < C; ++k) {
             const int g = lane * C + k;
             const StagePred sp = pred(k);
-            const real l = S(FX + 0, k), ps = S(FX + 1, k), kp = S(FX + 2, k), u = S(FX + 3, k),
-                        s0 = S(FX + 4, k), s1 = S(FX + 5, k);
+            StageRO q;
+            Vec4 x0, x1, oy, cz;
+            {
+                real loaded[44];
+                store.template ld4n_nowait<11>(GA0, k, loaded);
+                store.wait_ld();
+                unpack_stage(loaded, q, x0, x1, oy, cz);
+            }
+            const real l = x0.x, ps = x0.y, kp = x0.z, u = x0.w, s0 = x1.x, s1 = x1.y;
             if (sp.real) {
                 const int i = g - 1;
                 sol[0 * nmax + i] = (double)l;
@@ -1944,15 +2019,15 @@ struct QpWarp {
             }
             // row values, read uniformly (the writes below are lane-divergent)
             real zo_[3], yo_[3];
+            const real oyv[3] = {oy.x, oy.y, oy.z};
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const real obr = S(FOB + r, k);
-                zo_[r] = (sp.last && r < 2) ? zend[r] : obr;
-                yo_[r] = (real)S(FOR_ + r, k) * (real)S(FOY + r, k);
+                zo_[r] = (sp.last && r < 2) ? zend[r] : q.ob[r];
+                yo_[r] = q.Ro[r] * oyv[r];
             }
-            const real zk_ = S(FKZ, k), yk_ = (real)S(FKR, k) * (real)S(FKY, k);
-            const real zc0_ = S(FCZ + 0, k), zc1_ = S(FCZ + 1, k);
-            const real yc0_ = (real)S(FCR + 0, k) * (real)S(FCY + 0, k), yc1_ = (real)S(FCR + 1, k) * (real)S(FCY + 1, k);
+            const real zk_ = x1.z, yk_ = q.Rk * x1.w;
+            const real zc0_ = cz.x, zc1_ = cz.y;
+            const real yc0_ = q.Rc[0] * cz.z, yc1_ = q.Rc[1] * cz.w;
             // rows in the reference's order
             if (yf || zf) {
 #pragma unroll
