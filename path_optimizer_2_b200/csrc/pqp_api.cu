@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
         int chunk = 0;
         if (ka.ready) {
             // streamed launch: this instance's inputs may still be in flight
-            chunk = qp / ka.chunk_len;
+            while (chunk + 1 < ka.n_chunks && qp >= ka.chunk_lo[chunk + 1]) ++chunk;
             bool landed = true;
             if (lane == 0) {
                 const volatile int *flag = ka.ready + chunk;
@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
             __syncwarp();
             if (lane == 0) {
                 __threadfence();  // this instance's outputs before the count
-                const int lo = chunk * ka.chunk_len;
-                const int len = (lo + ka.chunk_len <= ka.batch) ? ka.chunk_len : ka.batch - lo;
+                const int len = ka.chunk_lo[chunk + 1] - ka.chunk_lo[chunk];
                 if (atomicAdd(ka.done + chunk, 1) + 1 == len) {
                     __threadfence_system();
                     *reinterpret_cast<volatile int *>(ka.host_done + chunk) = 1;
@@ -591,7 +590,8 @@ cudaError_t dmalloc(T **p, size_t count) {
 struct StreamedLaunch {
     const int *ready = nullptr;
     int *done = nullptr, *host_done = nullptr;
-    int chunk_len = 0;
+    int n_chunks = 0;
+    int chunk_lo[9] = {};
 };
 
 int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, int mode,
@@ -622,7 +622,8 @@ int run_device(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out *out, 
     ka.ready = sl ? sl->ready : nullptr;
     ka.done = sl ? sl->done : nullptr;
     ka.host_done = sl ? sl->host_done : nullptr;
-    ka.chunk_len = sl ? sl->chunk_len : 0;
+    ka.n_chunks = sl ? sl->n_chunks : 0;
+    for (int c = 0; c < 9; ++c) ka.chunk_lo[c] = sl ? sl->chunk_lo[c] : 0;
     ka.warm = esc ? h->e_warm : h->d_warm;
     ka.scal = esc ? h->e_scal : h->d_scal;
     ka.dy = esc ? h->e_dy : h->d_dy;
@@ -765,6 +766,21 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     if (nchunks > pqp_handle::kStreams) nchunks = pqp_handle::kStreams;
     const int per = (B + nchunks - 1) / nchunks;
     nchunks = (B + per - 1) / per;
+    // chunk boundaries. Large batches use a ramp instead of equal chunks: nothing can start before the FIRST chunk
+    // has landed and nothing is returned before the LAST chunk has finished, so those two are small (1/32 and 2/32 of
+    // the batch) and the middle ones carry the volume.
+    int lo_of[pqp_handle::kStreams + 1];
+    if (nchunks == pqp_handle::kStreams && B >= 32 * min_chunk) {
+        static const int w[pqp_handle::kStreams] = {1, 3, 6, 6, 6, 5, 3, 2};  // / 32
+        int acc = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            lo_of[c] = (int)((long long)B * acc / 32);
+            acc += w[c];
+        }
+        lo_of[nchunks] = B;
+    } else {
+        for (int c = 0; c <= nchunks; ++c) lo_of[c] = (c * per < B) ? c * per : B;
+    }
     cudaStream_t sk = h->streams[0], sc = h->streams[1], sd = h->streams[2];
     for (int c = 0; c < pqp_handle::kStreams; ++c) h->h_done[c] = 0;
     PQP_CUDA(h, cudaMemsetAsync(h->d_ready, 0, pqp_handle::kStreams * sizeof(int), sk));
@@ -782,12 +798,13 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     sl.ready = h->d_ready;
     sl.done = h->d_done;
     sl.host_done = h->d_hdone;
-    sl.chunk_len = per;
+    sl.n_chunks = nchunks;
+    for (int c = 0; c <= pqp_handle::kStreams; ++c) sl.chunk_lo[c] = c <= nchunks ? lo_of[c] : B;
     // The chunk copies are queued BEFORE the launch: they are asynchronous (pinned buffers), so the
     // kernel still overlaps them, and a tool that makes launches blocking (ncu serialises kernels)
     // cannot leave the kernel waiting for copies the host has not issued yet.
     for (int c = 0; c < nchunks; ++c) {
-        const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
+        const int lo = lo_of[c], hi = lo_of[c + 1];
         const size_t nb = (size_t)(hi - lo);
         PQP_CUDA(h, cudaMemcpyAsync(h->d_knots + (size_t)lo * PQP_NFIELDS * nmax, in->knots + (size_t)lo * PQP_NFIELDS * nmax,
                                     nb * PQP_NFIELDS * nmax * sizeof(double), cudaMemcpyHostToDevice, sc));
@@ -801,7 +818,7 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
     if (rc) return rc;
     h->host_inputs_resident = true;
     for (int c = 0; c < nchunks; ++c) {
-        const int lo = c * per, hi = (lo + per < B) ? lo + per : B;
+        const int lo = lo_of[c], hi = lo_of[c + 1];
         const size_t nb = (size_t)(hi - lo);
         // wait until the kernel announces the chunk (or has ended, e.g. after an error)
         volatile int *flag = h->h_done + c;

@@ -117,13 +117,14 @@ struct KernelArgs {
     int *status, *iters;
     int *work_counter;  // persistent kernels: next instance to take (zeroed before the launch)
     // streamed launch (host API): the kernel starts before the inputs have landed; instance qp
-    // belongs to chunk qp / chunk_len, whose H2D copy is followed by a write to ready[chunk];
+    // belongs to the chunk c with chunk_lo[c] <= qp < chunk_lo[c + 1], whose H2D copy is followed by a write to ready[c];
     // done[chunk] counts finished instances and host_done[chunk] (mapped host memory) is set
     // when a chunk is complete so the host can start its D2H copy. All null for plain launches.
     const int *ready;
     int *done;
     int *host_done;
-    int chunk_len;
+    int n_chunks;
+    int chunk_lo[9];  // chunk boundaries (n_chunks + 1 entries); chunks need not be equal
     int *flags;  // optional: bit 0 = infeasibility suspected (certificate conditions 1-2 held)
     double *x_full, *y_full, *z_full, *info;
     void *warm, *scal, *dy, *rho_state;  // per-instance scratch in the kernel's scalar type
@@ -1254,9 +1255,13 @@ struct QpWarp {
         for (int k = 0; k < C; ++k) {
             const StagePred sp = pred(k);
             StageRO q;
-            load_ro(k, q);
             Vec4 x0, x1, oy, cz;
-            load_rw(k, x0, x1, oy, cz);
+            {
+                real loaded[44];
+                store.template ld4n_nowait<11>(GA0, k, loaded);
+                store.wait_ld();
+                unpack_stage(loaded, q, x0, x1, oy, cz);
+            }
             const real x[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
             real ax[6];
             if (initial) {

@@ -66,7 +66,7 @@ int run_batch(EmuHandle *h, const pqp_batch_in *in, const pqp_batch_out *out, in
     ka.ready = nullptr;
     ka.done = nullptr;
     ka.host_done = nullptr;
-    ka.chunk_len = 0;
+    ka.n_chunks = 0;
     ka.x_full = out->x_full;
     ka.y_full = out->y_full;
     ka.z_full = out->z_full;
