@@ -21,7 +21,7 @@ python profiles/traffic_from_ncu.py $OUT/admm_full_${TAG}_bits128.ncu-rep 8192 2
     "cold-only handle (option bit 128): inputs once + solution once; Ruiz / delta_y scratch is per resident warp and stays in L2"
 python profiles/traffic_from_ncu.py $OUT/admm_full_${TAG}_bits0.ncu-rep 8192 240 $OUT/traffic_cold_n240.json \
     "handle that keeps the warm state for pqp_resolve: + 18 KB per instance of scaled x, z, y"
-python profiles/ncu_lines.py $OUT/admm_full_${TAG}_bits128.ncu-rep > $OUT/ncu_${TAG}_functions.txt 2>&1
+python profiles/ncu_lines.py $OUT/admm_full_${TAG}_bits128.ncu-rep path_optimizer_2_b200/csrc/pqp_kernel.cuh 25 > $OUT/ncu_${TAG}_functions.txt 2>&1
 {
   echo "# cuobjdump -sass path_optimizer_2_b200/libpqp_b200.so | mnemonic counts"
   cuobjdump -sass path_optimizer_2_b200/libpqp_b200.so > $OUT/sass_full.txt
