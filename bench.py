@@ -526,32 +526,59 @@ def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, wo
         rank = int(os.environ.get("RANK", "0"))
         mine = tab[rank * B:(rank + 1) * B]
         assert np.array_equal(mine["status"], status) and np.array_equal(mine["iters"], iters), "gathered table is wrong"
-    for s_ in svs[1:]:
-        s_.close()
-
-    # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed)
+    # ---- e2e: host buffers through the public host-pointer call (H2D + kernel + D2H timed). With K batches in
+    # flight the caller drives K handles from K host threads (a handle is single-threaded, handles are independent):
+    # every step is still one synchronous pqp_solve of a whole batch from pinned host memory into pinned host memory.
     pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
     p_knots, p_inst, p_n = pin(hb.knots), pin(hb.inst), pin(hb.n)
     hbp = abi.HostBatch(p_knots.numpy(), p_inst.numpy(), p_n.numpy())
-    hres = abi.HostResult(B, n, full=False, info=False)
-    p_sol, p_cost = pin(hres.sol), pin(hres.cost)
-    p_status, p_iters = pin(hres.status), pin(hres.iters)
-    hres.sol, hres.cost, hres.status, hres.iters = p_sol.numpy(), p_cost.numpy(), p_status.numpy(), p_iters.numpy()
-    for _ in range(2):
-        sv.solve(hbp, out=hres)
+    hress, keep = [], []
+    for _ in range(K):
+        hres = abi.HostResult(B, n, full=False, info=False)
+        p_sol, p_cost = pin(hres.sol), pin(hres.cost)
+        p_status, p_iters = pin(hres.status), pin(hres.iters)
+        hres.sol, hres.cost, hres.status, hres.iters = p_sol.numpy(), p_cost.numpy(), p_status.numpy(), p_iters.numpy()
+        hress.append(hres)
+        keep.append((p_sol, p_cost, p_status, p_iters))
+    for k in range(K):
+        for _ in range(2):
+            svs[k].solve(hbp, out=hress[k])
+    errs = []
+
+    def host_worker(k):
+        try:
+            torch.cuda.set_device(local_rank)
+            for _ in range(k, e2e_steps, K):
+                svs[k].solve(hbp, out=hress[k])  # synchronous: returns after the D2H copy completed
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
     barrier(world)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sv.solve(hbp, out=hres)  # synchronous: returns after the D2H copy completed
+    if K == 1:
+        host_worker(0)
+    else:
+        import threading
+        ths = [threading.Thread(target=host_worker, args=(k,)) for k in range(K)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0, dev, world)
+    if errs:
+        raise errs[0]
+    hres = hress[0]
+    for k in range(1, K):
+        assert np.array_equal(hress[k].status, hres.status) and np.array_equal(hress[k].sol, hres.sol)
     h2d = int(hb.knots.nbytes + hb.inst.nbytes + hb.n.nbytes)
     d2h = int(hres.sol.nbytes + hres.cost.nbytes + hres.status.nbytes + hres.iters.nbytes)
     if not (option_bits & 2):  # the host call escalates suspected-infeasible instances to FP64, the device call cannot
         assert np.array_equal(hres.status, status), "host-API and device-API runs disagree"
     info = sv.kernel_info
     kms = gather_scalars(kernel_ms, dev, world)
-    sv.close()
+    for s_ in svs:
+        s_.close()
     return {"value": world * B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kernel_ms, "inflight": K,
             "kernel_ms_per_rank": kms, "e2e_value": world * B * e2e_steps / e2e_s, "e2e_steps": e2e_steps,
             "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clk, "status": status, "iters": iters,
@@ -942,7 +969,9 @@ def main():
             },
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "steps": r["e2e_steps"]},
+                    "steps": r["e2e_steps"], "batches_in_flight": r["inflight"],
+                    "how": "every step = one synchronous pqp_solve of the whole batch, pinned host inputs -> pinned host "
+                           "results; %d handle(s), one host thread per handle" % r["inflight"]},
             "gpu_launches": r["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(n, B, cold_only), "peak_source": peak_src,

@@ -8,6 +8,7 @@
 //
 // There is no CPU fallback in this library: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -821,9 +822,14 @@ int run_host_streamed(pqp_handle *h, const pqp_batch_in *in, const pqp_batch_out
         const int lo = lo_of[c], hi = lo_of[c + 1];
         const size_t nb = (size_t)(hi - lo);
         // wait until the kernel announces the chunk (or has ended, e.g. after an error)
+        // (short spin, then 20 us naps: a chunk takes ~ a millisecond, and a caller that drives several handles
+        // from several threads must not burn a core per handle)
         volatile int *flag = h->h_done + c;
         for (unsigned spin = 0; *flag == 0; ++spin) {
-            if ((spin & 0x3ff) == 0x3ff && cudaStreamQuery(sk) != cudaErrorNotReady) break;
+            if (spin < 4096) continue;
+            if ((spin & 0x3f) == 0 && cudaStreamQuery(sk) != cudaErrorNotReady) break;
+            const struct timespec nap = {0, 20000};
+            nanosleep(&nap, nullptr);
         }
         PQP_CUDA(h, cudaMemcpyAsync(h->h_status + lo, h->d_status + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
         PQP_CUDA(h, cudaMemcpyAsync(h->h_flags + lo, h->d_flags + lo, nb * sizeof(int), cudaMemcpyDeviceToHost, sd));
