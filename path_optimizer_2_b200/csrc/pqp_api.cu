@@ -154,9 +154,10 @@ struct TmemStore {
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
     static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8 (512 columns) and at C = 4 with 256 columns, 10 at C = 16, else 0
     uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
+    uint32_t cur;  // stage cursor: tb + k * (columns per stage) of the stage a hot loop is at (see seek)
     float *sm;    // spill area (shared memory) of this warp: [spill slot][k][lane] float4
     int lane;
-    __device__ TmemStore(uint32_t t, float *s, int l) : tb(t), sm(s), lane(l) {}
+    __device__ TmemStore(uint32_t t, float *s, int l) : tb(t), cur(t), sm(s), lane(l) {}
     // Which groups leave tensor memory first when the warp's columns do not hold all 18: the
     // clearance / proximal weights GR5, GS6 (least frequently read), then the other read-only groups
     // (4, 3, 2, 1, 0), then the factor from its end (17 .. 12), the read-write groups last.
@@ -215,6 +216,46 @@ struct TmemStore {
         }
     }
     __device__ void wait_ld() const { tmem_wait_ld(); }
+    // Stage cursor. tcgen05.ld/st take their address from a UNIFORM register; an address computed from a loop
+    // counter that ptxas keeps in a vector register costs one R2UR per access (5.7 % of the kernel's executed
+    // instructions before this, profiles/r2/README.md). seek(k) produces the stage's column base in a uniform
+    // register once per stage; the `_cur` accessors address "the cursor's stage" (the caller passes the same
+    // stage as k, used by the spilled groups).
+    static constexpr uint32_t kStride = (uint32_t)(kGroups * 4);
+    __device__ void seek(int k) {
+        // (redux.sync delivers its result in a uniform register; a loop-carried cursor would be moved to a vector
+        // register by ptxas and converted back at every access)
+        cur = C == 1 ? tb : __reduce_or_sync(0xffffffffu, tb + (uint32_t)k * kStride);
+    }
+    __device__ uint32_t ccol(int g) const { return cur + (uint32_t)(slot(g) * 4); }
+    __device__ void st4_cur(int g, int k, const float4 &v) {
+        if (spilled(g)) { *sp(g, k) = v; return; }
+        tmem_st4(ccol(g), v);
+    }
+    template <int N> __device__ void ld4n_nowait_cur(int g0, int k, float (&out)[4 * N]) const {
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+            float o[4];
+            if (spilled(g0 + g)) {
+                const float4 v = *sp(g0 + g, k);
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            } else {
+                tmem_ld4_nowait(ccol(g0 + g), o);
+            }
+            out[4 * g] = o[0]; out[4 * g + 1] = o[1]; out[4 * g + 2] = o[2]; out[4 * g + 3] = o[3];
+        }
+    }
+    // group g of the stage AFTER the cursor's (of the cursor's own stage when that is the last one)
+    __device__ void ld4_nowait_next(int g, int k, float (&out)[4]) const {
+        if (spilled(g)) {
+            const float4 v = *sp(g, k < C - 1 ? k + 1 : k);
+            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        } else {
+            const uint32_t last = tb + (uint32_t)((C - 1) * kGroups * 4);
+            const uint32_t a = (cur == last) ? cur : cur + kStride;
+            tmem_ld4_nowait(a + (uint32_t)(slot(g) * 4), out);
+        }
+    }
     template <int N> __device__ void ld4n(int g0, int k, float (&out)[4 * N]) const {
 #pragma unroll
         for (int g = 0; g < N; ++g) {
@@ -256,7 +297,8 @@ __global__ void __launch_bounds__(32 * WT, 1) pqp_admm_kernel_tmem(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // lanes of sub-partition (warp & 3); the second warp of a sub-partition takes the upper columns
-    const uint32_t tb = tbase_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * Store::kGroups * 4 * C);
+    const uint32_t tb_v = tbase_s + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * Store::kGroups * 4 * C);
+    const uint32_t tb = __reduce_or_sync(0xffffffffu, tb_v);
     float *spill = reinterpret_cast<float *>(smem_raw) + (size_t)warp * kSpillFloats;
     for (;;) {
         int qp = 0;

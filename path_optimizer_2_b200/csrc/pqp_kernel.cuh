@@ -307,6 +307,11 @@ struct SmemStore {
     template <int N> PQP_DEV void ld4n_nowait(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k, out); }
     PQP_DEV void wait_ld() const {}
     PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
+    // stage cursor (see TmemStore): plain stage indexing under this policy
+    PQP_DEV void seek(int) {}
+    PQP_DEV void st4_cur(int g, int k, const Vec4 &v) { st4(g, k, v); }
+    template <int N> PQP_DEV void ld4n_nowait_cur(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k, out); }
+    PQP_DEV void ld4_nowait_next(int g, int k, real (&out)[4]) const { ld4n<1>(g, k < C - 1 ? k + 1 : k, out); }
 };
 
 // =========================================================================================
@@ -314,6 +319,7 @@ struct SmemStore {
 // this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction
 // cache (40 % no_inst stalls in profiles/r1/ncu_v1_unrolled_summary.txt).
 #define PQP_ROLL _Pragma("unroll 1")
+#define PQP_SWEEP_UNROLL _Pragma("unroll")
 #ifndef PQP_UPDATE_UNROLL
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
 #endif
@@ -368,6 +374,11 @@ struct QpWarp {
     };
     PQP_DEV SRef S(int f, int k) { return SRef{store, f, k}; }
     PQP_DEV VRef V(int g, int k) { return VRef{store, g, k}; }
+    struct VcRef {  // stage k = the store's cursor stage
+        Store &st; int g, k;
+        PQP_DEV VcRef &operator=(const Vec4 &v) { st.st4_cur(g, k, v); return *this; }
+    };
+    PQP_DEV VcRef Vc(int g, int k) { return VcRef{store, g, k}; }
     PQP_DEV real &G(real *base, int f, int k) { return base[(f * C + k) * 32 + lane]; }
     PQP_DEV real &GL(real *base, int f, int k, int ln) { return base[(f * C + k) * 32 + ln]; }
     // row-class bitmask of stage k, kept in the pad component of the yhat group (exact small integer)
@@ -969,7 +980,7 @@ struct QpWarp {
         }
         store.wait_ld();
         bk[0] = bvv[0]; bk[1] = bvv[1]; bk[2] = bvv[2];
-        PQP_ROLL
+        PQP_SWEEP_UNROLL
         for (int k = 0; k < C - 1; ++k) {
             // the next step's factor and rhs are in flight while this step computes; one wait at the end
             if (k + 1 < C - 1) {
@@ -1082,7 +1093,7 @@ struct QpWarp {
             store.wait_ld();
             vcur.x = t4[0]; vcur.y = t4[1]; vcur.z = t4[2]; vcur.w = t4[3];
         }
-        PQP_ROLL
+        PQP_SWEEP_UNROLL
         for (int k = C - 2; k >= 0; --k) {
             // the next step's factor and rhs are in flight while this step computes; one wait at the end
             real t4[4];
@@ -1584,16 +1595,16 @@ struct QpWarp {
             wc[1] = q.Rc[1] * ((zn - ax[5]) - cz.w);
             if (kCheck) cert_row(5, k, q.Rc[1] * (zt - zn), q.clo[1], q.chi[1]);
         }
-        V(GX0, k) = x0;
-        V(GX1, k) = x1;
-        V(GOY, k) = oy;
-        V(GCZ, k) = cz;
+        Vc(GX0, k) = x0;
+        Vc(GX1, k) = x1;
+        Vc(GOY, k) = oy;
+        Vc(GCZ, k) = cz;
         {
             Vec4 g5, g6;
             g5.x = q.Rc[0]; g5.y = q.Rc[1]; g5.z = ax[0]; g5.w = ax[1];
             g6.x = ax[2]; g6.y = ax[3]; g6.z = ax[4]; g6.w = ax[5];
-            V(GR5, k) = g5;
-            V(GS6, k) = g6;
+            Vc(GR5, k) = g5;
+            Vc(GS6, k) = g6;
         }
         local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
@@ -1610,13 +1621,14 @@ struct QpWarp {
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
+            store.seek(k);
             const StagePred sp = pred(k);
             // one load batch per stage: the next stage's dx and this stage's 11 groups are issued together and
             // waited for once (three dependent load -> wait round trips per stage before; the tensor-memory
             // access code held 24 % of the kernel's stall samples, profiles/r2/README.md)
             real dwv[4], loaded[44];
-            store.template ld4n_nowait<1>(GBV, k < C - 1 ? k + 1 : k, dwv);
-            store.template ld4n_nowait<11>(GA0, k, loaded);
+            store.ld4_nowait_next(GBV, k, dwv);
+            store.template ld4n_nowait_cur<11>(GA0, k, loaded);
             store.wait_ld();
             const real dt[3] = {dv.x, dv.y, dv.z};
             real dn[3];
@@ -1632,7 +1644,7 @@ struct QpWarp {
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
             bv.z = bk[2] - ((sp.real && k > 0) ? wprev[2] : real(0.0));
             bv.w = real(0.0);
-            V(GBV, k) = bv;
+            Vc(GBV, k) = bv;
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
             dv = dw;
