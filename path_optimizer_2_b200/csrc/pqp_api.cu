@@ -152,6 +152,7 @@ struct TmemStore {
     static constexpr int kAll = pqp::NFIELD / 4;                       // 18 groups
     static constexpr int kFit = COLS / (4 * C);                        // groups that fit in this warp's columns
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
+    static constexpr bool kUnrollCr = COLS == 512;                     // one warp per scheduler (see cr_forward_level)
     static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8 (512 columns) and at C = 4 with 256 columns, 10 at C = 16, else 0
     uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
     uint32_t cur;  // stage cursor: tb + k * (columns per stage) of the stage a hot loop is at (see seek)

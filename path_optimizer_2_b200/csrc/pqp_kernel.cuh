@@ -290,6 +290,7 @@ struct SmemStore {
     typedef typename Vec4T<real>::type Vec4;
     real *sm;
     int lane;
+    static constexpr bool kUnrollCr = false;  // several warps per scheduler: keep the hot loop small
     PQP_DEV SmemStore(real *s, int l) : sm(s), lane(l) {}
     PQP_DEV real ld(int f, int k) const { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
     PQP_DEV void st(int f, int k, real v) { sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)] = v; }
@@ -1013,6 +1014,45 @@ struct QpWarp {
         solve_tail(bk, acc);
         store.fence();  // the update reads x~ from GBV
     }
+    // One level of the reduction: the lanes with (lane mod 2h) == h are eliminated, their neighbours at distance h
+    // (lane mod 2h == 0) absorb G- b and G+ b of both eliminated neighbours. Every lane computes and sends (the
+    // receiver selects: only a surviving lane may change its rhs - an eliminated lane's rhs is what its own back
+    // substitution uses); a surviving lane's right neighbour always exists, its left one except for lane 0.
+    PQP_DEV void cr_forward_level(int t, real (&bs)[3]) {
+        const int h = 1 << t;
+        const bool surv = (lane & (2 * h - 1)) == 0;
+        real upd[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const real vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
+            const real vp = crGp[3 * r] * bs[0] + crGp[3 * r + 1] * bs[1] + crGp[3 * r + 2] * bs[2];
+            const real fr = shfl_down(vm, h, lane);
+            real fl = shfl_up(vp, h, lane);
+            if (lane == 0) fl = real(0.0);
+            upd[r] = surv ? (fr + fl) : real(0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) bs[r] -= upd[r];
+    }
+    // back substitution of the lanes eliminated at level t from their two solved neighbours (branch-free: every
+    // lane evaluates, the eliminated ones keep the result)
+    PQP_DEV void cr_backward_level(int t, const real (&ts)[3], real (&xs)[3]) {
+        const int h = 1 << t;
+        const bool elim = (lane & (2 * h - 1)) == h;
+        real xl[3], xr[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            xl[r] = shfl_up(xs[r], h, lane);
+            xr[r] = shfl_down(xs[r], h, lane);
+            if (lane + h > 31) xr[r] = real(0.0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const real v = ts[c] - (crGm[c] * xl[0] + crGm[3 + c] * xl[1] + crGm[6 + c] * xl[2]) -
+                           (crGp[c] * xr[0] + crGp[3 + c] * xr[1] + crGp[6 + c] * xr[2]);
+            xs[c] = elim ? v : xs[c];
+        }
+    }
     // separators (cyclic reduction across lanes) + backward sweep; x~ ends up in GBV
     PQP_DEV void solve_tail(const real (&bk)[3], const real (&acc)[3]) {
         real f[24], fnx[24];
@@ -1023,28 +1063,15 @@ struct QpWarp {
             if (lane == 31) fr = real(0.0);
             bs[r] = bk[r] - fr;
         }
-        // cyclic reduction, forward (rolled: measured +4..10 % wherever more than one warp per
-        // scheduler is resident - smaller hot loop - and neutral at n = 240; profiles/r1/README.md)
-        PQP_CR_UNROLL
-        for (int t = 0; t < 5; ++t) {
-            const int h = 1 << t;
-            const bool elim = (lane & (2 * h - 1)) == h;
-            const bool surv = (lane & (2 * h - 1)) == 0;
-            real upd[3];
+        // cyclic reduction over the 32 separators: 5 forward levels, 3x3 solve, 5 backward levels. Rolled where
+        // several warps share a scheduler (smaller hot loop: +4..10 %, profiles/r1/README.md); unrolled with
+        // constant shuffle distances and lane masks where one warp owns its scheduler (Store::kUnrollCr).
+        if (Store::kUnrollCr) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                real vm = crGm[3 * r] * bs[0] + crGm[3 * r + 1] * bs[1] + crGm[3 * r + 2] * bs[2];
-                real vp = crGp[3 * r] * bs[0] + crGp[3 * r + 1] * bs[1] + crGp[3 * r + 2] * bs[2];
-                vm = elim ? vm : real(0.0);
-                vp = elim ? vp : real(0.0);
-                real fr = shfl_down(vm, h, lane);
-                real fl = shfl_up(vp, h, lane);
-                if (lane + h > 31) fr = real(0.0);
-                if (lane < h) fl = real(0.0);
-                upd[r] = surv ? (fr + fl) : real(0.0);
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) bs[r] -= upd[r];
+            for (int t = 0; t < 5; ++t) cr_forward_level(t, bs);
+        } else {
+            PQP_ROLL
+            for (int t = 0; t < 5; ++t) cr_forward_level(t, bs);
         }
         real ts[3], xs[3];
 #pragma unroll
@@ -1052,24 +1079,12 @@ struct QpWarp {
             ts[r] = crAinv[SI(r, 0)] * bs[0] + crAinv[SI(r, 1)] * bs[1] + crAinv[SI(r, 2)] * bs[2];
             xs[r] = ts[r];
         }
-        // cyclic reduction, backward
-        PQP_CR_UNROLL
-        for (int t = 4; t >= 0; --t) {
-            const int h = 1 << t;
-            const bool elim = (lane & (2 * h - 1)) == h;
-            real xl[3], xr[3];
+        if (Store::kUnrollCr) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                xl[r] = shfl_up(xs[r], h, lane);
-                xr[r] = shfl_down(xs[r], h, lane);
-                if (lane + h > 31) xr[r] = real(0.0);
-            }
-            if (elim) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    xs[c] = ts[c] - (crGm[c] * xl[0] + crGm[3 + c] * xl[1] + crGm[6 + c] * xl[2]) -
-                            (crGp[c] * xr[0] + crGp[3 + c] * xr[1] + crGp[6 + c] * xr[2]);
-            }
+            for (int t = 4; t >= 0; --t) cr_backward_level(t, ts, xs);
+        } else {
+            PQP_ROLL
+            for (int t = 4; t >= 0; --t) cr_backward_level(t, ts, xs);
         }
         // local backward substitution
         real xSL[3], xn[3];
