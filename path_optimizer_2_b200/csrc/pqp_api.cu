@@ -246,6 +246,38 @@ struct TmemStore {
             out[4 * g] = o[0]; out[4 * g + 1] = o[1]; out[4 * g + 2] = o[2]; out[4 * g + 3] = o[3];
         }
     }
+    // the same for the stage AFTER the cursor's (prefetch; the cursor's own stage again when that is the last one)
+    __device__ uint32_t ahead() const {
+        const uint32_t last = tb + (uint32_t)((C - 1) * kGroups * 4);
+        return (cur == last) ? cur : cur + kStride;
+    }
+    template <int N> __device__ void ld4n_nowait_ahead(int g0, int k, float (&out)[4 * N]) const {
+        const uint32_t a = ahead();
+        const int ka = k < C - 1 ? k + 1 : k;
+#pragma unroll
+        for (int g = 0; g < N; ++g) {
+            float o[4];
+            if (spilled(g0 + g)) {
+                const float4 v = *sp(g0 + g, ka);
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            } else {
+                tmem_ld4_nowait(a + (uint32_t)(slot(g0 + g) * 4), o);
+            }
+            out[4 * g] = o[0]; out[4 * g + 1] = o[1]; out[4 * g + 2] = o[2]; out[4 * g + 3] = o[3];
+        }
+    }
+    // group g two stages after the cursor's (clamped to the last stage)
+    __device__ void ld4_nowait_ahead_next(int g, int k, float (&out)[4]) const {
+        if (spilled(g)) {
+            const float4 v = *sp(g, k < C - 2 ? k + 2 : C - 1);
+            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        } else {
+            const uint32_t last = tb + (uint32_t)((C - 1) * kGroups * 4);
+            const uint32_t a1 = ahead();
+            const uint32_t a2 = (a1 == last) ? a1 : a1 + kStride;
+            tmem_ld4_nowait(a2 + (uint32_t)(slot(g) * 4), out);
+        }
+    }
     // group g of the stage AFTER the cursor's (of the cursor's own stage when that is the last one)
     __device__ void ld4_nowait_next(int g, int k, float (&out)[4]) const {
         if (spilled(g)) {

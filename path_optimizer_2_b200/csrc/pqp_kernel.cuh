@@ -313,6 +313,8 @@ struct SmemStore {
     PQP_DEV void st4_cur(int g, int k, const Vec4 &v) { st4(g, k, v); }
     template <int N> PQP_DEV void ld4n_nowait_cur(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k, out); }
     PQP_DEV void ld4_nowait_next(int g, int k, real (&out)[4]) const { ld4n<1>(g, k < C - 1 ? k + 1 : k, out); }
+    template <int N> PQP_DEV void ld4n_nowait_ahead(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k < C - 1 ? k + 1 : k, out); }
+    PQP_DEV void ld4_nowait_ahead_next(int g, int k, real (&out)[4]) const { ld4n<1>(g, k < C - 2 ? k + 2 : C - 1, out); }
 };
 
 // =========================================================================================
@@ -1514,7 +1516,8 @@ struct QpWarp {
 
     template <bool kCheck>
     PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
-                                   real (&wo)[3], real (&bk)[3], const real (&loaded)[44]) {
+                                   real (&wo)[3], real (&bk)[3], const real (&loaded)[44], real (&nloaded)[44],
+                                   real (&ndwv)[4]) {
         const StagePred sp = pred(k);
         StageRO q;
         Vec4 x0, x1, oy, cz;
@@ -1621,6 +1624,9 @@ struct QpWarp {
             Vc(GR5, k) = g5;
             Vc(GS6, k) = g6;
         }
+        // the next stage's load batch is in flight while this stage's rhs part is computed (no wait here)
+        store.ld4_nowait_ahead_next(GBV, k, ndwv);
+        store.template ld4n_nowait_ahead<11>(GA0, k, nloaded);
         local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
 
@@ -1634,17 +1640,18 @@ struct QpWarp {
         if (lane == 31) { dnb[0] = dnb[1] = dnb[2] = real(0.0); }
         if (kCheck) { cert_nrm = real(0.0); cert_lhs = real(0.0); }
         real wprev[3] = {real(0.0), real(0.0), real(0.0)};
+        // one load batch per stage (the next stage's dx and the stage's 11 groups, one wait), issued one stage
+        // ahead: stage k+1's batch is in flight while stage k's rhs part is computed
+        real dwv[4], loaded[44];
+        store.seek(0);
+        store.ld4_nowait_next(GBV, 0, dwv);
+        store.template ld4n_nowait_cur<11>(GA0, 0, loaded);
+        store.wait_ld();
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
             store.seek(k);
             const StagePred sp = pred(k);
-            // one load batch per stage: the next stage's dx and this stage's 11 groups are issued together and
-            // waited for once (three dependent load -> wait round trips per stage before; the tensor-memory
-            // access code held 24 % of the kernel's stall samples, profiles/r2/README.md)
-            real dwv[4], loaded[44];
-            store.ld4_nowait_next(GBV, k, dwv);
-            store.template ld4n_nowait_cur<11>(GA0, k, loaded);
-            store.wait_ld();
+            real ndwv[4], nloaded[44];
             const real dt[3] = {dv.x, dv.y, dv.z};
             real dn[3];
             dn[0] = (k == C - 1) ? dnb[0] : dwv[0];
@@ -1653,7 +1660,7 @@ struct QpWarp {
             Vec4 dw;
             dw.x = dwv[0]; dw.y = dwv[1]; dw.z = dwv[2]; dw.w = dwv[3];
             real wo[3], bk[3];
-            update_stage_incr<kCheck>(k, first, warm, dt, dn, wo, bk, loaded);
+            update_stage_incr<kCheck>(k, first, warm, dt, dn, wo, bk, loaded, nloaded, ndwv);
             Vec4 bv;
             bv.x = bk[0] - ((sp.real && k > 0) ? wprev[0] : real(0.0));
             bv.y = bk[1] - ((sp.real && k > 0) ? wprev[1] : real(0.0));
@@ -1663,6 +1670,11 @@ struct QpWarp {
 #pragma unroll
             for (int r = 0; r < 3; ++r) wprev[r] = wo[r];
             dv = dw;
+            store.wait_ld();
+#pragma unroll
+            for (int j = 0; j < 44; ++j) loaded[j] = nloaded[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dwv[j] = ndwv[j];
         }
         fix_first_stage(wprev);
     }
