@@ -1515,7 +1515,7 @@ struct QpWarp {
     }
 
     template <bool kCheck>
-    PQP_DEV void update_stage_incr(int k, bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
+    PQP_DEV void update_stage_incr(int k, const bool first, bool warm, const real (&dt)[3], const real (&dn)[3],
                                    real (&wo)[3], real (&bk)[3], const real (&loaded)[44], real (&nloaded)[44],
                                    real (&ndwv)[4]) {
         const StagePred sp = pred(k);
@@ -1630,8 +1630,12 @@ struct QpWarp {
         local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
 
-    template <bool kCheck>
-    PQP_DEV void admm_update_incr(bool first, bool warm) {
+    // kMaybeFirst = false: the caller knows this is not the first iteration of a solve, and the stage loop carries
+    // no branch around the z0 code (that taken branch and the refetch behind it were 3.5 % of the kernel's stall
+    // samples, profiles/r2/README.md)
+    template <bool kCheck, bool kMaybeFirst>
+    PQP_DEV void admm_update_incr(bool first_arg, bool warm) {
+        const bool first = kMaybeFirst && first_arg;
         Vec4 dv = V(GBV, 0);
         real dnb[3];
         dnb[0] = shfl_down(dv.x, 1, lane);
@@ -1997,8 +2001,9 @@ struct QpWarp {
             if (to_check <= 0) to_check = P.check_every > 0 ? P.check_every : -1;
             if (to_adapt <= 0) to_adapt = (P.adaptive_rho && P.adaptive_interval > 0) ? P.adaptive_interval : -1;
             if (Incr) {
-                if (can_check) admm_update_incr<true>(iter == 1, warm);
-                else admm_update_incr<false>(iter == 1, warm);
+                if (can_check) admm_update_incr<true, true>(iter == 1, warm);
+                else if (iter == 1) admm_update_incr<false, true>(true, warm);
+                else admm_update_incr<false, false>(false, warm);
             } else {
                 if (can_check) admm_update<true>(iter == 1, warm);
                 else admm_update<false>(iter == 1, warm);
