@@ -430,6 +430,11 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
+def sv_uses_tmem(n, batch):
+    """The library's storage policy: tensor memory for n_max >= 128, and for 64..127 up to 4096 instances."""
+    return n >= 128 or (n >= 64 and batch <= 4096)
+
+
 def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, world, dev, gather=True, clocks=False,
                  inflight=1):
     """Cold solves of this rank's batch `hb`: device-resident value, end-to-end value, kernel time.
@@ -965,7 +970,9 @@ def main():
                 "admm_step": ("increment form (dx solve, carried row values)"
                               if (args.option_bits & 32) or (not (args.option_bits & (64 | 2)) and n >= 64)
                               else "textbook form"),
-                "state_storage": "tensor memory (tcgen05.ld/st), persistent CTAs" if info["smem_per_warp"] < 72 * 128 else "shared memory",
+                "state_storage": ("tensor memory (tcgen05.ld/st) for the iterates and read-only stage data + %d KB of shared memory per warp "
+                                  "for the factor and weight groups, persistent CTAs" % (info["smem_per_warp"] // 1024))
+                                 if sv_uses_tmem(n, B) else "shared memory",
             },
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],

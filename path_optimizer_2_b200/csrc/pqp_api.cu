@@ -154,16 +154,23 @@ struct TmemStore {
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
     static constexpr bool kUnrollCr = COLS == 512;                     // one warp per scheduler (see cr_forward_level)
     static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8 (512 columns) and at C = 4 with 256 columns, 10 at C = 16, else 0
+    // Which groups leave tensor memory first when the warp's columns do not hold all 18.
+    // C <= 8 (two groups leave): the clearance / proximal weights GR5, GS6 (least frequently read), then the other
+    // read-only groups (4, 3, 2, 1, 0), then the factor from its end (17 .. 12), the read-write groups last.
+    // C = 16 (ten groups leave): the factor first (17 .. 12), then GR5, GS6, then 4, 3, .. (measured +2.6 % at
+    // n = 400). Sending the factor to shared memory at C = 8 as well - tensor memory is read at 64 B per cycle,
+    // shared memory at 128 B, and the sweeps' factor reads are half of all loads - measured -1.7 %
+    // (profiles/r2/README.md): four warps share the one shared-memory port.
+    static constexpr bool kFactorFirst = C >= 16;
     uint32_t tb;  // TMEM address of this warp's lane block (lane base in bits 31:16)
     uint32_t cur;  // stage cursor: tb + k * (columns per stage) of the stage a hot loop is at (see seek)
     float *sm;    // spill area (shared memory) of this warp: [spill slot][k][lane] float4
     int lane;
     __device__ TmemStore(uint32_t t, float *s, int l) : tb(t), cur(t), sm(s), lane(l) {}
-    // Which groups leave tensor memory first when the warp's columns do not hold all 18: the
-    // clearance / proximal weights GR5, GS6 (least frequently read), then the other read-only groups
-    // (4, 3, 2, 1, 0), then the factor from its end (17 .. 12), the read-write groups last.
     __host__ __device__ static constexpr int spill_rank(int g) {
-        return g == pqp::GR5 ? 0 : g == pqp::GS6 ? 1 : g <= 4 ? 6 - g : g >= pqp::GF0 ? 7 + (17 - g) : 13 + (11 - g);
+        return kFactorFirst
+                   ? (g >= pqp::GF0 ? 17 - g : g == pqp::GR5 ? 6 : g == pqp::GS6 ? 7 : g <= 4 ? 8 + (4 - g) : 13 + (11 - g))
+                   : (g == pqp::GR5 ? 0 : g == pqp::GS6 ? 1 : g <= 4 ? 6 - g : g >= pqp::GF0 ? 7 + (17 - g) : 13 + (11 - g));
     }
     __host__ __device__ static constexpr bool spilled(int g) { return spill_rank(g) < kSpill; }
     // number of spilled groups with an index below g, in closed form (no loops: g reaches these helpers as a
@@ -171,10 +178,15 @@ struct TmemStore {
     __host__ __device__ static constexpr int imax(int a, int b) { return a > b ? a : b; }
     __host__ __device__ static constexpr int imin(int a, int b) { return a < b ? a : b; }
     __host__ __device__ static constexpr int spilled_below(int g) {
-        return ((kSpill > 0 && g > pqp::GR5) ? 1 : 0) + ((kSpill > 1 && g > pqp::GS6) ? 1 : 0) +
-               imax(0, imin(g, 5) - imax(0, 7 - kSpill)) +           // read-only groups 4, 3, .. leave from the top
-               imax(0, imin(g, 12) - imax(7, 25 - kSpill)) +         // read-write groups 11 .. 7 (last to leave)
-               imax(0, imin(g, 18) - imax(12, 25 - kSpill));         // factor groups 17 .. 12
+        return kFactorFirst
+                   ? ((kSpill > 6 && g > pqp::GR5) ? 1 : 0) + ((kSpill > 7 && g > pqp::GS6) ? 1 : 0) +
+                         imax(0, imin(g, 5) - imax(0, 13 - kSpill)) +    // read-only groups 4, 3, .. leave from the top
+                         imax(0, imin(g, 12) - imax(7, 25 - kSpill)) +   // read-write groups 11 .. 7 (last to leave)
+                         imax(0, imin(g, 18) - imax(12, 18 - kSpill))    // factor groups 17 .. 12 (first to leave)
+                   : ((kSpill > 0 && g > pqp::GR5) ? 1 : 0) + ((kSpill > 1 && g > pqp::GS6) ? 1 : 0) +
+                         imax(0, imin(g, 5) - imax(0, 7 - kSpill)) +     // read-only groups 4, 3, .. leave from the top
+                         imax(0, imin(g, 12) - imax(7, 25 - kSpill)) +   // read-write groups 11 .. 7 (last to leave)
+                         imax(0, imin(g, 18) - imax(12, 25 - kSpill));   // factor groups 17 .. 12
     }
     __host__ __device__ static constexpr int slot(int g) { return g - spilled_below(g); }
     __host__ __device__ static constexpr int spslot(int g) { return spilled_below(g); }
