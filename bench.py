@@ -431,8 +431,8 @@ def barrier(world):
 
 
 def sv_uses_tmem(n, batch):
-    """The library's storage policy: tensor memory for n_max >= 128, and for 64..127 up to 4096 instances."""
-    return n >= 128 or (n >= 64 and batch <= 4096)
+    """The library's storage policy: tensor memory for n_max >= 64."""
+    return n >= 64
 
 
 def measure_cold(args, hb, option_bits, steps, warmup, e2e_steps, local_rank, world, dev, gather=True, clocks=False,
@@ -847,8 +847,10 @@ def secondary(args, rank, local_rank, world, dev, hb_primary):
         a1.workload, a1.batch, a1.n = "sharedmap", 1024, 120
         hb1, wl1, ex1 = make_workload(a1, 1024, 0, device=local_rank)
         lines1, dmap1 = ex1.pop("_lines"), ex1.pop("_dmap")
-        r1 = measure_cold(a1, hb1, args.option_bits, min(args.steps, 10), 3, 5, local_rank, world, dev, gather=False)
+        r1 = measure_cold(a1, hb1, args.option_bits, min(args.steps, 10), 3, 6, local_rank, world, dev, gather=False,
+                          inflight=args.inflight)
         sec["configs[1]"] = {"workload": wl1, "value": r1["value"], "unit": UNIT, "e2e": r1["e2e_value"],
+                             "batches_in_flight": r1["inflight"],
                              "ms_per_step": r1["ms_per_step"], "kernel_ms": r1["kernel_ms"],
                              "mean_admm_iters": float(np.mean(r1["iters"])),
                              "solved_fraction": float(np.mean(r1["status"] == abi.PQP_SOLVED)),

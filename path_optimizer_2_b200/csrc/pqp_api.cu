@@ -146,13 +146,17 @@ __device__ __forceinline__ void tmem_st4(uint32_t a, const float4 &v) {
                  : "memory");
 }
 
+// where the cyclic-reduction levels are unrolled (see cr_forward_level); overridable for A/B builds
+#ifndef PQP_UNROLL_CR_COND
+#define PQP_UNROLL_CR_COND true
+#endif
 template <int C, int COLS = 512>
 struct TmemStore {
     typedef float4 Vec4;
     static constexpr int kAll = pqp::NFIELD / 4;                       // 18 groups
     static constexpr int kFit = COLS / (4 * C);                        // groups that fit in this warp's columns
     static constexpr int kGroups = kFit < kAll ? kFit : kAll;          // groups kept in TMEM
-    static constexpr bool kUnrollCr = COLS == 512;                     // one warp per scheduler (see cr_forward_level)
+    static constexpr bool kUnrollCr = PQP_UNROLL_CR_COND;              // see cr_forward_level
     static constexpr int kSpill = kAll - kGroups;                      // 2 at C = 8 (512 columns) and at C = 4 with 256 columns, 10 at C = 16, else 0
     // Which groups leave tensor memory first when the warp's columns do not hold all 18.
     // C <= 8 (two groups leave): the clearance / proximal weights GR5, GS6 (least frequently read), then the other
@@ -1130,13 +1134,11 @@ int pqp_create(const pqp_params *params, int32_t n_max, int32_t batch_max, int32
     h->fp64 = (params->reserved & 2) != 0;
     h->escalate = (params->reserved & 4) == 0;
     h->cold_only = (params->reserved & 128) != 0;
-    // storage policy of the FP32 kernel: tensor memory where shared memory limits residency to
-    // 3 QPs per SM (n_max >= 128: 819 k vs 628 k solves/s at n = 240), shared memory otherwise
-    // (1.5x better at n = 60). At 64 <= n_max <= 127 tensor memory holds 8 QPs per SM against 6:
-    // one wave instead of two for batches around 1024 (1.09 M vs 0.91 M solves/s at B = 1024,
-    // 1.37 vs 1.29 at 2048, 1.48 vs 1.52 at 8192), so it is chosen for handles of <= 4096
-    // instances. Bits 8 / 16 force one or the other.
-    const bool auto_tmem = h->chunk >= 8 || (h->chunk == 4 && batch_max <= 4096);
+    // storage policy of the FP32 kernel (measured, profiles/r2/policy_ab.log): tensor memory for n_max >= 64
+    // (chunks of 4, 8, 16 stages per lane: 8 / 4 / 2 QPs per SM; at n = 240 shared memory would hold 3 per SM, at
+    // n = 120 it holds 6 but runs 3.48 ms against 3.21 ms per 8192 instances, at 1024 instances 0.92 vs 0.76 ms),
+    // shared memory below (n = 60: 1.59 vs 1.82 ms). Bits 8 / 16 force one or the other.
+    const bool auto_tmem = h->chunk >= 4;
     h->use_tmem = !h->fp64 && ((params->reserved & 8) != 0 || (auto_tmem && (params->reserved & 16) == 0));
     // form of the ADMM step (FP32 kernels): the increment form (dx solve, row values A x carried and
     // advanced by alpha A dx) follows the FP64 oracle's rho schedule - same iteration count in ~99-100 %

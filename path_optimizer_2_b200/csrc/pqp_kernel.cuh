@@ -290,7 +290,10 @@ struct SmemStore {
     typedef typename Vec4T<real>::type Vec4;
     real *sm;
     int lane;
-    static constexpr bool kUnrollCr = false;  // several warps per scheduler: keep the hot loop small
+    // cyclic-reduction levels unrolled? Under this policy several warps share a scheduler and the hot loop should
+    // stay small: measured +5 % / +7.5 % at C = 2 / 1 (n = 60 / 30), -5.5 % at C = 4 (n = 120), -4 % in FP64
+    // (profiles/r2/cr_unroll_smem_ab.log)
+    static constexpr bool kUnrollCr = C <= 2 && sizeof(real) == 4;
     PQP_DEV SmemStore(real *s, int l) : sm(s), lane(l) {}
     PQP_DEV real ld(int f, int k) const { return sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)]; }
     PQP_DEV void st(int f, int k, real v) { sm[(((f >> 2) * C + k) * 32 + lane) * 4 + (f & 3)] = v; }
@@ -1065,9 +1068,9 @@ struct QpWarp {
             if (lane == 31) fr = real(0.0);
             bs[r] = bk[r] - fr;
         }
-        // cyclic reduction over the 32 separators: 5 forward levels, 3x3 solve, 5 backward levels. Rolled where
-        // several warps share a scheduler (smaller hot loop: +4..10 %, profiles/r1/README.md); unrolled with
-        // constant shuffle distances and lane masks where one warp owns its scheduler (Store::kUnrollCr).
+        // cyclic reduction over the 32 separators: 5 forward levels, 3x3 solve, 5 backward levels; unrolled with
+        // constant shuffle distances and lane masks under the tensor-memory policy (Store::kUnrollCr; at C = 4 with
+        // two warps per scheduler: +8..21 % on 1024-instance batches, profiles/r2/cr_unroll_c4_ab.log)
         if (Store::kUnrollCr) {
 #pragma unroll
             for (int t = 0; t < 5; ++t) cr_forward_level(t, bs);
