@@ -430,6 +430,31 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank's host threads on the CPUs of the GPU's NUMA node, so that the pinned
+    host buffers it allocates (local allocation policy) sit behind the memory controllers next to its PCIe root.
+    Eight ranks move 8 x 205 MB of host memory per 5.7 ms step end to end; from one socket's memory that stops at
+    ~170 GB/s (profiles/r2/scale_r2_builder.txt). Returns the node, or None when the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 - no sysfs / no permission: keep the default placement
+        return None
+
+
 def sv_uses_tmem(n, batch):
     """The library's storage policy: tensor memory for n_max >= 64."""
     return n >= 64
@@ -917,6 +942,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -978,7 +1004,7 @@ def main():
             },
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "steps": r["e2e_steps"], "batches_in_flight": r["inflight"],
+                    "steps": r["e2e_steps"], "batches_in_flight": r["inflight"], "host_numa_node": numa,
                     "how": "every step = one synchronous pqp_solve of the whole batch, pinned host inputs -> pinned host "
                            "results; %d handle(s), one host thread per handle" % r["inflight"]},
             "gpu_launches": r["launches"],
