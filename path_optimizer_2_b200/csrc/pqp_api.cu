@@ -323,6 +323,24 @@ struct TmemStore {
 };
 
 
+// compile-time check of the closed-form spill map against its definition (rank order) for every store in use
+template <class Store> constexpr bool spill_map_consistent() {
+    int seen = 0;
+    for (int g = 0; g <= Store::kAll; ++g) {
+        if (Store::spilled_below(g) != seen) return false;
+        if (g < Store::kAll && Store::spilled(g)) ++seen;
+    }
+    if (seen != Store::kSpill) return false;
+    for (int a = 0; a < Store::kAll; ++a)  // the ranks are a permutation of 0 .. 17
+        for (int b = a + 1; b < Store::kAll; ++b)
+            if (Store::spill_rank(a) == Store::spill_rank(b)) return false;
+    return true;
+}
+static_assert(spill_map_consistent<TmemStore<1, 512>>() && spill_map_consistent<TmemStore<2, 512>>() &&
+                  spill_map_consistent<TmemStore<4, 256>>() && spill_map_consistent<TmemStore<8, 512>>() &&
+                  spill_map_consistent<TmemStore<16, 512>>(),
+              "TmemStore::spilled_below does not match spill_rank");
+
 // Tensor-memory persistent kernel (FP32): one CTA per SM with WT warps (4, or 8 when two warps
 // can share a TMEM sub-partition: 256 columns each); every warp solves one QP at a time and takes
 // the next unsolved instance from a global work counter (iteration counts vary 3x between
