@@ -998,8 +998,8 @@ def main():
                 "admm_step": ("increment form (dx solve, carried row values)"
                               if (args.option_bits & 32) or (not (args.option_bits & (64 | 2)) and n >= 64)
                               else "textbook form"),
-                "state_storage": ("tensor memory (tcgen05.ld/st) for the iterates and read-only stage data + %d KB of shared memory per warp "
-                                  "for the factor and weight groups, persistent CTAs" % (info["smem_per_warp"] // 1024))
+                "state_storage": ("tensor memory (tcgen05.ld/st), persistent CTAs; %d KB of shared memory per warp for the groups "
+                                  "that do not fit the warp's columns" % (info["smem_per_warp"] // 1024))
                                  if sv_uses_tmem(n, B) else "shared memory",
             },
             "clocks": r["clocks"],
