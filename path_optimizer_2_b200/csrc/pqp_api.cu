@@ -140,6 +140,35 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t a, float (&o)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a) : "memory");
     o[0] = __uint_as_float(r0); o[1] = __uint_as_float(r1); o[2] = __uint_as_float(r2); o[3] = __uint_as_float(r3);
 }
+__device__ __forceinline__ void tmem_ldx8_nowait(uint32_t a, float *o) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldx16_nowait(uint32_t a, float *o) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(a) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldx32_nowait(uint32_t a, float *o) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+}
+// G consecutive float4 groups (G = 1, 2, 4, 8) starting at column address a, in ONE tcgen05.ld
+template <int G> __device__ __forceinline__ void tmem_ldg_nowait(uint32_t a, float *o) {
+    if (G == 8) tmem_ldx32_nowait(a, o);
+    else if (G == 4) tmem_ldx16_nowait(a, o);
+    else if (G == 2) tmem_ldx8_nowait(a, o);
+    else {
+        float t[4];
+        tmem_ld4_nowait(a, t);
+        o[0] = t[0]; o[1] = t[1]; o[2] = t[2]; o[3] = t[3];
+    }
+}
 __device__ __forceinline__ void tmem_st4(uint32_t a, const float4 &v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(__float_as_uint(v.x)),
                  "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
@@ -207,6 +236,29 @@ struct TmemStore {
         tmem_st1(col(g, k) + (f & 3), v);
         tmem_wait_st();
     }
+    // Groups g0 .. g0+N-1 of one stage: groups kept in tensor memory sit in consecutive columns (slot(g) counts
+    // the unspilled groups below g), so a run of 2 / 4 / 8 of them is ONE tcgen05.ld.x8 / x16 / x32 instead of one
+    // .x4 per group. run_at(g, end): length of the longest such run starting at g.
+    __host__ __device__ static constexpr int run_at(int g, int end) {
+        int n = 0;
+        while (g + n < end && !spilled(g + n)) ++n;
+        return n >= 8 ? 8 : n >= 4 ? 4 : n >= 2 ? 2 : n;
+    }
+    template <int G0, int N, int I> struct Loader {
+        static constexpr int kRun = I < N ? (spilled(G0 + I) ? 0 : run_at(G0 + I, G0 + N)) : 0;
+        static constexpr int kStep = kRun > 0 ? kRun : 1;
+        // base: column address of the stage block; k: stage index for the spilled groups
+        __device__ static void go(const TmemStore &st, uint32_t base, int k, float *out) {
+            if (I >= N) return;
+            if (kRun == 0) {
+                const float4 v = *st.sp(G0 + I, k);
+                out[4 * I] = v.x; out[4 * I + 1] = v.y; out[4 * I + 2] = v.z; out[4 * I + 3] = v.w;
+            } else {
+                tmem_ldg_nowait<(kRun > 0 ? kRun : 1)>(base + (uint32_t)(slot(G0 + I) * 4), out + 4 * I);
+            }
+            Loader<G0, N, (I + kStep < N ? I + kStep : N)>::go(st, base, k, out);
+        }
+    };
     __device__ float4 ld4(int g, int k) const {
         if (spilled(g)) return *sp(g, k);
         float o[4];
@@ -233,6 +285,16 @@ struct TmemStore {
         }
     }
     __device__ void wait_ld() const { tmem_wait_ld(); }
+    // compile-time group range: runs of consecutive tensor-memory groups become one wide load (see Loader)
+    template <int G0, int N> __device__ void ld_run_nowait(int k, float (&out)[4 * N]) const {
+        Loader<G0, N, 0>::go(*this, tb + (uint32_t)(k * kGroups * 4), k, out);
+    }
+    template <int G0, int N> __device__ void ld_run_nowait_cur(int k, float (&out)[4 * N]) const {
+        Loader<G0, N, 0>::go(*this, cur, k, out);
+    }
+    template <int G0, int N> __device__ void ld_run_nowait_ahead(int k, float (&out)[4 * N]) const {
+        Loader<G0, N, 0>::go(*this, ahead(), k < C - 1 ? k + 1 : k, out);
+    }
     // Stage cursor. tcgen05.ld/st take their address from a UNIFORM register; an address computed from a loop
     // counter that ptxas keeps in a vector register costs one R2UR per access (5.7 % of the kernel's executed
     // instructions before this, profiles/r2/README.md). seek(k) produces the stage's column base in a uniform

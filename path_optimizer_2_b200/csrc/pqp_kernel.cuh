@@ -313,6 +313,9 @@ struct SmemStore {
     PQP_DEV void fence() {}  // stores of this lane are visible to its later loads
     // stage cursor (see TmemStore): plain stage indexing under this policy
     PQP_DEV void seek(int) {}
+    template <int G0, int N> PQP_DEV void ld_run_nowait(int k, real (&out)[4 * N]) const { ld4n<N>(G0, k, out); }
+    template <int G0, int N> PQP_DEV void ld_run_nowait_cur(int k, real (&out)[4 * N]) const { ld4n<N>(G0, k, out); }
+    template <int G0, int N> PQP_DEV void ld_run_nowait_ahead(int k, real (&out)[4 * N]) const { ld4n<N>(G0, k < C - 1 ? k + 1 : k, out); }
     PQP_DEV void st4_cur(int g, int k, const Vec4 &v) { st4(g, k, v); }
     template <int N> PQP_DEV void ld4n_nowait_cur(int g0, int k, real (&out)[4 * N]) const { ld4n<N>(g0, k, out); }
     PQP_DEV void ld4_nowait_next(int g, int k, real (&out)[4]) const { ld4n<1>(g, k < C - 1 ? k + 1 : k, out); }
@@ -966,10 +969,10 @@ struct QpWarp {
     // issues the loads only: the caller waits once (store.wait_ld) for this and whatever else it issued
     PQP_DEV void load_factor(int k, real (&f)[24], bool with_dinv) {
         if (with_dinv) {
-            store.template ld4n_nowait<6>(GF0, k, f);
+            store.template ld_run_nowait<GF0, 6>(k, f);
         } else {
             real t[20];
-            store.template ld4n_nowait<5>(GF0 + 1, k, t);
+            store.template ld_run_nowait<GF0 + 1, 5>(k, t);
 #pragma unroll
             for (int j = 0; j < 20; ++j) f[4 + j] = t[j];
         }
@@ -1629,7 +1632,7 @@ struct QpWarp {
         }
         // the next stage's load batch is in flight while this stage's rhs part is computed (no wait here)
         store.ld4_nowait_ahead_next(GBV, k, ndwv);
-        store.template ld4n_nowait_ahead<11>(GA0, k, nloaded);
+        store.template ld_run_nowait_ahead<GA0, 11>(k, nloaded);
         local_rhs_incr(q, sp, x, wo, wk, wc, bk);
     }
 
@@ -1652,7 +1655,7 @@ struct QpWarp {
         real dwv[4], loaded[44];
         store.seek(0);
         store.ld4_nowait_next(GBV, 0, dwv);
-        store.template ld4n_nowait_cur<11>(GA0, 0, loaded);
+        store.template ld_run_nowait_cur<GA0, 11>(0, loaded);
         store.wait_ld();
         PQP_UPDATE_UNROLL
         for (int k = 0; k < C; ++k) {
