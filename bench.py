@@ -197,6 +197,22 @@ def measured_traffic(n, instances, cold_only):
         return None
 
 
+def measured_issue(n, cold_only):
+    """What actually bounds the kernel, from the same capture: warp instructions per launch and the share of cycles
+    in which a scheduler issued (one warp per scheduler: the kernel is latency / issue bound, not HBM bound)."""
+    name = "traffic_cold_n%d%s.json" % (n, "_coldonly" if cold_only else "")
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", name)) as f:
+            r = json.load(f)
+        if r.get("issue_active_pct") is None:
+            return None
+        return {"warp_instructions_per_launch": r["warp_instructions"], "issue_active_pct": r["issue_active_pct"],
+                "registers_per_thread": r.get("registers_per_thread"), "batch": r["batch"],
+                "source": "ncu --set full capture of this round (profiles/r2/%s)" % name}
+    except Exception:
+        return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -1012,6 +1028,7 @@ def main():
                          "frac": achieved / peak, "traffic": measured_traffic(n, B, cold_only), "peak_source": peak_src,
                          "kernel": "pqp_admm_kernel_tmem", "kernel_ms": r["kernel_ms"],
                          "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "issue": measured_issue(n, cold_only),
                          "note": "per-iteration state is on-chip (tensor memory / shared memory); the path is "
                                  "latency/issue bound, not HBM bound (see DESIGN.md)"},
         }

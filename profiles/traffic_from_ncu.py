@@ -26,6 +26,9 @@ rec = {"kernel": vals[col["Kernel Name"]] if "Kernel Name" in col else "pqp_admm
        "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
        "dram_bytes_per_instance": (rd + wr) / batch, "algorithmic_bytes_per_instance": 104 * n + 56,
        "gpu_time_ms": get("gpu__time_duration.sum") / 1e6 if units[col["gpu__time_duration.sum"]].lower() in ("ns", "nsecond") else get("gpu__time_duration.sum"),
+       "warp_instructions": get("smsp__inst_executed.sum") if "smsp__inst_executed.sum" in col else None,
+       "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active") if "smsp__issue_active.avg.pct_of_peak_sustained_active" in col else None,
+       "registers_per_thread": get("launch__registers_per_thread") if "launch__registers_per_thread" in col else None,
        "note": note, "source": "ncu --set full --clock-control none (profiles/capture_r2.sh), report " + rep.split("/")[-1]}
 with open(out, "w") as f:
     json.dump(rec, f, indent=1)
