@@ -43,3 +43,13 @@ def test_b200_arm_refuses_to_run_without_a_device():
         pass
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, cwd=ROOT)
     assert p.returncode != 0 and "no CPU path" in (p.stderr + p.stdout)
+
+
+def test_numa_binding_is_a_no_op_without_a_device():
+    """bench.py binds each rank to its GPU's NUMA node when N > 1; without a device (or without sysfs topology) it
+    must leave the process where it is and report None."""
+    import os
+    import bench
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before

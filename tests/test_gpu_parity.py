@@ -368,3 +368,37 @@ def test_stage_times_of_a_single_path_call(solver_mod):
     assert abs(ms["h2d"] + ms["kernel"] + ms["d2h"] - ms["total"]) < 0.05 * ms["total"] + 1e-3
     sv.close()
 
+
+
+def test_two_handles_driven_by_two_host_threads(solver_mod):
+    """A handle is single-threaded, handles are independent: two host threads that each drive their own handle
+    through the synchronous host-pointer call (how bench.py keeps two batches in flight end to end) get the
+    answers of a lone call, bit for bit, whatever the interleaving of their launches and copies."""
+    import threading
+    params = abi.default_params(reserved=128)
+    hb = synthetic.make_batch(3, 1500, 240)   # > 592 resident warps: the two persistent launches really share the SMs
+    ref_sv = solver_mod.PathQpSolver(params, n_max=hb.n_max, batch_max=hb.batch)
+    ref = ref_sv.solve(hb)
+    ref_sv.close()
+    svs = [solver_mod.PathQpSolver(params, n_max=hb.n_max, batch_max=hb.batch) for _ in range(2)]
+    outs, errs = [[], []], []
+
+    def worker(k):
+        try:
+            for _ in range(4):
+                outs[k].append(svs[k].solve(hb))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for k in range(2):
+        assert len(outs[k]) == 4
+        for r in outs[k]:
+            assert np.array_equal(r.status, ref.status) and np.array_equal(r.iters, ref.iters)
+            assert np.array_equal(r.sol, ref.sol) and np.array_equal(r.cost, ref.cost)
+        svs[k].close()
