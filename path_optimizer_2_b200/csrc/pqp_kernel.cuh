@@ -324,23 +324,22 @@ struct SmemStore {
 };
 
 // =========================================================================================
-// All per-stage loops are deliberately NOT unrolled (#pragma unroll 1): the first version of
-// this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction
-// cache (40 % no_inst stalls in profiles/r1/ncu_v1_unrolled_summary.txt).
+// Which loops are unrolled is a measured choice (profiles/r1, profiles/r2 README):
+//  * per-stage loops with large bodies (stage update, residuals, set-up) stay rolled (#pragma unroll 1): the first
+//    version of this kernel unrolled them, which produced a 45 KB hot loop that thrashed the instruction cache (40 %
+//    no_inst stalls, profiles/r1/ncu_v1_unrolled_summary.txt); the rolled stage-update loop fits the 6 KB L0;
+//  * the substitution sweeps are fully unrolled: rolled, half of their instructions were register copies of the
+//    prefetched factor and address conversions (profiles/r2/README.md);
+//  * the cyclic-reduction levels are unrolled per storage policy (Store::kUnrollCr).
 #define PQP_ROLL _Pragma("unroll 1")
 #define PQP_SWEEP_UNROLL _Pragma("unroll")
-#ifndef PQP_UPDATE_UNROLL
 #define PQP_UPDATE_UNROLL _Pragma("unroll 1")
-#endif
 // QpWarp's last template argument selects the ADMM step in increment form (solve
 // K dx = -(r_dual + A'R r_prim), x~ = x + dx, with l carried as l + l_lo) instead of the textbook
 // form (solve K x~ = S x + A'(R z - y)): algebraically the same iteration, but its rounding error
 // scales with |dx| instead of |x|, so the FP32 kernel follows the FP64 oracle's rho schedule
 // (same iteration count in 98-99 % of instances instead of 85 %, ~6 % fewer iterations) at ~8 % more
 // instructions per iteration (profiles/r1/README.md).
-#ifndef PQP_CR_UNROLL
-#define PQP_CR_UNROLL _Pragma("unroll 1")
-#endif
 
 template <int C, typename real, typename Store = SmemStore<C, real>, bool Incr = false>
 struct QpWarp {
